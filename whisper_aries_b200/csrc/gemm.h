@@ -1,0 +1,39 @@
+// Host-side interface of the tcgen05 GEMM (gemm_sm100.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+namespace aries {
+
+enum GemmEpilogue {
+    EPI_BIAS_BF16 = 0,          // out bf16 = acc + bias                       (QKV projection)
+    EPI_BIAS_GELU_BF16 = 1,     // out bf16 = gelu_erf(acc + bias)             (MLP fc1, conv1)
+    EPI_BIAS_RESID_F32 = 2,     // out f32  = acc + bias + resid               (attention out-proj, MLP fc2)
+    EPI_BIAS_GELU_POS_F32 = 3,  // out f32  = gelu_erf(acc + bias) + pos[t]    (conv2 + positional table)
+};
+
+struct GemmParams {
+    int M, N, K;        // GEMM rows (incl. rows the remap drops), columns, depth (K % 64 == 0)
+    int a_cols;         // inner extent of A's tensor map: K index kk reads (row + kk / a_cols, col kk % a_cols)
+    int p_in;           // row r -> b = r / p_in, t = r % p_in
+    int t_valid;        // row is written only when t < t_valid
+    int p_out;          // output row = b * p_out + t + row_off
+    int row_off;
+    int ldo;            // leading dimension of out / resid (elements)
+    const float* bias;  // [N]
+    const float* resid; // f32, indexed like out (EPI_BIAS_RESID_F32; may alias out)
+    const float* pos;   // f32 [t_valid, N] (EPI_BIAS_GELU_POS_F32)
+    void* out;
+};
+
+int gemm_block_n(int N);
+cudaError_t gemm_init_device();
+cudaError_t gemm_launch(int epi, const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const GemmParams& p,
+                        int sm_count, cudaStream_t stream);
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency).
+// bf16 tensor, dims/strides innermost first; strides[0] is implied (2 bytes); 128-byte swizzle.
+cudaError_t make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const unsigned long long* dims,
+                           const unsigned long long* strides_bytes, const unsigned* box);
+
+}  // namespace aries

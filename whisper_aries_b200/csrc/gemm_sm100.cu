@@ -1,0 +1,268 @@
+// Persistent, warp-specialised bf16 GEMM for sm_100a: TMA -> smem ring -> tcgen05.mma -> TMEM -> fused epilogue.
+//
+//   C[M,N] = A[M,K] * B[N,K]^T  (A, B bf16 K-major; f32 accumulate in TMEM)
+//
+// One CTA per SM loops over 128 x BN output tiles (n fastest so the weight matrix stays L2-resident while an
+// A panel is swept).  Roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warps 2..9 =
+// epilogue (two warps per TMEM lane quarter, each owning half of the tile's columns).  The accumulator is
+// double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the main loop of tile i+1.
+//
+// The A operand's K index may wrap onto following rows ("a_cols" < K): that is how the encoder's two Conv1d
+// layers (k=3) run as implicit GEMMs over a zero-padded time-major activation without materialising im2col
+// (CT2 ref: layers::WhisperEncoder conv1/conv2).  Epilogues fuse bias, exact-erf GELU,
+// the residual add and the positional-embedding add and remap GEMM rows to output
+// rows so padded rows are never written.
+#include "gemm.h"
+#include "ptx.cuh"
+
+namespace aries {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;                       // 64 bf16 = 128 B = one SWIZZLE_128B atom row
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + kEpiWarps * 32;
+
+template <int BN>
+struct Cfg {
+    static constexpr int kStages = (BN == 256) ? 4 : 6;
+    static constexpr int kABytes = BM * BK * 2;
+    static constexpr int kBBytes = BN * BK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kBarBytes = 256;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;   // +1024: manual 1 KB alignment
+    static constexpr uint32_t kTmemCols = 2 * BN;
+};
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  const GemmParams p) {
+    using C = Cfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+    uint64_t* empty_bar = full_bar + C::kStages;
+    uint64_t* tfull_bar = empty_bar + C::kStages;      // [2] accumulator ready
+    uint64_t* tempty_bar = tfull_bar + 2;              // [2] accumulator drained
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    const int num_m = (p.M + BM - 1) / BM;
+    const int num_n = p.N / BN;
+    const int num_tiles = num_m * num_n;
+    const int num_kb = p.K / BK;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_b);
+        for (int s = 0; s < C::kStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tfull_bar[s], 1);
+            mbar_init(&tempty_bar[s], kEpiWarps);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<C::kTmemCols>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ------------------------------------------------------------ TMA producer
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = (tile / num_n) * BM;
+                const int n0 = (tile % num_n) * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * C::kStageBytes;
+                    uint8_t* sb = sa + C::kABytes;
+                    mbar_expect_tx(&full_bar[stage], C::kStageBytes);
+                    const int kk = kb * BK;
+                    const int roff = kk / p.a_cols;
+                    tma_load_2d(sa, &tmap_a, &full_bar[stage], kk - roff * p.a_cols, m0 + roff);
+                    tma_load_2d(sb, &tmap_b, &full_bar[stage], kk, n0);
+                    if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ------------------------------------------------------------ MMA issuer
+            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, false, false);
+            constexpr uint64_t desc_hi = umma_smem_desc_hi(16, 1024);   // K-major SW128: SBO = 8 rows * 128 B
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int as = it & 1;
+                const uint32_t aphase = (it >> 1) & 1;
+                mbar_wait(&tempty_bar[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = base + stage * C::kStageBytes;
+                    const uint32_t sb = sa + C::kABytes;
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        umma_bf16_ss(d_tmem, umma_smem_desc(sa + k * 32, desc_hi), umma_smem_desc(sb + k * 32, desc_hi),
+                                     idesc, (kb | k) != 0);
+                    }
+                    umma_commit(&empty_bar[stage]);          // frees the smem slot once these MMAs retire
+                    if (kb == num_kb - 1) umma_commit(&tfull_bar[as]);
+                    if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        // ---------------------------------------------------------------- epilogue warps
+        const int ew = warp - 2;
+        const int quarter = warp & 3;          // TMEM lane quarter this warp may touch
+        const int half = ew >> 2;              // which half of the tile's columns
+        constexpr int kChunks = (BN / 2) / 32;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            const int m0 = (tile / num_n) * BM;
+            const int n0 = (tile % num_n) * BN + half * (BN / 2);
+            const int r = m0 + quarter * 32 + lane;
+            const int b = r / p.p_in;
+            const int t = r - b * p.p_in;
+            const bool valid = (r < p.M) && (t < p.t_valid);
+            const long long orow = (long long)b * p.p_out + t + p.row_off;
+
+            mbar_wait(&tfull_bar[as], aphase);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < kChunks; ++c) {
+                uint32_t acc[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN + half * (BN / 2) + c * 32;
+                tmem_ld_32x32b_x32(taddr, acc);
+                tmem_ld_wait();
+                const int nc = n0 + c * 32;
+                float v[32];
+                const float4* bias4 = reinterpret_cast<const float4*>(p.bias + nc);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 bb = __ldg(bias4 + j);
+                    v[4 * j + 0] = __uint_as_float(acc[4 * j + 0]) + bb.x;
+                    v[4 * j + 1] = __uint_as_float(acc[4 * j + 1]) + bb.y;
+                    v[4 * j + 2] = __uint_as_float(acc[4 * j + 2]) + bb.z;
+                    v[4 * j + 3] = __uint_as_float(acc[4 * j + 3]) + bb.w;
+                }
+                if (EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_GELU_POS_F32) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+                }
+                if (valid) {
+                    if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16) {
+                        uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + nc);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            uint4 q;
+                            q.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+                            q.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+                            q.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+                            q.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+                            o[j] = q;
+                        }
+                    } else {
+                        const float* add = (EPI == EPI_BIAS_RESID_F32) ? (p.resid + orow * p.ldo + nc)
+                                                                       : (p.pos + (long long)t * p.N + nc);
+                        const float4* a4 = reinterpret_cast<const float4*>(add);
+                        float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + orow * p.ldo + nc);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 a = a4[j];
+                            o[j] = make_float4(v[4 * j + 0] + a.x, v[4 * j + 1] + a.y, v[4 * j + 2] + a.z,
+                                               v[4 * j + 3] + a.w);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<C::kTmemCols>(tmem_base);
+    }
+}
+
+template <int BN, int EPI>
+cudaError_t launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int sm_count,
+                       cudaStream_t stream) {
+    using C = Cfg<BN>;
+    auto kern = gemm_bf16_tcgen05<BN, EPI>;
+    const int tiles = ((p.M + BM - 1) / BM) * (p.N / BN);
+    const int grid = tiles < sm_count ? tiles : sm_count;
+    kern<<<grid, kThreads, C::kSmemBytes, stream>>>(ta, tb, p);
+    return cudaGetLastError();
+}
+
+template <int BN>
+cudaError_t launch_bn(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int sm_count,
+                      cudaStream_t stream) {
+    switch (epi) {
+        case EPI_BIAS_BF16: return launch_one<BN, EPI_BIAS_BF16>(ta, tb, p, sm_count, stream);
+        case EPI_BIAS_GELU_BF16: return launch_one<BN, EPI_BIAS_GELU_BF16>(ta, tb, p, sm_count, stream);
+        case EPI_BIAS_RESID_F32: return launch_one<BN, EPI_BIAS_RESID_F32>(ta, tb, p, sm_count, stream);
+        case EPI_BIAS_GELU_POS_F32: return launch_one<BN, EPI_BIAS_GELU_POS_F32>(ta, tb, p, sm_count, stream);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace
+
+int gemm_block_n(int N) { return (N % 256 == 0) ? 256 : 128; }
+
+namespace {
+template <int BN, int EPI>
+cudaError_t set_smem() {
+    return cudaFuncSetAttribute(gemm_bf16_tcgen05<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                Cfg<BN>::kSmemBytes);
+}
+template <int BN>
+cudaError_t set_smem_bn() {
+    cudaError_t e;
+    if ((e = set_smem<BN, EPI_BIAS_BF16>()) != cudaSuccess) return e;
+    if ((e = set_smem<BN, EPI_BIAS_GELU_BF16>()) != cudaSuccess) return e;
+    if ((e = set_smem<BN, EPI_BIAS_RESID_F32>()) != cudaSuccess) return e;
+    return set_smem<BN, EPI_BIAS_GELU_POS_F32>();
+}
+}  // namespace
+
+// Per device (call after cudaSetDevice): opt in to > 48 KB dynamic shared memory for every instance.
+cudaError_t gemm_init_device() {
+    cudaError_t e = set_smem_bn<256>();
+    if (e != cudaSuccess) return e;
+    return set_smem_bn<128>();
+}
+
+cudaError_t gemm_launch(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int sm_count,
+                        cudaStream_t stream) {
+    if (p.K % BK != 0 || p.N % 128 != 0 || p.a_cols % BK != 0 || p.M <= 0) return cudaErrorInvalidValue;
+    return gemm_block_n(p.N) == 256 ? launch_bn<256>(epi, ta, tb, p, sm_count, stream)
+                                    : launch_bn<128>(epi, ta, tb, p, sm_count, stream);
+}
+
+}  // namespace aries
