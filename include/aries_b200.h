@@ -1,0 +1,133 @@
+/* aries_b200.h — C ABI of the B200-native log-mel + Whisper-encoder path.
+ *
+ * Drop-in boundary for the hot path Whisper-Aries obtains from faster-whisper 1.1.1 / CTranslate2 4.6.0
+ * (requirements.txt:12,9), which the reference enters at final_optimized_transcriber.py:326
+ * (model.transcribe(chunk_audio, ...); warm-up at :189; model built at :179-182; large-v3 forced at
+ * conversation_transcriber.py:72-77).  Upstream, that call runs
+ *     FeatureExtractor.__call__(waveform, padding=160)            -> aries_logmel_run / aries_logmel_run_host
+ *     WhisperModel.encode(features) -> ctranslate2 Whisper.encode -> aries_encoder_run / aries_encoder_run_host
+ * per 30-second window.  Each entry point below names the upstream interface it replaces.
+ *
+ * Conventions
+ *   - plain C types only; every handle is opaque; no exceptions cross the boundary.
+ *   - return value: 0 (ARIES_OK) or a negative ARIES_E* code; aries_last_error() gives the message of the last
+ *     failure on the calling thread.  The Python shim maps ARIES_EINVAL -> ValueError (upstream raises
+ *     ValueError("Invalid input features shape...") from std::invalid_argument), everything else -> RuntimeError.
+ *   - inputs are borrowed for the duration of the call; outputs are caller-allocated; weights are copied at create.
+ *   - "dev" pointers are device memory on the context's GPU; the *_host variants take host memory (pageable or
+ *     pinned), do the copies on the context's stream and return after synchronising.
+ *   - stream arguments are cudaStream_t passed as void* (NULL = the legacy default stream).  Device-pointer entry
+ *     points are stream-ordered and do not synchronise the host.
+ *   - threading: one in-flight call per handle; distinct handles (also on different GPUs) are independent — the
+ *     reference's model of one model object per worker thread (final_optimized_transcriber.py:256-262).
+ *   - there is no CPU fallback: every entry point fails with ARIES_ECUDA when no sm_100 device is usable.
+ */
+#ifndef ARIES_B200_H_
+#define ARIES_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define ARIES_API __attribute__((visibility("default")))
+#else
+#define ARIES_API
+#endif
+
+#define ARIES_OK 0
+#define ARIES_EINVAL (-1)   /* bad argument / shape (-> ValueError) */
+#define ARIES_ECUDA (-2)    /* CUDA runtime or driver failure (-> RuntimeError) */
+#define ARIES_ENOMEM (-3)   /* allocation failure */
+#define ARIES_ESTATE (-4)   /* handle used on the wrong context / after destroy */
+
+typedef struct aries_ctx aries_ctx;
+typedef struct aries_mel aries_mel;
+typedef struct aries_encoder aries_encoder;
+
+/* ABI version of this header (major * 100 + minor). */
+ARIES_API int aries_abi_version(void);
+/* Message of the last failed call on this thread ("" if none). Never NULL. */
+ARIES_API const char* aries_last_error(void);
+
+/* One context per GPU. Replaces: the device selection inside WhisperModel(device=..., device_index=...)
+ * (final_optimized_transcriber.py:179-182; round-robin placement in "Yasmeen's code/complete_fixed_whisper.py":179-184). */
+ARIES_API int aries_init(int device, aries_ctx** out);
+ARIES_API int aries_destroy(aries_ctx* ctx);
+ARIES_API int aries_device(const aries_ctx* ctx);
+ARIES_API int aries_sm_count(const aries_ctx* ctx);
+
+/* ---------------------------------------------------------------------------------------------- log-mel
+ * Replaces faster_whisper.feature_extractor.FeatureExtractor (n_fft 400, hop 160, sampling rate 16 kHz).
+ * mel_filters: host f32 [n_mels, 201] exactly as FeatureExtractor.get_mel_filters returns it. */
+ARIES_API int aries_logmel_create(aries_ctx* ctx, int n_mels, const float* mel_filters, aries_mel** out);
+ARIES_API int aries_logmel_destroy(aries_mel* mel);
+/* (n_samples + padding) / 160: the frame count FeatureExtractor.__call__ returns (last STFT frame dropped). */
+ARIES_API int64_t aries_logmel_num_frames(int64_t n_samples, int padding);
+
+/* FeatureExtractor.__call__(waveform, padding) for `batch` equally long signals.
+ *   pcm_dev    device f32, signal i starts at pcm_dev + i * pcm_stride (floats)
+ *   out_dev    device f32 [batch, n_mels, frames_out]
+ *   frames_out frames stored per signal: pass aries_logmel_num_frames() for the upstream result, or 3000 for
+ *              the window WhisperModel.encode consumes (pad_or_trim: zero-filled past the last real frame).
+ *              The clamp maximum is always taken over ALL frames of the call, as upstream does. */
+ARIES_API int aries_logmel_run(aries_mel* mel, const float* pcm_dev, int batch, int64_t n_samples, int64_t pcm_stride,
+                     int padding, float* out_dev, int frames_out, void* stream);
+/* Same, host buffers (pcm_host contiguous [batch, n_samples], out_host [batch, n_mels, frames_out]). */
+ARIES_API int aries_logmel_run_host(aries_mel* mel, const float* pcm_host, int batch, int64_t n_samples, int padding,
+                          float* out_host, int frames_out);
+
+/* ---------------------------------------------------------------------------------------------- encoder
+ * Replaces ctranslate2.models.Whisper.encode (layers::WhisperEncoder): conv1(k3,s1,p1)+GELU, conv2(k3,s2,p1)+GELU,
+ * + position encodings, n_layers pre-norm blocks (MHA with q scaled by head_dim^-0.5 and no key bias, GELU MLP),
+ * final LayerNorm (eps 1e-5).  bf16 tensor-core arithmetic, f32 accumulation / residual stream / LN / softmax. */
+typedef struct aries_encoder_cfg {
+    int32_t n_mels;     /* 80 | 128 */
+    int32_t d_model;    /* multiple of 128 */
+    int32_t n_heads;    /* d_model / 64 */
+    int32_t n_layers;
+    int32_t d_ffn;      /* multiple of 128 */
+    int32_t n_ctx;      /* 1500 */
+} aries_encoder_cfg;
+
+/* One tensor of the CTranslate2 Whisper model ("encoder/conv1/weight", "encoder/layer_0/self_attention/linear_0/weight",
+ * ...), host f32, C-contiguous. */
+typedef struct aries_weight_desc {
+    const char* name;
+    const float* data;
+    int32_t ndim;
+    int64_t shape[4];
+} aries_weight_desc;
+
+ARIES_API int aries_encoder_create(aries_ctx* ctx, const aries_encoder_cfg* cfg, const aries_weight_desc* weights,
+                         int n_weights, aries_encoder** out);
+ARIES_API int aries_encoder_destroy(aries_encoder* enc);
+/* Bytes of device scratch aries_encoder_run needs for `batch` windows (0 on error). */
+ARIES_API size_t aries_encoder_workspace_bytes(const aries_encoder* enc, int batch);
+
+/* Whisper.encode(features).
+ *   mel_dev    device f32 [batch, n_mels, frames], frames <= 3000 (shorter inputs are zero-padded like CT2 pads)
+ *   out_dev    device bf16 [batch, 1500, d_model]
+ *   workspace  device scratch, 256-byte aligned, >= aries_encoder_workspace_bytes(enc, batch) */
+ARIES_API int aries_encoder_run(aries_encoder* enc, const float* mel_dev, int batch, int frames, void* out_dev,
+                      void* workspace, size_t workspace_bytes, void* stream);
+/* Same with host buffers: mel_host f32 [batch, n_mels, frames] -> out_host bf16 (raw uint16) [batch, 1500, d_model];
+ * device scratch is owned (and grown on demand) by the handle. */
+ARIES_API int aries_encoder_run_host(aries_encoder* enc, const float* mel_host, int batch, int frames, uint16_t* out_host);
+
+/* Fused front end + encoder (additive extension): PCM -> log-mel -> encoder without the mel tensor leaving the GPU.
+ * Equivalent to encode(pad_or_trim(feature_extractor(pcm))[:, :3000]) for 30-second windows (n_samples <= 480000). */
+ARIES_API int aries_encode_pcm(aries_encoder* enc, aries_mel* mel, const float* pcm_dev, int batch, int64_t n_samples,
+                     int64_t pcm_stride, void* out_dev, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Number of kernels the last aries_logmel_run / aries_encoder_run / aries_encode_pcm on this handle launched. */
+ARIES_API int aries_logmel_last_launches(const aries_mel* mel);
+ARIES_API int aries_encoder_last_launches(const aries_encoder* enc);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ARIES_B200_H_ */

@@ -1,0 +1,120 @@
+"""CPU: the C-ABI library loads and exports every symbol include/*.h declares; host logic of the shim and scheduler.
+No compute calls here (no GPU in this container)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import logmel as omel, synth as osynth
+from whisper_aries_b200 import FeatureExtractor, _lib, partition_windows, synthetic
+from whisper_aries_b200.scheduler import ChunkScheduler, split_into_windows
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    names = set()
+    for h in ("aries_b200.h", "aries_b200_test.h"):
+        src = open(os.path.join(ROOT, "include", h)).read()
+        names |= set(re.findall(r"ARIES_API\s+[\w\s\*]+?\b(aries_\w+)\s*\(", src))
+    return names
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    names = declared_symbols()
+    assert len(names) >= 22
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/ but not exported"
+    assert names == set(_lib.PROTOTYPES), "ctypes prototypes and the headers disagree"
+    assert lib.aries_abi_version() == 100
+
+
+def test_no_cpu_fallback_when_no_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    rc = lib.aries_init(0, ctypes.byref(h))
+    assert rc == _lib.ARIES_ECUDA and "no CPU fallback" in _lib.last_error()
+    fe = FeatureExtractor(feature_size=80)          # host-side construction works ...
+    with pytest.raises(RuntimeError):               # ... but computing without a GPU fails loudly
+        fe(np.zeros(16000, np.float32))
+    with pytest.raises(ValueError):
+        FeatureExtractor(device="cpu")
+
+
+def test_pure_host_entry_points():
+    lib = _lib.load()
+    assert lib.aries_logmel_num_frames(480000, 160) == 3001
+    assert lib.aries_logmel_num_frames(1234, 160) == 8
+    assert lib.aries_logmel_num_frames(8000, 0) == 50
+    assert lib.aries_encoder_workspace_bytes(None, 4) == 0
+    assert lib.aries_logmel_destroy(None) == 0 and lib.aries_encoder_destroy(None) == 0 and lib.aries_destroy(None) == 0
+
+
+def test_feature_extractor_surface_matches_upstream():
+    fe = FeatureExtractor(feature_size=128)
+    assert (fe.n_fft, fe.hop_length, fe.chunk_length, fe.n_samples, fe.nb_max_frames) == (400, 160, 30, 480000, 3000)
+    assert fe.time_per_frame == 0.01 and fe.sampling_rate == 16000
+    assert fe.mel_filters.shape == (128, 201) and fe.mel_filters.dtype == np.float32
+    for n in (80, 128):
+        assert np.array_equal(FeatureExtractor.get_mel_filters(16000, 400, n), omel.mel_filterbank(n))
+    with pytest.raises(ValueError):
+        FeatureExtractor(n_fft=512)
+
+
+def test_synthetic_generators_match_the_oracles():
+    assert np.array_equal(synthetic.window_signal(5, 4000), osynth.window_signal(5, 4000))
+    a, b = synthetic.encoder_weights(synthetic.SHAPES["micro"]), osynth.encoder_weights(osynth.SHAPES["micro"])
+    assert a.keys() == b.keys() and all(np.array_equal(a[k], b[k]) for k in a)
+    for k in synthetic.SHAPES:
+        assert synthetic.SHAPES[k].flops_per_window == osynth.SHAPES[k].flops_per_window
+
+
+def test_partition_is_contiguous_and_complete():
+    assert partition_windows(120, 8) == [(i * 15, i * 15 + 15) for i in range(8)]
+    assert partition_windows(120, 4)[-1] == (90, 120)
+    for n in (0, 1, 5, 63, 64, 121):
+        for g in (1, 2, 3, 8):
+            parts = partition_windows(n, g)
+            assert len(parts) == g and parts[0][0] == 0 and parts[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+            assert max(b - a for a, b in parts) - min(b - a for a, b in parts if b > a or n == 0) <= max(1, -(-n // g))
+    with pytest.raises(ValueError):
+        partition_windows(4, 0)
+
+
+def test_split_into_windows_zero_pads_the_tail():
+    x = np.arange(10, dtype=np.float32) + 1
+    w = split_into_windows(x, 4)
+    assert w.shape == (3, 4) and w[2].tolist() == [9, 10, 0, 0]
+    assert split_into_windows(x[:8], 4).shape == (2, 4)
+
+
+def test_scheduler_with_fake_devices_keeps_order_and_isolates_failures():
+    windows = np.arange(10 * 3, dtype=np.float32).reshape(10, 3)
+    out = np.zeros((10, 2), np.float32)
+    seen = []
+
+    def make(worker_id, fail=False):
+        def run(w, start, stop, o):
+            seen.append((worker_id, start, stop))
+            if fail:
+                raise RuntimeError("device lost")
+            o[start:stop, 0] = w[start:stop].sum(axis=1)
+            o[start:stop, 1] = worker_id
+        return run
+
+    res = ChunkScheduler([make(0), make(1, fail=True), make(2)]).run(windows, out)
+    assert [r.chunk_id for r in res] == [0, 1, 2]
+    assert [r.success for r in res] == [True, False, True] and "device lost" in res[1].error
+    assert [(r.start, r.stop) for r in res] == [(0, 4), (4, 8), (8, 10)]
+    assert np.array_equal(out[:4, 0], windows[:4].sum(axis=1)) and (out[4:8] == 0).all()
+    assert out[8:, 1].tolist() == [2, 2]
+    # more devices than windows: trailing shards are empty and succeed
+    res = ChunkScheduler([make(i) for i in range(4)]).run(windows[:2], np.zeros((2, 2), np.float32))
+    assert [r.n_windows for r in res] == [1, 1, 0, 0] and all(r.success for r in res)

@@ -1,0 +1,26 @@
+// Host-side interface of the fused attention kernel (attention_sm100.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "gemm.h"
+
+namespace aries {
+
+struct AttnParams {
+    int batch;
+    int T;          // sequence length (1500)
+    int d_model;    // n_heads * 64
+    int n_heads;
+    void* out;      // bf16 [batch * T, d_model]
+};
+
+cudaError_t attention_init_device();
+// qk: bf16 [batch * T, 2 * d_model] (queries then keys, as the QKV GEMM writes them);
+// vt: bf16 [batch, n_heads, 64, t_pad] (values, transposed by the QKV GEMM's epilogue).
+cudaError_t attention_make_maps(const void* qk, const void* vt, int batch, int T, int d_model, int n_heads, int t_pad,
+                                CUtensorMap* map_qk, CUtensorMap* map_vt);
+cudaError_t attention_launch(const CUtensorMap& map_qk, const CUtensorMap& map_vt, const AttnParams& p,
+                             cudaStream_t stream);
+
+}  // namespace aries

@@ -1,0 +1,397 @@
+// extern "C" surface of libaries_b200.so (include/aries_b200.h, include/aries_b200_test.h).
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/aries_b200.h"
+#include "../../include/aries_b200_test.h"
+#include "attention.h"
+#include "encoder.h"
+#include "gemm.h"
+#include "layernorm.h"
+#include "logmel.h"
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const std::string& msg) {
+    g_error = msg;
+    return code;
+}
+int fail_cuda(const char* what, cudaError_t e) {
+    g_error = std::string(what) + ": " + cudaGetErrorString(e);
+    cudaGetLastError();   // clear the sticky-free error state
+    return e == cudaErrorMemoryAllocation ? ARIES_ENOMEM : (e == cudaErrorInvalidValue ? ARIES_EINVAL : ARIES_ECUDA);
+}
+
+constexpr unsigned kMagicCtx = 0xA51E5001u, kMagicMel = 0xA51E5002u, kMagicEnc = 0xA51E5003u;
+
+}  // namespace
+
+struct aries_ctx {
+    unsigned magic;
+    int device;
+    int sm_count;
+    bool kernels_ready;
+};
+
+struct aries_mel {
+    unsigned magic;
+    aries_ctx* ctx;
+    aries::LogmelPlan* plan;
+    int last_launches;
+    // scratch for the host-buffer variant
+    float* d_pcm;
+    size_t pcm_cap;
+    float* d_out;
+    size_t out_cap;
+};
+
+struct aries_encoder {
+    unsigned magic;
+    aries_ctx* ctx;
+    aries::EncoderPlan* plan;
+    // scratch for the host-buffer variant
+    void* d_ws;
+    size_t ws_cap;
+    float* d_mel;
+    size_t mel_cap;
+    void* d_out;
+    size_t out_cap;
+};
+
+namespace {
+
+int use(const aries_ctx* ctx) {
+    if (!ctx || ctx->magic != kMagicCtx) return fail(ARIES_ESTATE, "invalid context handle");
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return fail_cuda("cudaSetDevice", e);
+    return ARIES_OK;
+}
+
+int ensure_kernels(aries_ctx* ctx) {
+    if (ctx->kernels_ready) return ARIES_OK;
+    cudaError_t e;
+    if ((e = aries::gemm_init_device()) != cudaSuccess) return fail_cuda("gemm_init_device", e);
+    if ((e = aries::attention_init_device()) != cudaSuccess) return fail_cuda("attention_init_device", e);
+    ctx->kernels_ready = true;
+    return ARIES_OK;
+}
+
+template <class T>
+int grow(T** ptr, size_t* cap, size_t bytes) {
+    if (bytes <= *cap) return ARIES_OK;
+    cudaFree(*ptr);
+    *ptr = nullptr;
+    *cap = 0;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(ptr), bytes);
+    if (e != cudaSuccess) return fail_cuda("cudaMalloc", e);
+    *cap = bytes;
+    return ARIES_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int aries_abi_version(void) { return 100; }
+
+const char* aries_last_error(void) { return g_error.c_str(); }
+
+int aries_init(int device, aries_ctx** out) {
+    if (!out) return fail(ARIES_EINVAL, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(ARIES_ECUDA, std::string("no CUDA device is usable (this library has no CPU fallback): ") +
+                                     (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    if (device < 0 || device >= n) return fail(ARIES_EINVAL, "device index out of range");
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail_cuda("cudaGetDeviceProperties", e);
+    if (prop.major != 10)
+        return fail(ARIES_ECUDA, "device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                                     "; this library is compiled for sm_100a (B200) only");
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return fail_cuda("cudaSetDevice", e);
+    aries_ctx* c = new (std::nothrow) aries_ctx{kMagicCtx, device, prop.multiProcessorCount, false};
+    if (!c) return fail(ARIES_ENOMEM, "out of host memory");
+    *out = c;
+    return ARIES_OK;
+}
+
+int aries_destroy(aries_ctx* ctx) {
+    if (!ctx) return ARIES_OK;
+    if (ctx->magic != kMagicCtx) return fail(ARIES_ESTATE, "invalid context handle");
+    ctx->magic = 0;
+    delete ctx;
+    return ARIES_OK;
+}
+
+int aries_device(const aries_ctx* ctx) { return (ctx && ctx->magic == kMagicCtx) ? ctx->device : -1; }
+int aries_sm_count(const aries_ctx* ctx) { return (ctx && ctx->magic == kMagicCtx) ? ctx->sm_count : -1; }
+
+// ------------------------------------------------------------------------------------------------ log-mel
+int aries_logmel_create(aries_ctx* ctx, int n_mels, const float* mel_filters, aries_mel** out) {
+    if (!out) return fail(ARIES_EINVAL, "out is NULL");
+    *out = nullptr;
+    int rc = use(ctx);
+    if (rc) return rc;
+    if (!mel_filters) return fail(ARIES_EINVAL, "mel_filters is NULL");
+    aries::LogmelPlan* plan = nullptr;
+    const char* why = "";
+    cudaError_t e = aries::logmel_plan_create(ctx->device, ctx->sm_count, n_mels, mel_filters, &plan, &why);
+    if (e != cudaSuccess) {
+        g_error = std::string("aries_logmel_create: ") + why;
+        cudaGetLastError();
+        return e == cudaErrorInvalidValue ? ARIES_EINVAL : ARIES_ECUDA;
+    }
+    aries_mel* m = new (std::nothrow) aries_mel{kMagicMel, ctx, plan, 0, nullptr, 0, nullptr, 0};
+    if (!m) {
+        aries::logmel_plan_destroy(plan);
+        return fail(ARIES_ENOMEM, "out of host memory");
+    }
+    *out = m;
+    return ARIES_OK;
+}
+
+int aries_logmel_destroy(aries_mel* mel) {
+    if (!mel) return ARIES_OK;
+    if (mel->magic != kMagicMel) return fail(ARIES_ESTATE, "invalid log-mel handle");
+    use(mel->ctx);
+    aries::logmel_plan_destroy(mel->plan);
+    cudaFree(mel->d_pcm);
+    cudaFree(mel->d_out);
+    mel->magic = 0;
+    delete mel;
+    return ARIES_OK;
+}
+
+int64_t aries_logmel_num_frames(int64_t n_samples, int padding) {
+    if (n_samples < 0 || padding < 0) return 0;
+    return (n_samples + padding) / 160;
+}
+
+int aries_logmel_run(aries_mel* mel, const float* pcm_dev, int batch, int64_t n_samples, int64_t pcm_stride,
+                     int padding, float* out_dev, int frames_out, void* stream) {
+    if (!mel || mel->magic != kMagicMel) return fail(ARIES_ESTATE, "invalid log-mel handle");
+    int rc = use(mel->ctx);
+    if (rc) return rc;
+    if (batch <= 0 || n_samples <= 0 || padding < 0 || frames_out < 0 || pcm_stride < n_samples || !pcm_dev || !out_dev)
+        return fail(ARIES_EINVAL, "aries_logmel_run: need batch > 0, n_samples > 0, padding >= 0, frames_out >= 0, "
+                                  "pcm_stride >= n_samples and non-NULL buffers");
+    if ((n_samples + padding) / 160 > (1 << 24)) return fail(ARIES_EINVAL, "aries_logmel_run: signal too long");
+    cudaError_t e = aries::logmel_run(mel->plan, pcm_dev, batch, n_samples, pcm_stride, padding, out_dev, frames_out,
+                                      static_cast<cudaStream_t>(stream), &mel->last_launches);
+    if (e != cudaSuccess) return fail_cuda("aries_logmel_run", e);
+    return ARIES_OK;
+}
+
+int aries_logmel_run_host(aries_mel* mel, const float* pcm_host, int batch, int64_t n_samples, int padding,
+                          float* out_host, int frames_out) {
+    if (!mel || mel->magic != kMagicMel) return fail(ARIES_ESTATE, "invalid log-mel handle");
+    int rc = use(mel->ctx);
+    if (rc) return rc;
+    if (batch <= 0 || n_samples <= 0 || !pcm_host || !out_host || frames_out < 0)
+        return fail(ARIES_EINVAL, "aries_logmel_run_host: bad arguments");
+    const size_t in_bytes = (size_t)batch * n_samples * 4;
+    const size_t out_bytes = (size_t)batch * aries::logmel_plan_n_mels(mel->plan) * frames_out * 4;
+    if ((rc = grow(&mel->d_pcm, &mel->pcm_cap, in_bytes))) return rc;
+    if ((rc = grow(&mel->d_out, &mel->out_cap, out_bytes ? out_bytes : 4))) return rc;
+    cudaError_t e;
+    if ((e = cudaMemcpyAsync(mel->d_pcm, pcm_host, in_bytes, cudaMemcpyHostToDevice, 0)) != cudaSuccess)
+        return fail_cuda("H2D copy", e);
+    if ((rc = aries_logmel_run(mel, mel->d_pcm, batch, n_samples, n_samples, padding, mel->d_out, frames_out, nullptr)))
+        return rc;
+    if (out_bytes && (e = cudaMemcpyAsync(out_host, mel->d_out, out_bytes, cudaMemcpyDeviceToHost, 0)) != cudaSuccess)
+        return fail_cuda("D2H copy", e);
+    if ((e = cudaStreamSynchronize(0)) != cudaSuccess) return fail_cuda("aries_logmel_run_host", e);
+    return ARIES_OK;
+}
+
+int aries_logmel_last_launches(const aries_mel* mel) { return (mel && mel->magic == kMagicMel) ? mel->last_launches : -1; }
+
+// ------------------------------------------------------------------------------------------------ encoder
+int aries_encoder_create(aries_ctx* ctx, const aries_encoder_cfg* cfg, const aries_weight_desc* weights,
+                         int n_weights, aries_encoder** out) {
+    if (!out) return fail(ARIES_EINVAL, "out is NULL");
+    *out = nullptr;
+    int rc = use(ctx);
+    if (rc) return rc;
+    if (!cfg || !weights || n_weights <= 0) return fail(ARIES_EINVAL, "aries_encoder_create: cfg / weights missing");
+    std::vector<aries::WeightView> views(n_weights);
+    for (int i = 0; i < n_weights; ++i) {
+        if (!weights[i].name || weights[i].ndim < 1 || weights[i].ndim > 4)
+            return fail(ARIES_EINVAL, "aries_encoder_create: malformed weight descriptor");
+        views[i].name = weights[i].name;
+        views[i].data = weights[i].data;
+        views[i].ndim = weights[i].ndim;
+        for (int k = 0; k < 4; ++k) views[i].shape[k] = k < weights[i].ndim ? weights[i].shape[k] : 1;
+    }
+    aries::EncoderShapeC shape{cfg->n_mels, cfg->d_model, cfg->n_heads, cfg->n_layers, cfg->d_ffn, cfg->n_ctx};
+    aries::EncoderPlan* plan = nullptr;
+    std::string why;
+    cudaError_t e = aries::encoder_plan_create(ctx->device, ctx->sm_count, shape, views.data(), n_weights, &plan, &why);
+    if (e != cudaSuccess) {
+        g_error = "aries_encoder_create: " + why;
+        cudaGetLastError();
+        return e == cudaErrorInvalidValue ? ARIES_EINVAL : (e == cudaErrorMemoryAllocation ? ARIES_ENOMEM : ARIES_ECUDA);
+    }
+    ctx->kernels_ready = true;
+    aries_encoder* h = new (std::nothrow) aries_encoder{kMagicEnc, ctx, plan, nullptr, 0, nullptr, 0, nullptr, 0};
+    if (!h) {
+        aries::encoder_plan_destroy(plan);
+        return fail(ARIES_ENOMEM, "out of host memory");
+    }
+    *out = h;
+    return ARIES_OK;
+}
+
+int aries_encoder_destroy(aries_encoder* enc) {
+    if (!enc) return ARIES_OK;
+    if (enc->magic != kMagicEnc) return fail(ARIES_ESTATE, "invalid encoder handle");
+    use(enc->ctx);
+    aries::encoder_plan_destroy(enc->plan);
+    cudaFree(enc->d_ws);
+    cudaFree(enc->d_mel);
+    cudaFree(enc->d_out);
+    enc->magic = 0;
+    delete enc;
+    return ARIES_OK;
+}
+
+size_t aries_encoder_workspace_bytes(const aries_encoder* enc, int batch) {
+    if (!enc || enc->magic != kMagicEnc || batch <= 0) return 0;
+    return aries::encoder_workspace_bytes(enc->plan, batch);
+}
+
+static int check_features(const aries_encoder* enc, int batch, int frames) {
+    if (batch <= 0 || frames <= 0 || frames > 3000) {
+        const aries::EncoderShapeC* c = aries::encoder_plan_cfg(enc->plan);
+        return fail(ARIES_EINVAL, "Invalid input features shape: expected an input with shape (batch, " +
+                                      std::to_string(c->n_mels) + ", <=3000), but got (" + std::to_string(batch) + ", " +
+                                      std::to_string(c->n_mels) + ", " + std::to_string(frames) + ")");
+    }
+    return ARIES_OK;
+}
+
+int aries_encoder_run(aries_encoder* enc, const float* mel_dev, int batch, int frames, void* out_dev, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+    if (!enc || enc->magic != kMagicEnc) return fail(ARIES_ESTATE, "invalid encoder handle");
+    int rc = use(enc->ctx);
+    if (rc) return rc;
+    if ((rc = check_features(enc, batch, frames))) return rc;
+    if (!mel_dev || !out_dev) return fail(ARIES_EINVAL, "aries_encoder_run: NULL buffer");
+    cudaError_t e = aries::encoder_run(enc->plan, mel_dev, batch, frames, out_dev, workspace, workspace_bytes,
+                                       static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) {
+        g_error = std::string("aries_encoder_run: ") + aries::encoder_plan_error(enc->plan);
+        cudaGetLastError();
+        return e == cudaErrorInvalidValue ? ARIES_EINVAL : ARIES_ECUDA;
+    }
+    return ARIES_OK;
+}
+
+int aries_encoder_run_host(aries_encoder* enc, const float* mel_host, int batch, int frames, uint16_t* out_host) {
+    if (!enc || enc->magic != kMagicEnc) return fail(ARIES_ESTATE, "invalid encoder handle");
+    int rc = use(enc->ctx);
+    if (rc) return rc;
+    if ((rc = check_features(enc, batch, frames))) return rc;
+    if (!mel_host || !out_host) return fail(ARIES_EINVAL, "aries_encoder_run_host: NULL buffer");
+    const aries::EncoderShapeC* c = aries::encoder_plan_cfg(enc->plan);
+    const size_t in_bytes = (size_t)batch * c->n_mels * frames * 4;
+    const size_t out_bytes = (size_t)batch * c->n_ctx * c->d_model * 2;
+    const size_t ws = aries::encoder_workspace_bytes(enc->plan, batch);
+    if ((rc = grow(&enc->d_mel, &enc->mel_cap, in_bytes))) return rc;
+    if ((rc = grow(&enc->d_out, &enc->out_cap, out_bytes))) return rc;
+    if ((rc = grow(&enc->d_ws, &enc->ws_cap, ws))) return rc;
+    cudaError_t e;
+    if ((e = cudaMemcpyAsync(enc->d_mel, mel_host, in_bytes, cudaMemcpyHostToDevice, 0)) != cudaSuccess)
+        return fail_cuda("H2D copy", e);
+    if ((rc = aries_encoder_run(enc, enc->d_mel, batch, frames, enc->d_out, enc->d_ws, enc->ws_cap, nullptr))) return rc;
+    if ((e = cudaMemcpyAsync(out_host, enc->d_out, out_bytes, cudaMemcpyDeviceToHost, 0)) != cudaSuccess)
+        return fail_cuda("D2H copy", e);
+    if ((e = cudaStreamSynchronize(0)) != cudaSuccess) return fail_cuda("aries_encoder_run_host", e);
+    return ARIES_OK;
+}
+
+int aries_encode_pcm(aries_encoder* enc, aries_mel* mel, const float* pcm_dev, int batch, int64_t n_samples,
+                     int64_t pcm_stride, void* out_dev, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!enc || enc->magic != kMagicEnc) return fail(ARIES_ESTATE, "invalid encoder handle");
+    if (!mel || mel->magic != kMagicMel) return fail(ARIES_ESTATE, "invalid log-mel handle");
+    if (mel->ctx != enc->ctx) return fail(ARIES_ESTATE, "log-mel and encoder handles belong to different contexts");
+    int rc = use(enc->ctx);
+    if (rc) return rc;
+    const aries::EncoderShapeC* c = aries::encoder_plan_cfg(enc->plan);
+    if (aries::logmel_plan_n_mels(mel->plan) != c->n_mels)
+        return fail(ARIES_EINVAL, "aries_encode_pcm: the log-mel handle's n_mels differs from the encoder's");
+    if (batch <= 0 || n_samples <= 0 || n_samples > 480000)
+        return fail(ARIES_EINVAL, "aries_encode_pcm: need batch > 0 and 0 < n_samples <= 480000 (one 30-second window)");
+    const size_t need = aries::encoder_workspace_bytes(enc->plan, batch);
+    if (!workspace || workspace_bytes < need) return fail(ARIES_EINVAL, "aries_encode_pcm: workspace too small");
+    float* mel_buf = aries::encoder_workspace_mel(enc->plan, workspace, batch);
+    if ((rc = aries_logmel_run(mel, pcm_dev, batch, n_samples, pcm_stride, 160, mel_buf, 3000, stream))) return rc;
+    return aries_encoder_run(enc, mel_buf, batch, 3000, out_dev, workspace, workspace_bytes, stream);
+}
+
+int aries_encoder_last_launches(const aries_encoder* enc) {
+    return (enc && enc->magic == kMagicEnc) ? aries::encoder_plan_last_launches(enc->plan) : -1;
+}
+
+// ------------------------------------------------------------------------------------------------ test hooks
+int aries_test_gemm(aries_ctx* ctx, int epi, int M, int N, int K, const void* a, const void* b, const float* bias,
+                    const float* resid, const float* pos, int pos_rows, void* out, void* out2, int n_split,
+                    int t_rows, int t_pad, void* stream) {
+    int rc = use(ctx);
+    if (rc) return rc;
+    if ((rc = ensure_kernels(ctx))) return rc;
+    if (M <= 0 || N % 128 || K % 64 || epi < 0 || epi >= aries::EPI_COUNT) return fail(ARIES_EINVAL, "aries_test_gemm: bad shape");
+    CUtensorMap ta, tb;
+    const unsigned long long da[2] = {(unsigned long long)K, (unsigned long long)M}, sa[2] = {2, (unsigned long long)K * 2};
+    const unsigned long long db[2] = {(unsigned long long)K, (unsigned long long)N};
+    const unsigned ba[2] = {64, 128}, bb[2] = {64, (unsigned)aries::gemm_block_n(N)};
+    cudaError_t e;
+    if ((e = aries::make_tmap_bf16(&ta, a, 2, da, sa, ba)) != cudaSuccess) return fail_cuda("tensor map A", e);
+    if ((e = aries::make_tmap_bf16(&tb, b, 2, db, sa, bb)) != cudaSuccess) return fail_cuda("tensor map B", e);
+    aries::GemmParams p{};
+    p.M = M; p.N = N; p.K = K; p.a_cols = K;
+    p.p_in = M; p.t_valid = M; p.p_out = M; p.row_off = 0; p.ldo = N;
+    p.bias = bias; p.resid = resid; p.pos = pos; p.out = out;
+    if (epi == aries::EPI_BIAS_GELU_POS_F32) { p.p_in = pos_rows; p.t_valid = pos_rows; p.p_out = pos_rows; }
+    if (epi == aries::EPI_QKV_SPLIT_BF16) {
+        p.p_in = t_rows; p.t_valid = t_rows; p.p_out = t_rows; p.ldo = n_split;
+        p.out2 = out2; p.n_split = n_split; p.t_pad = t_pad;
+    }
+    if ((e = aries::gemm_launch(epi, ta, tb, p, ctx->sm_count, static_cast<cudaStream_t>(stream))) != cudaSuccess)
+        return fail_cuda("gemm_launch", e);
+    return ARIES_OK;
+}
+
+int aries_test_layernorm(aries_ctx* ctx, const float* x, const float* gamma, const float* beta, void* y, int64_t rows,
+                         int d, void* stream) {
+    int rc = use(ctx);
+    if (rc) return rc;
+    cudaError_t e = aries::layernorm_launch(x, gamma, beta, y, rows, d, 1e-5f, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail_cuda("layernorm_launch", e);
+    return ARIES_OK;
+}
+
+int aries_test_attention(aries_ctx* ctx, const void* qk, const void* vt, int batch, int T, int n_heads, int t_pad,
+                         void* out, void* stream) {
+    int rc = use(ctx);
+    if (rc) return rc;
+    if ((rc = ensure_kernels(ctx))) return rc;
+    CUtensorMap mq, mv;
+    cudaError_t e = aries::attention_make_maps(qk, vt, batch, T, n_heads * 64, n_heads, t_pad, &mq, &mv);
+    if (e != cudaSuccess) return fail_cuda("attention tensor maps", e);
+    aries::AttnParams p{batch, T, n_heads * 64, n_heads, out};
+    if ((e = aries::attention_launch(mq, mv, p, static_cast<cudaStream_t>(stream))) != cudaSuccess)
+        return fail_cuda("attention_launch", e);
+    return ARIES_OK;
+}
+
+}  // extern "C"

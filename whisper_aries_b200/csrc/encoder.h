@@ -1,0 +1,35 @@
+// Host-side interface of the encoder assembly (encoder.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+
+namespace aries {
+
+struct EncoderShapeC {
+    int n_mels, d_model, n_heads, n_layers, d_ffn, n_ctx;
+};
+
+struct WeightView {
+    const char* name;
+    const float* data;
+    int ndim;
+    long long shape[4];
+};
+
+struct EncoderPlan;
+
+cudaError_t encoder_plan_create(int device, int sm_count, const EncoderShapeC& cfg, const WeightView* weights,
+                                int n_weights, EncoderPlan** out, std::string* why);
+void encoder_plan_destroy(EncoderPlan* pl);
+size_t encoder_workspace_bytes(const EncoderPlan* pl, int batch);
+// mel: device f32 [batch, n_mels, frames]; out: device bf16 [batch, 1500, d_model].  Stream-ordered.
+cudaError_t encoder_run(EncoderPlan* pl, const float* mel, int batch, int frames, void* out_bf16, void* workspace,
+                        size_t ws_bytes, cudaStream_t stream);
+// f32 [batch, n_mels, 3000] scratch inside the workspace for the fused PCM path.
+float* encoder_workspace_mel(const EncoderPlan* pl, void* workspace, int batch);
+const char* encoder_plan_error(const EncoderPlan* pl);
+int encoder_plan_last_launches(const EncoderPlan* pl);
+const EncoderShapeC* encoder_plan_cfg(const EncoderPlan* pl);
+
+}  // namespace aries

@@ -10,6 +10,9 @@ enum GemmEpilogue {
     EPI_BIAS_GELU_BF16 = 1,     // out bf16 = gelu_erf(acc + bias)             (MLP fc1, conv1)
     EPI_BIAS_RESID_F32 = 2,     // out f32  = acc + bias + resid               (attention out-proj, MLP fc2)
     EPI_BIAS_GELU_POS_F32 = 3,  // out f32  = gelu_erf(acc + bias) + pos[t]    (conv2 + positional table)
+    EPI_QKV_SPLIT_BF16 = 4,     // acc + bias: columns < n_split -> out (row-major, ld = ldo, queries | keys);
+                                // columns >= n_split -> out2[b][head][c][t] (values, transposed for attention)
+    EPI_COUNT = 5,
 };
 
 struct GemmParams {
@@ -24,6 +27,9 @@ struct GemmParams {
     const float* resid; // f32, indexed like out (EPI_BIAS_RESID_F32; may alias out)
     const float* pos;   // f32 [t_valid, N] (EPI_BIAS_GELU_POS_F32)
     void* out;
+    void* out2;         // EPI_QKV_SPLIT_BF16: bf16 [batch, (N - n_split) / 64, 64, t_pad]
+    int n_split;        // EPI_QKV_SPLIT_BF16: first column of the transposed part (2 * d_model)
+    int t_pad;          // EPI_QKV_SPLIT_BF16: row pitch of out2 (elements)
 };
 
 int gemm_block_n(int N);

@@ -168,8 +168,16 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
                 }
-                if (valid) {
-                    if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16) {
+                if (EPI == EPI_QKV_SPLIT_BF16 && nc >= p.n_split) {
+                    // values: out2[b][head][c][t]; for a fixed column the warp's 32 rows are 32 consecutive t
+                    if (valid) {
+                        __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(p.out2) +
+                                            ((long long)b * (p.N - p.n_split) + (nc - p.n_split)) * p.t_pad + t;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) o2[(long long)j * p.t_pad] = __float2bfloat16_rn(v[j]);
+                    }
+                } else if (valid) {
+                    if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_QKV_SPLIT_BF16) {
                         uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + nc);
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
@@ -227,6 +235,7 @@ cudaError_t launch_bn(int epi, const CUtensorMap& ta, const CUtensorMap& tb, con
         case EPI_BIAS_GELU_BF16: return launch_one<BN, EPI_BIAS_GELU_BF16>(ta, tb, p, sm_count, stream);
         case EPI_BIAS_RESID_F32: return launch_one<BN, EPI_BIAS_RESID_F32>(ta, tb, p, sm_count, stream);
         case EPI_BIAS_GELU_POS_F32: return launch_one<BN, EPI_BIAS_GELU_POS_F32>(ta, tb, p, sm_count, stream);
+        case EPI_QKV_SPLIT_BF16: return launch_one<BN, EPI_QKV_SPLIT_BF16>(ta, tb, p, sm_count, stream);
     }
     return cudaErrorInvalidValue;
 }
@@ -247,6 +256,7 @@ cudaError_t set_smem_bn() {
     if ((e = set_smem<BN, EPI_BIAS_BF16>()) != cudaSuccess) return e;
     if ((e = set_smem<BN, EPI_BIAS_GELU_BF16>()) != cudaSuccess) return e;
     if ((e = set_smem<BN, EPI_BIAS_RESID_F32>()) != cudaSuccess) return e;
+    if ((e = set_smem<BN, EPI_QKV_SPLIT_BF16>()) != cudaSuccess) return e;
     return set_smem<BN, EPI_BIAS_GELU_POS_F32>();
 }
 }  // namespace

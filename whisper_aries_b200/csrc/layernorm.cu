@@ -1,0 +1,92 @@
+// K4: LayerNorm over the f32 residual stream, bf16 out (the A operand of the next GEMM, or the encoder output).
+// One warp per row; the row stays in registers between the mean, variance and normalise passes, so HBM sees one
+// f32 read and one bf16 write per element.  (CT2 ops::LayerNorm; eps 1e-5.)
+#include <cuda_bf16.h>
+
+#include "layernorm.h"
+
+namespace aries {
+
+namespace {
+
+constexpr int kWarpsPerBlock = 8;
+
+template <int NV>   // NV float4 per lane: d = 128 * NV
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) layernorm_kernel(const float* __restrict__ x,
+                                                                        const float* __restrict__ gamma,
+                                                                        const float* __restrict__ beta,
+                                                                        __nv_bfloat16* __restrict__ y, long long rows,
+                                                                        float eps) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    constexpr int d = NV * 128;
+    const float4* xr = reinterpret_cast<const float4*>(x + row * d);
+    float4 v[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) v[j] = __ldcs(xr + lane + 32 * j);
+    float s = 0.0f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * (1.0f / d);
+    float q = 0.0f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, e = v[j].w - mean;
+        q += (a * a + b * b) + (c * c + e * e);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q * (1.0f / d) + eps);
+    const float4* g4 = reinterpret_cast<const float4*>(gamma);
+    const float4* b4 = reinterpret_cast<const float4*>(beta);
+    uint2* yr = reinterpret_cast<uint2*>(y + row * d);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const float4 g = __ldg(g4 + lane + 32 * j);
+        const float4 b = __ldg(b4 + lane + 32 * j);
+        const __nv_bfloat162 lo = __floats2bfloat162_rn((v[j].x - mean) * rstd * g.x + b.x,
+                                                        (v[j].y - mean) * rstd * g.y + b.y);
+        const __nv_bfloat162 hi = __floats2bfloat162_rn((v[j].z - mean) * rstd * g.z + b.z,
+                                                        (v[j].w - mean) * rstd * g.w + b.w);
+        uint2 o;
+        o.x = *reinterpret_cast<const unsigned*>(&lo);
+        o.y = *reinterpret_cast<const unsigned*>(&hi);
+        yr[lane + 32 * j] = o;
+    }
+}
+
+template <int NV>
+cudaError_t launch(const float* x, const float* g, const float* b, void* y, long long rows, float eps,
+                   cudaStream_t stream) {
+    const long long blocks = (rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    layernorm_kernel<NV><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, stream>>>(x, g, b,
+                                                                              reinterpret_cast<__nv_bfloat16*>(y), rows,
+                                                                              eps);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t layernorm_launch(const float* x, const float* gamma, const float* beta, void* y, long long rows, int d,
+                             float eps, cudaStream_t stream) {
+    if (rows <= 0) return cudaSuccess;
+    if (d % 128 != 0) return cudaErrorInvalidValue;
+    switch (d / 128) {
+        case 1: return launch<1>(x, gamma, beta, y, rows, eps, stream);
+        case 2: return launch<2>(x, gamma, beta, y, rows, eps, stream);
+        case 3: return launch<3>(x, gamma, beta, y, rows, eps, stream);
+        case 4: return launch<4>(x, gamma, beta, y, rows, eps, stream);
+        case 5: return launch<5>(x, gamma, beta, y, rows, eps, stream);
+        case 6: return launch<6>(x, gamma, beta, y, rows, eps, stream);
+        case 8: return launch<8>(x, gamma, beta, y, rows, eps, stream);
+        case 10: return launch<10>(x, gamma, beta, y, rows, eps, stream);
+        case 12: return launch<12>(x, gamma, beta, y, rows, eps, stream);
+        case 16: return launch<16>(x, gamma, beta, y, rows, eps, stream);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace aries

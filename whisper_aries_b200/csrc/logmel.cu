@@ -1,0 +1,433 @@
+// K1: log-mel spectrogram for sm_100a.  One persistent CTA per SM walks 64-frame tiles of the batch.
+//
+// Replaces faster-whisper 1.1.1 FeatureExtractor.__call__ (numpy, host, single thread),
+// which the reference reaches through model.transcribe (ref: final_optimized_transcriber.py:326, warm-up :189).
+//
+// Per tile (see logmel_core.cuh for the transform):
+//   PCM (prefetched into registers during the previous tile's mel phase, coalesced float4, reflect / zero pad
+//   resolved on the fly) -> skewed shared tile -> stage 1 (window, 20-pt FFTs, frame separation, twiddles)
+//   -> exchange -> stage 2 (20-pt FFTs, |X|^2) -> sparse mel filters -> log10 / scale in registers
+//   -> coalesced stores of (log10(mel) + 4) / 4, plus the running per-item maximum (warp shuffles -> shared
+//   atomics -> one global atomic per tile) and the tile minimum.
+// The "max(x, global_max - 8)" clamp needs the maximum over the WHOLE call, so it is applied by a second, tiny
+// kernel that only rewrites tiles whose minimum is below the threshold (most tiles of real audio are not).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "logmel.h"
+#include "logmel_core.cuh"
+
+namespace aries {
+
+using namespace mel;
+
+namespace {
+
+constexpr int kThreads = 640;                                   // 20 warps = the 20 items of each stage
+constexpr int kPcmWordsPadded = (kPcmWords + 3) & ~3;
+constexpr int kMaxMelWeights = 1024;
+constexpr int kMaxMels = 256;
+constexpr int kFloat4PerTile = kTileSamples / 4;                // 2620
+constexpr int kPrefetch = (kFloat4PerTile + kThreads - 1) / kThreads;   // 5 float4 per thread
+
+__constant__ Tables c_tables;
+
+struct Smem {
+    float pcm[2][kPcmWordsPadded];
+    float e_re[kExchangeFloat2];      // P (201 x 64 floats) aliases e_re/e_im
+    float e_im[kExchangeFloat2];
+    float melw[kMaxMelWeights];
+    short mstart[kMaxMels];
+    short mcount[kMaxMels];
+    short moffset[kMaxMels];
+    unsigned red_max;
+    unsigned red_min;
+};
+static_assert(kPowerFloats <= 2 * kExchangeFloat2, "power tile must fit in the exchange buffer");
+static_assert(sizeof(Smem) <= 227 * 1024, "shared memory budget");
+
+__device__ __forceinline__ unsigned order_f32(float v) {
+    const unsigned u = __float_as_uint(v);
+    return u ^ ((u >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+__device__ __forceinline__ float unorder_f32(unsigned u) {
+    return __uint_as_float(u ^ ((u >> 31) ? 0x80000000u : 0xFFFFFFFFu));
+}
+
+struct Params {
+    const float* pcm;
+    long long pcm_stride;
+    long long n_samples;
+    long long padded_len;       // n_samples + padding
+    int batch;
+    int n_frames;               // (n_samples + padding) / 160
+    int tiles_per_item;
+    int n_mels;
+    float* out;
+    int frames_out;
+    long long out_stride;       // n_mels * frames_out
+    unsigned* gmax;             // [batch], order_f32 encoded
+    float* tile_min;            // [batch][tiles_per_item]
+    const float* melw;
+    const short* mstart;
+    const short* mcount;
+    const short* moffset;
+    int n_weights;
+};
+
+__device__ __forceinline__ void prefetch_tile(const Params& p, int tile, float4 (&r)[kPrefetch]) {
+    const int b = tile / p.tiles_per_item;
+    const int t = tile - b * p.tiles_per_item;
+    const long long s0 = (long long)t * (kTileFrames * kHop);
+    const float* base = p.pcm + (long long)b * p.pcm_stride;
+    const bool fast = (s0 >= kNfft / 2) && (s0 + kTileSamples - kNfft / 2 <= p.n_samples) &&
+                      ((reinterpret_cast<uintptr_t>(base) & 15) == 0);
+    if (fast) {
+        const float4* src = reinterpret_cast<const float4*>(base + (s0 - kNfft / 2));
+#pragma unroll
+        for (int k = 0; k < kPrefetch; ++k) {
+            const int i4 = threadIdx.x + k * kThreads;
+            if (i4 < kFloat4PerTile) r[k] = __ldg(src + i4);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < kPrefetch; ++k) {
+            const int i4 = threadIdx.x + k * kThreads;
+            if (i4 < kFloat4PerTile) {
+                float v[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const long long j = source_index(s0 + 4 * i4 + c, p.n_samples, p.padded_len);
+                    v[c] = (j >= 0) ? __ldg(base + j) : 0.0f;
+                }
+                r[k] = make_float4(v[0], v[1], v[2], v[3]);
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void store_tile(float* pcm, const float4 (&r)[kPrefetch]) {
+#pragma unroll
+    for (int k = 0; k < kPrefetch; ++k) {
+        const int i4 = threadIdx.x + k * kThreads;
+        if (i4 < kFloat4PerTile) {
+            float* d = pcm + pcm_addr(4 * i4);         // the 4 samples share one 160-block: consecutive words
+            d[0] = r[k].x; d[1] = r[k].y; d[2] = r[k].z; d[3] = r[k].w;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) logmel_tiles_kernel(const Params p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+    float* P = sm.e_re;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int total_tiles = p.batch * p.tiles_per_item;
+
+    for (int i = threadIdx.x; i < p.n_weights; i += kThreads) sm.melw[i] = p.melw[i];
+    for (int i = threadIdx.x; i < p.n_mels; i += kThreads) {
+        sm.mstart[i] = p.mstart[i];
+        sm.mcount[i] = p.mcount[i];
+        sm.moffset[i] = p.moffset[i];
+    }
+    if (threadIdx.x == 0) {
+        sm.red_max = 0u;
+        sm.red_min = 0xFFFFFFFFu;
+    }
+    MelBank bank{sm.melw, sm.mstart, sm.mcount, sm.moffset};
+
+    int tile = blockIdx.x;
+    if (tile < total_tiles) {
+        float4 r[kPrefetch];
+        prefetch_tile(p, tile, r);
+        store_tile(sm.pcm[0], r);
+    }
+    __syncthreads();
+
+    for (int it = 0; tile < total_tiles; tile += gridDim.x, ++it) {
+        const float* cur = sm.pcm[it & 1];
+        float* nxt = sm.pcm[(it & 1) ^ 1];
+        const int b = tile / p.tiles_per_item;
+        const int t = tile - b * p.tiles_per_item;
+
+        stage1(cur, sm.e_re, sm.e_im, c_tables, warp, lane);
+        __syncthreads();
+        {
+            float yr[20], yi[20];
+            stage2_load(sm.e_re, sm.e_im, warp, lane, yr, yi);
+            __syncthreads();                      // every E read is done before P (aliasing E) is written
+            stage2_power(P, warp, lane, yr, yi);
+        }
+        __syncthreads();
+
+        const int next = tile + gridDim.x;
+        const bool has_next = next < total_tiles;
+        float4 r[kPrefetch];
+        if (has_next) prefetch_tile(p, next, r);
+
+        // ---- mel filters + log: warp item = (mel bin, half of the tile), lane = frame
+        float vmax = -INFINITY, vmin = INFINITY;
+        float* out_b = p.out + (long long)b * p.out_stride;
+        for (int item = warp; item < 2 * p.n_mels; item += kThreads / 32) {
+            const int m = item >> 1;
+            const int col = lane + 32 * (item & 1);
+            const int f = t * kTileFrames + col;
+            const float acc = mel_dot(P, bank, m, col);
+            const float v = fmaf(__log2f(fmaxf(acc, 1e-10f)), 0.07525749891599529f, 1.0f);   // (log10 + 4) / 4
+            if (f < p.n_frames) {
+                vmax = fmaxf(vmax, v);
+                vmin = fminf(vmin, v);
+                if (f < p.frames_out) out_b[(long long)m * p.frames_out + f] = v;
+            }
+        }
+        if (has_next) store_tile(nxt, r);
+
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+            vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+        }
+        if (lane == 0) {
+            atomicMax(&sm.red_max, order_f32(vmax));
+            atomicMin(&sm.red_min, order_f32(vmin));
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            atomicMax(p.gmax + b, sm.red_max);
+            p.tile_min[tile] = unorder_f32(sm.red_min);
+            sm.red_max = 0u;
+            sm.red_min = 0xFFFFFFFFu;
+        }
+        // the next write of red_* is three barriers away; the next read of P/E likewise
+    }
+}
+
+// Second pass: x = max(x, max - 2) where needed (== (max(log10, gmax - 8) + 4) / 4), zeros after the last frame
+// when the caller asked for more frames than the audio has (pad_or_trim).
+__global__ void __launch_bounds__(256) logmel_clamp_kernel(const Params p) {
+    const int t = blockIdx.x;
+    const int b = blockIdx.y;
+    const float thr = unorder_f32(p.gmax[b]) - 2.0f;
+    const int f0 = t * kTileFrames;
+    const bool has_tail = f0 + kTileFrames > p.n_frames;               // tile reaches past the last real frame
+    const bool needs_clamp = (t < p.tiles_per_item) && (p.tile_min[b * p.tiles_per_item + t] < thr);
+    if (!has_tail && !needs_clamp) return;
+    float* out_b = p.out + (long long)b * p.out_stride;
+    for (int i = threadIdx.x; i < p.n_mels * kTileFrames; i += blockDim.x) {
+        const int m = i / kTileFrames;
+        const int f = f0 + (i % kTileFrames);
+        if (f >= p.frames_out) continue;
+        float* q = out_b + (long long)m * p.frames_out + f;
+        if (f >= p.n_frames) {
+            *q = 0.0f;
+        } else if (needs_clamp) {
+            const float v = *q;
+            if (v < thr) *q = thr;
+        }
+    }
+}
+
+// [B, n_mels, frames] f32  ->  [B, frames + 2, c_pad] bf16, time-major with one zero row before and after and
+// zero channels beyond n_mels: the layout the conv1 implicit GEMM reads (encoder.cu).
+__global__ void __launch_bounds__(256) mel_to_time_major_kernel(const float* __restrict__ mel, int n_mels, int frames,
+                                                                int frames_in_stride, unsigned short* __restrict__ out,
+                                                                int c_pad) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const int f0 = blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
+    const float* src = mel + (long long)b * n_mels * frames_in_stride;
+    for (int r = ty; r < 32; r += 8) {
+        const int c = c0 + r, f = f0 + tx;
+        tile[r][tx] = (c < n_mels && f < frames) ? src[(long long)c * frames_in_stride + f] : 0.0f;
+    }
+    __syncthreads();
+    unsigned short* dst = out + ((long long)b * (3000 + 2) + 1) * c_pad;
+    for (int r = ty; r < 32; r += 8) {
+        const int f = f0 + r, c = c0 + tx;
+        if (f < 3000 && c < c_pad) {
+            const float v = tile[tx][r];
+            // round-to-nearest-even bf16
+            unsigned u = __float_as_uint(v);
+            u += 0x7FFFu + ((u >> 16) & 1u);
+            dst[(long long)f * c_pad + c] = (unsigned short)(u >> 16);
+        }
+    }
+}
+
+void build_tables(Tables& tb) {
+    const double pi = 3.14159265358979323846;
+    for (int i = 0; i < kNfft; ++i) tb.window[i] = (float)(0.5 - 0.5 * std::cos(2.0 * pi * i / kNfft));
+    for (int k1 = 0; k1 <= 10; ++k1) {
+        for (int n2 = 0; n2 < 20; ++n2) {
+            const double a = 2.0 * pi * (double)(k1 * n2) / 400.0;
+            const double scale = (k1 == 10) ? 2.0 : 1.0;
+            tb.tw_re[k1][n2] = (float)(scale * std::cos(a));
+            tb.tw_im[k1][n2] = (float)(-scale * std::sin(a));
+        }
+    }
+}
+
+}  // namespace
+
+void logmel_host_tables(mel::Tables* tb) { build_tables(*tb); }
+
+struct LogmelPlan {
+    int device = 0;
+    int n_mels = 0;
+    int sm_count = 0;
+    int n_weights = 0;
+    float* d_melw = nullptr;
+    short* d_start = nullptr;
+    short* d_count = nullptr;
+    short* d_offset = nullptr;
+    // scratch, grown on demand
+    unsigned* d_gmax = nullptr;
+    float* d_tile_min = nullptr;
+    int cap_batch = 0;
+    long long cap_tiles = 0;
+};
+
+cudaError_t logmel_plan_create(int device, int sm_count, int n_mels, const float* filters, LogmelPlan** out,
+                               const char** why) {
+    *out = nullptr;
+    if (n_mels <= 0 || n_mels > kMaxMels) {
+        *why = "n_mels out of range (1..256)";
+        return cudaErrorInvalidValue;
+    }
+    std::vector<float> w;
+    std::vector<short> start(n_mels), count(n_mels), offset(n_mels);
+    for (int m = 0; m < n_mels; ++m) {
+        int lo = -1, hi = -1;
+        for (int k = 0; k < kBins; ++k) {
+            if (filters[m * kBins + k] != 0.0f) {
+                if (lo < 0) lo = k;
+                hi = k;
+            }
+        }
+        start[m] = (short)(lo < 0 ? 0 : lo);
+        count[m] = (short)(lo < 0 ? 0 : hi - lo + 1);
+        offset[m] = (short)w.size();
+        for (int k = 0; k < count[m]; ++k) w.push_back(0.25f * filters[m * kBins + lo + k]);   // power carries x4
+    }
+    if ((int)w.size() > kMaxMelWeights) {
+        *why = "mel filter bank too dense for the sparse kernel (more than 1024 taps)";
+        return cudaErrorInvalidValue;
+    }
+    LogmelPlan* pl = new LogmelPlan();
+    pl->device = device;
+    pl->n_mels = n_mels;
+    pl->sm_count = sm_count;
+    pl->n_weights = (int)w.size();
+    cudaError_t e;
+    Tables tb;
+    build_tables(tb);
+    if ((e = cudaMemcpyToSymbol(c_tables, &tb, sizeof(tb))) != cudaSuccess) goto fail;
+    if ((e = cudaFuncSetAttribute(logmel_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)sizeof(Smem))) != cudaSuccess)
+        goto fail;
+    if ((e = cudaMalloc(&pl->d_melw, sizeof(float) * (w.size() + 1))) != cudaSuccess) goto fail;
+    if ((e = cudaMalloc(&pl->d_start, sizeof(short) * n_mels)) != cudaSuccess) goto fail;
+    if ((e = cudaMalloc(&pl->d_count, sizeof(short) * n_mels)) != cudaSuccess) goto fail;
+    if ((e = cudaMalloc(&pl->d_offset, sizeof(short) * n_mels)) != cudaSuccess) goto fail;
+    if ((e = cudaMemcpy(pl->d_melw, w.data(), sizeof(float) * w.size(), cudaMemcpyHostToDevice)) != cudaSuccess) goto fail;
+    if ((e = cudaMemcpy(pl->d_start, start.data(), sizeof(short) * n_mels, cudaMemcpyHostToDevice)) != cudaSuccess) goto fail;
+    if ((e = cudaMemcpy(pl->d_count, count.data(), sizeof(short) * n_mels, cudaMemcpyHostToDevice)) != cudaSuccess) goto fail;
+    if ((e = cudaMemcpy(pl->d_offset, offset.data(), sizeof(short) * n_mels, cudaMemcpyHostToDevice)) != cudaSuccess) goto fail;
+    *out = pl;
+    return cudaSuccess;
+fail:
+    *why = cudaGetErrorString(e);
+    logmel_plan_destroy(pl);
+    return e;
+}
+
+void logmel_plan_destroy(LogmelPlan* pl) {
+    if (!pl) return;
+    cudaFree(pl->d_melw);
+    cudaFree(pl->d_start);
+    cudaFree(pl->d_count);
+    cudaFree(pl->d_offset);
+    cudaFree(pl->d_gmax);
+    cudaFree(pl->d_tile_min);
+    delete pl;
+}
+
+int logmel_plan_n_mels(const LogmelPlan* pl) { return pl->n_mels; }
+
+cudaError_t logmel_run(LogmelPlan* pl, const float* pcm, int batch, long long n_samples, long long pcm_stride,
+                       int padding, float* out, int frames_out, cudaStream_t stream, int* launches) {
+    const long long padded = n_samples + padding;
+    const int n_frames = (int)(padded / kHop);
+    const int tiles = (n_frames + kTileFrames - 1) / kTileFrames;
+    cudaError_t e;
+    if (batch > pl->cap_batch || (long long)batch * tiles > pl->cap_tiles) {
+        // growing the scratch synchronises; steady-state calls with the same shape do not
+        if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
+        cudaFree(pl->d_gmax);
+        cudaFree(pl->d_tile_min);
+        pl->d_gmax = nullptr;
+        pl->d_tile_min = nullptr;
+        pl->cap_batch = 0;
+        pl->cap_tiles = 0;
+        if ((e = cudaMalloc(&pl->d_gmax, sizeof(unsigned) * batch)) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&pl->d_tile_min, sizeof(float) * (size_t)batch * (tiles > 0 ? tiles : 1))) != cudaSuccess)
+            return e;
+        pl->cap_batch = batch;
+        pl->cap_tiles = (long long)batch * tiles;
+    }
+    Params p{};
+    p.pcm = pcm;
+    p.pcm_stride = pcm_stride;
+    p.n_samples = n_samples;
+    p.padded_len = padded;
+    p.batch = batch;
+    p.n_frames = n_frames;
+    p.tiles_per_item = tiles;
+    p.n_mels = pl->n_mels;
+    p.out = out;
+    p.frames_out = frames_out;
+    p.out_stride = (long long)pl->n_mels * frames_out;
+    p.gmax = pl->d_gmax;
+    p.tile_min = pl->d_tile_min;
+    p.melw = pl->d_melw;
+    p.mstart = pl->d_start;
+    p.mcount = pl->d_count;
+    p.moffset = pl->d_offset;
+    p.n_weights = pl->n_weights;
+    int n_launch = 0;
+    if ((e = cudaMemsetAsync(pl->d_gmax, 0, sizeof(unsigned) * batch, stream)) != cudaSuccess) return e;
+    const long long total = (long long)batch * tiles;
+    if (total > 0) {
+        const int grid = (int)(total < pl->sm_count ? total : pl->sm_count);
+        logmel_tiles_kernel<<<grid, kThreads, sizeof(Smem), stream>>>(p);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        ++n_launch;
+    }
+    const int out_tiles = (frames_out + kTileFrames - 1) / kTileFrames;
+    const int clamp_tiles = out_tiles > tiles ? out_tiles : tiles;
+    if (clamp_tiles > 0 && frames_out > 0) {
+        logmel_clamp_kernel<<<dim3(clamp_tiles, batch), 256, 0, stream>>>(p);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        ++n_launch;
+    }
+    if (launches) *launches = n_launch;
+    return cudaSuccess;
+}
+
+cudaError_t mel_to_time_major(const float* mel, int batch, int n_mels, int frames, void* out_bf16, int c_pad,
+                              cudaStream_t stream) {
+    dim3 grid((3000 + 31) / 32, (c_pad + 31) / 32, batch);
+    mel_to_time_major_kernel<<<grid, 256, 0, stream>>>(mel, n_mels, frames, frames,
+                                                       reinterpret_cast<unsigned short*>(out_bf16), c_pad);
+    return cudaGetLastError();
+}
+
+}  // namespace aries

@@ -1,0 +1,144 @@
+"""``encode`` half of ``faster_whisper.WhisperModel`` / ``ctranslate2.models.Whisper`` on a B200.
+
+Upstream: ``WhisperModel.encode(features)`` -> ``ctranslate2.models.Whisper.encode`` -> ``layers::WhisperEncoder``
+(SURVEY.md rows a-5..a-8), reached by the reference through ``model.transcribe`` (ref:
+final_optimized_transcriber.py:326; model built at :179-182 and forced to large-v3 at conversation_transcriber.py:72).
+Here the forward pass is hand-written sm_100a CUDA (tcgen05 GEMMs with fused epilogues, fused attention, LayerNorm)
+behind ``aries_encoder_run``; this file only moves pointers."""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from .feature_extractor import FeatureExtractor
+from .synthetic import SHAPES, EncoderShape
+
+
+class WhisperEncoder:
+    """Owns one ``aries_encoder`` handle (weights resident on one GPU) plus a growable device workspace."""
+
+    def __init__(self, shape: EncoderShape | str, weights: dict, device="cuda:0"):
+        import torch
+        self.shape = SHAPES[shape] if isinstance(shape, str) else shape
+        self.device_index = _lib.device_index_of(device)
+        self.device = torch.device("cuda", self.device_index)
+        self._ctx = _lib.Context.get(self.device_index)
+        lib = self._ctx.lib
+        cfg = _lib.EncoderCfg(self.shape.n_mels, self.shape.d_model, self.shape.n_heads, self.shape.n_layers,
+                              self.shape.d_ffn, self.shape.n_ctx)
+        keep, descs = [], (_lib.WeightDesc * len(weights))()
+        for i, (name, arr) in enumerate(weights.items()):
+            a = np.ascontiguousarray(np.asarray(arr), dtype=np.float32)
+            if a.ndim < 1 or a.ndim > 4:
+                raise ValueError(f"weight {name!r} has unsupported rank {a.ndim}")
+            keep.append(a)
+            descs[i].name = name.encode()
+            descs[i].data = a.ctypes.data
+            descs[i].ndim = a.ndim
+            for k in range(4):
+                descs[i].shape[k] = a.shape[k] if k < a.ndim else 1
+        h = ctypes.c_void_p()
+        _lib.check(lib.aries_encoder_create(self._ctx.handle, ctypes.byref(cfg), descs, len(weights), ctypes.byref(h)))
+        self._handle = h
+        self._ws = None
+        self._ws_batch = 0
+
+    def close(self):
+        if getattr(self, "_handle", None) is not None:
+            self._ctx.lib.aries_encoder_destroy(self._handle)
+            self._handle = None
+            self._ws = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def last_launches(self) -> int:
+        return self._ctx.lib.aries_encoder_last_launches(self._handle)
+
+    def workspace_bytes(self, batch: int) -> int:
+        return int(self._ctx.lib.aries_encoder_workspace_bytes(self._handle, batch))
+
+    def _workspace(self, batch: int):
+        import torch
+        if self._ws is None or batch > self._ws_batch:
+            self._ws = None
+            self._ws = torch.empty(self.workspace_bytes(batch), dtype=torch.uint8, device=self.device)
+            self._ws_batch = batch
+        return self._ws
+
+    def _check(self, shape) -> None:
+        if len(shape) != 3 or shape[1] != self.shape.n_mels or shape[2] > 3000 or shape[2] == 0 or shape[0] == 0:
+            raise ValueError(f"Invalid input features shape: expected an input with shape (batch, {self.shape.n_mels}, "
+                             f"<=3000), but got {tuple(shape)}")
+
+    def encode(self, features):
+        """features f32 ``[n_mels, frames]`` / ``[B, n_mels, frames]`` (numpy or torch, host or device), frames <= 3000
+        -> CUDA bf16 tensor ``[B, 1500, d_model]`` (device-resident, like upstream's StorageView)."""
+        import torch
+        if isinstance(features, torch.Tensor):
+            x = features
+        else:
+            x = torch.from_numpy(np.ascontiguousarray(np.asarray(features), dtype=np.float32))
+        if x.dim() == 2:
+            x = x[None]
+        self._check(tuple(x.shape))
+        x = x.to(device=self.device, dtype=torch.float32, non_blocking=True).contiguous()
+        batch, _, frames = x.shape
+        ws = self._workspace(batch)
+        out = torch.empty((batch, self.shape.n_ctx, self.shape.d_model), dtype=torch.bfloat16, device=self.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self._ctx.lib.aries_encoder_run(self._handle, x.data_ptr(), batch, frames, out.data_ptr(),
+                                                   ws.data_ptr(), ws.numel(), stream))
+        return out
+
+    def encode_pcm(self, extractor: FeatureExtractor, pcm, out=None):
+        """Fused PCM -> log-mel -> encoder for a CUDA f32 tensor ``[B, n_samples <= 480000]``; the mel tensor never
+        leaves the GPU.  Returns CUDA bf16 ``[B, 1500, d_model]``."""
+        import torch
+        if not (isinstance(pcm, torch.Tensor) and pcm.is_cuda and pcm.dtype == torch.float32):
+            raise ValueError("encode_pcm expects a CUDA float32 tensor [batch, n_samples]")
+        if pcm.dim() == 1:
+            pcm = pcm[None]
+        if pcm.stride(1) != 1:
+            pcm = pcm.contiguous()
+        batch, n = pcm.shape
+        ws = self._workspace(batch)
+        if out is None:
+            out = torch.empty((batch, self.shape.n_ctx, self.shape.d_model), dtype=torch.bfloat16, device=self.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self._ctx.lib.aries_encode_pcm(self._handle, extractor._mel(), pcm.data_ptr(), batch, n,
+                                                  pcm.stride(0), out.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+        return out
+
+
+class WhisperModel:
+    """The slice of ``faster_whisper.WhisperModel`` on the hot path: ``feature_extractor`` + ``encode``.
+
+    ``WhisperModel("large-v3", weights=..., device="cuda", device_index=0)`` mirrors the reference's construction
+    (ref: final_optimized_transcriber.py:179-182).  ``compute_type`` is accepted for signature compatibility; the
+    B200 path always computes in bf16 with f32 accumulation.  Decoding (``transcribe`` / ``generate``) is out of
+    scope for this library."""
+
+    def __init__(self, model_size_or_shape, weights: dict, device: str = "cuda", device_index: int = 0,
+                 compute_type: str = "bfloat16", **_ignored):
+        if device not in ("cuda", "auto"):
+            raise ValueError("whisper_aries_b200 has no CPU path: device must be 'cuda'")
+        dev = f"cuda:{device_index}"
+        shape = SHAPES[model_size_or_shape] if isinstance(model_size_or_shape, str) else model_size_or_shape
+        self.shape = shape
+        self.compute_type = compute_type
+        self.feature_extractor = FeatureExtractor(feature_size=shape.n_mels, device=dev)
+        self.encoder = WhisperEncoder(shape, weights, device=dev)
+
+    def encode(self, features):
+        return self.encoder.encode(features)
+
+    def encode_audio(self, pcm):
+        """PCM windows (CUDA f32 ``[B, <=480000]``) -> encoder states, fused on the device."""
+        return self.encoder.encode_pcm(self.feature_extractor, pcm)

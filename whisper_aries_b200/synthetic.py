@@ -1,0 +1,121 @@
+"""Deterministic synthetic audio and random-init encoder weights.
+
+No dataset or checkpoint exists offline, so bench.py / smoke() / the tests feed the kernels with these generators.
+Weight names follow CTranslate2's Whisper variables ("encoder/layer_3/ffn/linear_0/weight", ...), i.e. what a
+model.bin loader would hand to ``WhisperEncoder``."""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import numpy as np
+
+SAMPLE_RATE = 16000
+N_SAMPLES = 480000
+
+
+@dataclass(frozen=True)
+class EncoderShape:
+    name: str
+    n_mels: int
+    d_model: int
+    n_heads: int
+    n_layers: int
+    d_ffn: int
+    n_ctx: int = 1500
+
+    @property
+    def flops_per_window(self) -> float:
+        """2 * MACs of the conv stem + all layers for one 30-s window."""
+        d, t = self.d_model, self.n_ctx
+        conv = 2 * self.n_mels * 3 * d * 3000 + 2 * d * 3 * d * 1500
+        layer = 8 * t * d * d + 4 * t * t * d + 4 * t * d * self.d_ffn
+        return float(conv + self.n_layers * layer)
+
+
+SHAPES = {
+    "tiny": EncoderShape("tiny", 80, 384, 6, 4, 1536),
+    "medium": EncoderShape("medium", 80, 1024, 16, 24, 4096),
+    "large-v3": EncoderShape("large-v3", 128, 1280, 20, 32, 5120),
+    # not a Whisper size: the smallest shape every kernel tiling accepts, for fast parity tests
+    "micro": EncoderShape("micro", 80, 128, 2, 2, 512),
+}
+
+
+def tone_noise(seed: int, n: int = N_SAMPLES) -> np.ndarray:
+    rng = np.random.default_rng(seed)
+    t = np.arange(n) / SAMPLE_RATE
+    return (0.3 * np.sin(2 * np.pi * 220.0 * t) + 0.05 * rng.standard_normal(n)).astype(np.float32)
+
+
+def am_chirp(seed: int, n: int = N_SAMPLES) -> np.ndarray:
+    rng = np.random.default_rng(seed)
+    t = np.arange(n) / SAMPLE_RATE
+    car = np.sin(2 * np.pi * (200.0 * t + 40.0 * t * t))
+    env = 0.5 + 0.5 * np.sin(2 * np.pi * 3.0 * t)
+    return (0.3 * car * env + 1e-3 * rng.standard_normal(n)).astype(np.float32)
+
+
+def gapped(seed: int, n: int = N_SAMPLES) -> np.ndarray:
+    rng = np.random.default_rng(seed)
+    x = tone_noise(seed + 1000, n)
+    seg = SAMPLE_RATE // 2
+    n_seg = (n + seg - 1) // seg
+    silent = rng.random(n_seg) < 0.3
+    mask = np.repeat(~silent, seg)[:n]
+    return (x * mask).astype(np.float32)
+
+
+def window_signal(seed: int, n: int = N_SAMPLES) -> np.ndarray:
+    kind = seed % 3
+    if kind == 0:
+        return tone_noise(seed, n)
+    if kind == 1:
+        return am_chirp(seed, n)
+    return gapped(seed, n)
+
+
+def batch_signals(n_windows: int, first_seed: int = 0, n: int = N_SAMPLES) -> np.ndarray:
+    return np.stack([window_signal(first_seed + i, n) for i in range(n_windows)])
+
+
+def sinusoids(length: int, channels: int, max_timescale: float = 10000.0) -> np.ndarray:
+    inc = math.log(max_timescale) / (channels // 2 - 1)
+    inv = np.exp(-inc * np.arange(channels // 2))
+    ang = np.arange(length)[:, None] * inv[None, :]
+    return np.concatenate([np.sin(ang), np.cos(ang)], axis=1).astype(np.float32)
+
+
+def encoder_weights(shape: EncoderShape, seed: int = 1234) -> dict[str, np.ndarray]:
+    """N(0, 0.02^2) weights and biases (key bias zero), LayerNorm gamma = 1 + N(0, 0.02^2), sinusoidal positions."""
+    rng = np.random.default_rng(seed)
+    d, f = shape.d_model, shape.d_ffn
+
+    def nrm(*s):
+        return (0.02 * rng.standard_normal(s)).astype(np.float32)
+
+    w: dict[str, np.ndarray] = {}
+    w["encoder/conv1/weight"] = nrm(d, shape.n_mels, 3)
+    w["encoder/conv1/bias"] = nrm(d)
+    w["encoder/conv2/weight"] = nrm(d, d, 3)
+    w["encoder/conv2/bias"] = nrm(d)
+    w["encoder/position_encodings/encodings"] = sinusoids(shape.n_ctx, d)
+    for i in range(shape.n_layers):
+        p = f"encoder/layer_{i}"
+        w[f"{p}/self_attention/layer_norm/gamma"] = (1.0 + nrm(d)).astype(np.float32)
+        w[f"{p}/self_attention/layer_norm/beta"] = nrm(d)
+        w[f"{p}/self_attention/linear_0/weight"] = nrm(3 * d, d)
+        b = nrm(3 * d)
+        b[d:2 * d] = 0.0
+        w[f"{p}/self_attention/linear_0/bias"] = b
+        w[f"{p}/self_attention/linear_1/weight"] = nrm(d, d)
+        w[f"{p}/self_attention/linear_1/bias"] = nrm(d)
+        w[f"{p}/ffn/layer_norm/gamma"] = (1.0 + nrm(d)).astype(np.float32)
+        w[f"{p}/ffn/layer_norm/beta"] = nrm(d)
+        w[f"{p}/ffn/linear_0/weight"] = nrm(f, d)
+        w[f"{p}/ffn/linear_0/bias"] = nrm(f)
+        w[f"{p}/ffn/linear_1/weight"] = nrm(d, f)
+        w[f"{p}/ffn/linear_1/bias"] = nrm(d)
+    w["encoder/layer_norm/gamma"] = (1.0 + nrm(d)).astype(np.float32)
+    w["encoder/layer_norm/beta"] = nrm(d)
+    return w
