@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""Hot-path benchmark: log-mel + Whisper large-v3 encoder over 30-s windows, audio-seconds per second.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--windows 64] [--model large-v3]
+
+A step = one pass of the hot path over one batch of synthetic 30-s / 16 kHz windows per GPU (BASELINE.json config 3:
+"large-v3 batch of 64 x 30-s chunks"; weak scaling: every rank owns 64 windows, no collective on the data path).
+  value   whole-job audio-s/s with the PCM already resident in HBM (fused PCM -> log-mel -> encoder on the device)
+  e2e     the same metric through the public API with HOST buffers: pinned PCM -> H2D -> kernels -> D2H of the bf16
+          encoder states, copies inside the timed region (chunk scheduler, double-buffered micro-batches)
+  roofline        the dominant kernel (tcgen05 GEMM, all launches of the step) against the measured bf16 peak
+  roofline_mel    the log-mel kernel against the measured HBM bandwidth (BASELINE.json: "mel GB/s vs HBM")
+  cpu_baseline    the CPU oracle (numpy log-mel + torch fp32 encoder: a port of the reference's algorithm, since
+                  faster-whisper / ctranslate2 are not installable offline) on a bounded sample, host cores
+Under torchrun (N > 1) every rank runs the same loop on its own GPU; time = max over ranks."""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "audio-sec/sec (log-mel+encoder, large-v3)"
+UNIT = "audio-s/s"
+WINDOW_SECONDS = 30.0
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def load_traffic():
+    """dram bytes per launch from the committed ncu --set full captures (profiles/traffic.json), if any."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    return json.load(open(path)) if os.path.exists(path) else {}
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons while the timed region runs (pynvml; nvidia-smi as a fallback)."""
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+
+    def _run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+                     "hw_power_brake_slowdown": 0x80, "sync_boost": 0x10, "applications_clocks_setting": 0x2}
+            while not self._stop.is_set():
+                self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                try:
+                    r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+                self._stop.wait(0.05)
+        except Exception as exc:                                   # pragma: no cover
+            self.reasons.add(f"sampler_error:{type(exc).__name__}")
+
+    def __enter__(self):
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._thread.join(timeout=2)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def cpu_reference_step(n_windows: int, model: str, seed0: int = 0):
+    """The reference algorithm on the host cores: oracle log-mel (numpy) + oracle encoder (torch fp32, all threads).
+    This is the ONLY place bench.py executes oracle/ code, and only as the thing timed for the CPU baseline."""
+    import numpy as np
+    import torch
+    from oracle import encoder as oenc, logmel as omel, synth as osynth
+    shape = osynth.SHAPES[model]
+    w = cpu_reference_step.cache.get(model)
+    if w is None:
+        w = {k: torch.from_numpy(v) for k, v in osynth.encoder_weights(shape, 1234).items()}
+        cpu_reference_step.cache[model] = w
+    pcm = osynth.batch_signals(n_windows, seed0)
+    t0 = time.perf_counter()
+    feats = np.stack([omel.log_mel_window(x, shape.n_mels) for x in pcm])
+    t1 = time.perf_counter()
+    out = oenc.encoder_forward(feats, w, shape)
+    t2 = time.perf_counter()
+    return {"mel_s": t1 - t0, "enc_s": t2 - t1, "total_s": t2 - t0, "checksum": float(out.abs().mean())}
+
+
+cpu_reference_step.cache = {}
+
+
+def reference_backend():
+    """faster-whisper / ctranslate2 if some future image has them (also under baseline/_ref); otherwise the port."""
+    sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref"))
+    try:
+        import ctranslate2  # noqa: F401
+        import faster_whisper  # noqa: F401
+        return "reference"
+    except Exception:
+        return "port"
+    finally:
+        sys.path.pop(0)
+
+
+def run_reference(args, rank: int, world: int) -> int:
+    if rank != 0:
+        return 0
+    import torch
+    kind = reference_backend()
+    # (a real faster-whisper leg would need CT2-format weights; with random-init weights only the port can run)
+    sample_windows = 1
+    for _ in range(args.warmup):
+        cpu_reference_step(sample_windows, args.model)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_reference_step(sample_windows, args.model)
+    dt = time.perf_counter() - t0
+    value = args.steps * sample_windows * WINDOW_SECONDS / dt
+    cores = torch.get_num_threads()
+    sample = (f"{sample_windows} synthetic 30-s window per step (numpy log-mel + torch fp32 encoder, {args.model} shape, "
+              f"random-init weights); faster-whisper/ctranslate2 importable: {kind == 'reference'}")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.model} log-mel+encoder, {args.windows} x 30-s windows per GPU per step "
+                                   f"(reference arm: bounded sample of {sample_windows} window per step on the host CPU)",
+                       "windows_per_gpu": args.windows, "window_seconds": 30, "sample_rate": 16000},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main() -> int:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--windows", type=int, default=64, help="30-s windows per GPU per step")
+    ap.add_argument("--micro-batch", type=int, default=16, help="windows per H2D/compute/D2H micro-batch (e2e leg)")
+    ap.add_argument("--model", default="large-v3")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: whisper_aries_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)      # timing barrier / max only; the data path has no collective
+
+    from whisper_aries_b200 import WhisperModel, _lib, synthetic
+    from whisper_aries_b200.scheduler import ChunkScheduler, gpu_worker, partition_windows
+
+    shape = synthetic.SHAPES[args.model]
+    B = args.windows
+    weights = synthetic.encoder_weights(shape, 1234)
+    model = WhisperModel(shape, weights, device="cuda", device_index=local_rank)
+    del weights
+
+    # this rank's shard of the job's windows (static contiguous partition; the seeds make every window distinct)
+    start, stop = partition_windows(B * world, world)[rank]
+    base = synthetic.batch_signals(min(B, 12), first_seed=start)          # 12 distinct generators, cycled to B windows
+    pcm_host = torch.from_numpy(np.concatenate([base] * (-(-B // base.shape[0])))[:B].copy()).pin_memory()
+    pcm_dev = pcm_host.to(dev)
+    out_dev = torch.empty((B, shape.n_ctx, shape.d_model), dtype=torch.bfloat16, device=dev)
+    out_host = torch.empty((B, shape.n_ctx, shape.d_model), dtype=torch.bfloat16).pin_memory()
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step_resident():
+        model.encoder.encode_pcm(model.feature_extractor, pcm_dev, out=out_dev)
+
+    # ---------------------------------------------------------------- resident leg (value) with per-kernel events
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    model.encoder.set_profiling(True)
+    model.encoder.collect_profile()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            step_resident()
+        ev1.record()
+        barrier()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    prof = model.encoder.collect_profile()
+    model.encoder.set_profiling(False)
+    launches_per_step = model.feature_extractor.last_launches + model.encoder.last_launches
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    value = world * B * WINDOW_SECONDS * args.steps / (elapsed_ms * 1e-3)
+
+    # ---------------------------------------------------------------- e2e leg: host buffers through the scheduler
+    e2e = None
+    if not args.no_e2e:
+        sched = ChunkScheduler([gpu_worker(model, micro_batch=args.micro_batch)])
+
+        def step_e2e():
+            res = sched.run(pcm_host, out_host)
+            if not all(r.success for r in res):
+                raise RuntimeError(f"e2e step failed: {[r.error for r in res if not r.success]}")
+
+        for _ in range(max(1, min(args.warmup, 2))):
+            step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_e2e()
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * B * WINDOW_SECONDS * args.steps / float(t.item()), "unit": UNIT,
+               "h2d_bytes_per_step": int(pcm_host.numel() * 4), "d2h_bytes_per_step": int(out_host.numel() * 2),
+               "api": "ChunkScheduler(gpu_worker(WhisperModel)).run(pinned pcm, pinned out)",
+               "micro_batch": args.micro_batch}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---------------------------------------------------------------- roofline objects (rank 0's kernels)
+    peaks = load_peaks()
+    traffic = load_traffic()
+    d, f, T, L = shape.d_model, shape.d_ffn, shape.n_ctx, shape.n_layers
+    c_pad = (shape.n_mels + 63) // 64 * 64
+    gemm_flops_per_step = B * (2.0 * 3000 * 3 * c_pad * d + 2.0 * T * 3 * d * d
+                               + L * (2.0 * T * d * 3 * d + 2.0 * T * d * d + 4.0 * T * d * f))
+    gemm_classes = ["conv1_gemm", "conv2_gemm", "qkv_gemm", "oproj_gemm", "fc1_gemm", "fc2_gemm"]
+    gemm_ms = sum(prof[k][0] for k in gemm_classes)
+    gemm_launches = sum(prof[k][1] for k in gemm_classes)
+    gemm_tflops = gemm_flops_per_step * args.steps / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    peak_tf = peaks["bf16_tflops_sustained"]
+    roofline = {"kernel": "gemm_bf16_tcgen05 (all GEMM launches of the step: conv stem, QKV, out-proj, fc1, fc2)",
+                "bound": "tensor", "achieved": gemm_tflops, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": gemm_tflops / peak_tf, "peak_source": f"{peaks['source']} (sustained bf16 GEMM)",
+                "flops_per_launch": gemm_flops_per_step * args.steps / max(gemm_launches, 1),
+                "ms_per_launch": gemm_ms / max(gemm_launches, 1), "launches": gemm_launches,
+                "traffic": traffic.get("gemm_bf16_tcgen05")}
+    mel_bytes = B * (480000 * 4 + shape.n_mels * 3000 * 4)
+    mel_ms, mel_n = prof["logmel_tiles"]
+    mel_gbs = mel_bytes * mel_n / (mel_ms * 1e-3) / 1e9 if mel_ms > 0 else 0.0
+    roofline_mel = {"kernel": "logmel_tiles_kernel", "bound": "hbm", "achieved": mel_gbs, "peak": peaks["hbm_gbs"],
+                    "unit": "GB/s", "frac": mel_gbs / peaks["hbm_gbs"], "peak_source": peaks["source"],
+                    "bytes_per_launch": mel_bytes, "ms_per_launch": mel_ms / max(mel_n, 1),
+                    "traffic": traffic.get("logmel_tiles_kernel")}
+    attn_ms, attn_n = prof["attention"]
+    attn_flops = B * 4.0 * T * T * d
+    kernels = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps} for k, v in prof.items()}
+    kernels["attention"]["tflops"] = attn_flops * attn_n / (attn_ms * 1e-3) / 1e12 if attn_ms > 0 else 0.0
+    encoder_tflops = B * shape.flops_per_window * args.steps / (elapsed_ms * 1e-3) / 1e12
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        import torch as _t
+        n_sample = 2 if args.model == "large-v3" else 4
+        cpu_reference_step(1, args.model)                             # warm the weights / thread pool
+        r = cpu_reference_step(n_sample, args.model)
+        cpu_baseline = {"value": n_sample * WINDOW_SECONDS / r["total_s"], "unit": UNIT, "cores": _t.get_num_threads(),
+                        "kind": "port",
+                        "sample": f"{n_sample} windows of the same workload: numpy log-mel {r['mel_s']:.2f} s + torch fp32 "
+                                  f"encoder {r['enc_s']:.2f} s (oracle port; faster-whisper/ctranslate2 not installable offline)"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{args.model} log-mel+encoder, {B} x 30-s windows per GPU per step (BASELINE.json config 3)",
+                       "windows_per_gpu": B, "window_seconds": 30, "sample_rate": 16000, "n_mels": shape.n_mels,
+                       "d_model": d, "layers": L, "parallelism": f"data-parallel over windows, {world} rank(s), no collective",
+                       "l2": "per-step working set (PCM 123 MB + ~3.3 GB of activations) exceeds the 126 MB L2; no flush needed"},
+            "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
+            "roofline": roofline, "roofline_mel": roofline_mel, "encoder_tflops": encoder_tflops,
+            "encoder_frac_of_bf16_peak": encoder_tflops / peak_tf, "kernels": kernels, "cpu_baseline": cpu_baseline}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -127,6 +127,15 @@ ARIES_API int aries_encode_pcm(aries_encoder* enc, aries_mel* mel, const float* 
 ARIES_API int aries_logmel_last_launches(const aries_mel* mel);
 ARIES_API int aries_encoder_last_launches(const aries_encoder* enc);
 
+/* Per-kernel timing for the benchmark's roofline report (no upstream counterpart). When on, every kernel launched by
+ * aries_encoder_run / aries_encode_pcm is bracketed by CUDA events on the launching stream.
+ * aries_encoder_collect_profile synchronises on them and ADDS, per kernel class, the elapsed milliseconds to ms[i]
+ * and the number of launches to counts[i]; n must be >= ARIES_KERNEL_CLASSES. Class order: log-mel tiles,
+ * log-mel clamp, mel transpose, conv1, conv2, layer norm, qkv projection, attention, output projection, fc1, fc2. */
+#define ARIES_KERNEL_CLASSES 11
+ARIES_API int aries_encoder_set_profiling(aries_encoder* enc, int on);
+ARIES_API int aries_encoder_collect_profile(aries_encoder* enc, float* ms, int* counts, int n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,105 @@
+"""GPU parity: the encoder forward through the drop-in surface (WhisperModel.encode / aries_encoder_run) against the
+fp32 torch oracle, the golden fixtures (oracle + HF transformers) and the greedy-decode probe.
+Tolerances (north_star: "within bf16 tolerance, max-abs error and cosine >= 0.999 stated"): outputs are LayerNorm-ed
+(unit scale); we require cosine >= 0.999 on the whole tensor AND on the worst row, and max-abs <= 0.12."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import encoder as oenc, logmel as omel, synth as osynth
+from oracle.decoder import GreedyProbe
+
+pytestmark = pytest.mark.gpu
+MAX_ABS, COS = 0.12, 0.999
+
+
+def model_for(name):
+    from whisper_aries_b200 import WhisperModel, synthetic
+    shape = synthetic.SHAPES[name]
+    w = synthetic.encoder_weights(shape, 1234)
+    return WhisperModel(name, w, device="cuda", device_index=0), shape, w
+
+
+@pytest.fixture(scope="module")
+def gold(golden_dir):
+    return np.load(os.path.join(golden_dir, "encoder_golden.npz"))
+
+
+@pytest.mark.parametrize("name", ["micro", "tiny"])
+def test_encoder_vs_oracle_golden_and_tokens(gold, name):
+    model, shape, w = model_for(name)
+    feats = np.stack([omel.log_mel_window(osynth.window_signal(s), shape.n_mels) for s in (0, 1)])
+    out = model.encode(feats)
+    assert out.shape == (2, 1500, shape.d_model) and out.dtype == torch.bfloat16 and out.is_cuda
+    ref = oenc.encoder_forward(feats, w, shape)
+    cmp = oenc.compare(out.cpu(), ref)
+    assert cmp["cosine"] >= COS and cmp["min_row_cosine"] >= COS and cmp["max_abs"] <= MAX_ABS, cmp
+    pick = out.cpu().float()[:, ::50, ::8].numpy()
+    assert np.abs(pick - gold[f"{name}_out_pick"]).max() <= MAX_ABS              # committed oracle output
+    assert np.abs(pick - gold[f"{name}_hf_pick"]).max() <= MAX_ABS               # HF transformers' WhisperEncoder
+    probe, toks, margin = GreedyProbe.pick(ref, shape.d_model, shape.n_heads)
+    got, _ = probe.greedy(out.cpu())
+    assert np.array_equal(toks.numpy(), gold[f"{name}_probe_tokens"])
+    assert torch.equal(got[:, : toks.shape[1]], toks), "greedy token IDs differ from the oracle's"
+    # a single [n_mels, 3000] window (upstream's call shape) gives the same rows as the batch
+    one = model.encode(feats[1])
+    assert torch.equal(one[0], out[1])
+
+
+def test_fused_pcm_path_and_short_inputs():
+    model, shape, w = model_for("micro")
+    pcm = osynth.batch_signals(3, 40)
+    feats = np.stack([omel.log_mel_window(x, shape.n_mels) for x in pcm])
+    ref = oenc.encoder_forward(feats, w, shape)
+    fused = model.encode_audio(torch.from_numpy(pcm).cuda())
+    cmp = oenc.compare(fused.cpu(), ref)
+    assert cmp["cosine"] >= COS and cmp["max_abs"] <= MAX_ABS, cmp
+    two_step = model.encode(model.feature_extractor(torch.from_numpy(pcm).cuda(), frames_out=3000))
+    assert torch.equal(two_step, fused)
+    # fewer than 3000 frames: CT2 pads with zeros, so must we
+    short = model.encode(feats[:1, :, :1000])
+    padded = feats[:1].copy()
+    padded[:, :, 1000:] = 0
+    assert torch.equal(short, model.encode(padded))
+
+
+def test_invalid_feature_shapes_raise_value_error():
+    model, shape, _ = model_for("micro")
+    with pytest.raises(ValueError, match="Invalid input features shape"):
+        model.encode(np.zeros((1, shape.n_mels + 1, 3000), np.float32))
+    with pytest.raises(ValueError, match="Invalid input features shape"):
+        model.encode(np.zeros((1, shape.n_mels, 3001), np.float32))
+
+
+def test_missing_weight_is_reported():
+    from whisper_aries_b200 import WhisperEncoder, synthetic
+    shape = synthetic.SHAPES["micro"]
+    w = synthetic.encoder_weights(shape)
+    del w["encoder/layer_1/ffn/linear_1/bias"]
+    with pytest.raises(ValueError, match="missing weight: encoder/layer_1/ffn/linear_1/bias"):
+        WhisperEncoder(shape, w)
+
+
+def test_large_v3_single_window_vs_oracle():
+    """BASELINE config 2: one 30-s window at the large-v3 shape, bf16 on the GPU vs the fp32 CPU oracle."""
+    model, shape, w = model_for("large-v3")
+    feats = omel.log_mel_window(osynth.am_chirp(1), shape.n_mels)[None]
+    out = model.encode(feats)
+    ref = oenc.encoder_forward(feats, w, shape)
+    cmp = oenc.compare(out.cpu(), ref)
+    assert cmp["cosine"] >= COS and cmp["min_row_cosine"] >= 0.995 and cmp["max_abs"] <= 0.2, cmp
+    probe, toks, margin = GreedyProbe.pick(ref, shape.d_model, shape.n_heads, steps=12, max_tries=64, n_layers=1)
+    got, _ = probe.greedy(out.cpu(), steps=12)
+    assert torch.equal(got, toks)
+
+
+def test_scheduler_on_one_gpu_matches_direct_call():
+    from whisper_aries_b200.scheduler import ChunkScheduler, gpu_worker
+    model, shape, _ = model_for("micro")
+    pcm = osynth.batch_signals(5, 60)
+    direct = model.encode_audio(torch.from_numpy(pcm).cuda()).cpu()
+    out = torch.empty((5, 1500, shape.d_model), dtype=torch.bfloat16).pin_memory()
+    res = ChunkScheduler([gpu_worker(model, micro_batch=2)]).run(torch.from_numpy(pcm).pin_memory(), out)
+    assert all(r.success for r in res) and torch.equal(out, direct)

@@ -1,0 +1,111 @@
+"""GPU: each encoder kernel on its own (test hooks of the C ABI) against a plain torch fp32 reference of the same op.
+Tolerances: bf16 outputs within 2^-8 relative of the row scale; f32 outputs within bf16-operand rounding."""
+import ctypes
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from whisper_aries_b200 import _lib
+    return _lib.Context.get(0)
+
+
+def gemm_ref(a, b, bias, epi, resid, pos, pos_rows):
+    acc = a.float() @ b.float().t() + bias
+    if epi in (1, 3):
+        acc = torch.nn.functional.gelu(acc)
+    if epi == 2:
+        acc = acc + resid
+    if epi == 3:
+        acc = acc + pos[torch.arange(a.shape[0], device=a.device) % pos_rows]
+    return acc
+
+
+@pytest.mark.parametrize("shape", [(128, 128, 64), (300, 384, 128), (1500, 1280, 1280), (2900, 3840, 1280),
+                                   (700, 1280, 5120), (1000, 512, 128)])
+@pytest.mark.parametrize("epi", [0, 1, 2, 3])
+def test_gemm_epilogues(ctx, shape, epi):
+    M, N, K = shape
+    g = torch.Generator().manual_seed(M + N + K + epi)
+    a = (torch.randn(M, K, generator=g) * 0.5).cuda().bfloat16()
+    b = (torch.randn(N, K, generator=g) * 0.05).cuda().bfloat16()
+    bias = torch.randn(N, generator=g).cuda()
+    resid = torch.randn(M, N, generator=g).cuda()
+    pos_rows = 100
+    pos = torch.randn(pos_rows, N, generator=g).cuda()
+    Mx = (M // pos_rows) * pos_rows if epi == 3 else M
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16 if epi < 2 else torch.float32)
+    from whisper_aries_b200 import _lib
+    _lib.check(ctx.lib.aries_test_gemm(ctx.handle, epi, Mx, N, K, ptr(a), ptr(b), ptr(bias), ptr(resid), ptr(pos),
+                                       pos_rows, ptr(out), None, 0, 0, 0, None))
+    torch.cuda.synchronize()
+    ref = gemm_ref(a[:Mx], b, bias, epi, resid[:Mx], pos, pos_rows)
+    tol = 2e-3 + (ref.abs().max().item() * 2 ** -8 if epi < 2 else 0.0)
+    assert (out[:Mx].float() - ref).abs().max().item() <= tol
+    if Mx < M:
+        assert torch.isnan(out[Mx:].float()).all()                 # rows past M are never written
+
+
+def test_gemm_qkv_split(ctx):
+    from whisper_aries_b200 import _lib
+    B, T, d, K, t_pad = 2, 300, 256, 128, 304
+    g = torch.Generator().manual_seed(5)
+    a = (torch.randn(B * T, K, generator=g) * 0.5).cuda().bfloat16()
+    b = (torch.randn(3 * d, K, generator=g) * 0.05).cuda().bfloat16()
+    bias = torch.randn(3 * d, generator=g).cuda()
+    out = torch.zeros((B * T, 2 * d), device="cuda", dtype=torch.bfloat16)
+    out2 = torch.zeros((B, d // 64, 64, t_pad), device="cuda", dtype=torch.bfloat16)
+    _lib.check(ctx.lib.aries_test_gemm(ctx.handle, 4, B * T, 3 * d, K, ptr(a), ptr(b), ptr(bias), None, None, 0,
+                                       ptr(out), ptr(out2), 2 * d, T, t_pad, None))
+    torch.cuda.synchronize()
+    ref = a.float() @ b.float().t() + bias
+    assert (out.float() - ref[:, : 2 * d]).abs().max().item() <= 0.05
+    v = ref[:, 2 * d:].reshape(B, T, d // 64, 64).permute(0, 2, 3, 1)
+    assert (out2[..., :T].float() - v).abs().max().item() <= 0.05
+    assert out2[..., T:].abs().max().item() == 0
+
+
+def test_gemm_rejects_bad_shapes(ctx):
+    from whisper_aries_b200 import _lib
+    x = torch.zeros(128 * 128, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(ValueError):
+        _lib.check(ctx.lib.aries_test_gemm(ctx.handle, 0, 128, 100, 64, ptr(x), ptr(x), ptr(x), None, None, 0, ptr(x),
+                                           None, 0, 0, 0, None))
+
+
+@pytest.mark.parametrize("d", [128, 384, 1024, 1280])
+def test_layernorm(ctx, d):
+    from whisper_aries_b200 import _lib
+    x = torch.randn(999, d, device="cuda") * 3 + 0.5
+    gm, bt = torch.randn(d, device="cuda"), torch.randn(d, device="cuda")
+    y = torch.empty((999, d), device="cuda", dtype=torch.bfloat16)
+    _lib.check(ctx.lib.aries_test_layernorm(ctx.handle, ptr(x), ptr(gm), ptr(bt), ptr(y), 999, d, None))
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.layer_norm(x, (d,), gm, bt, 1e-5)
+    assert (y.float() - ref).abs().max().item() <= ref.abs().max().item() * 2 ** -8 + 1e-3
+
+
+@pytest.mark.parametrize("cfg", [(1, 128, 1), (1, 200, 2), (2, 1500, 2), (1, 1500, 20)])
+def test_attention(ctx, cfg):
+    from whisper_aries_b200 import _lib
+    B, T, H = cfg
+    d, t_pad = 64 * H, (T + 7) // 8 * 8
+    g = torch.Generator().manual_seed(T + H)
+    q, k, v = (torch.randn(B, T, H, 64, generator=g).cuda() * s for s in (1.5, 1.5, 1.0))
+    qk = torch.cat([q.reshape(B * T, d), k.reshape(B * T, d)], dim=1).bfloat16().contiguous()
+    vt = torch.full((B, H, 64, t_pad), float("nan"), device="cuda", dtype=torch.bfloat16)   # pad must never be read
+    vt[..., :T] = v.permute(0, 2, 3, 1).bfloat16()
+    out = torch.full((B * T, d), float("nan"), device="cuda", dtype=torch.bfloat16)
+    _lib.check(ctx.lib.aries_test_attention(ctx.handle, ptr(qk), ptr(vt), B, T, H, t_pad, ptr(out), None))
+    torch.cuda.synchronize()
+    qf, kf, vf = (t.bfloat16().float().permute(0, 2, 1, 3) for t in (q, k, v))
+    ref = (torch.softmax(qf @ kf.transpose(-1, -2) / 8.0, dim=-1) @ vf).permute(0, 2, 1, 3).reshape(B * T, d)
+    assert (out.float() - ref).abs().max().item() <= 0.03          # P and the output are rounded to bf16

@@ -51,11 +51,16 @@ PROTOTYPES = {
     "aries_encode_pcm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_size_t,
                                  c_void_p]),
     "aries_encoder_last_launches": (c_int, [c_void_p]),
+    "aries_encoder_set_profiling": (c_int, [c_void_p, c_int]),
+    "aries_encoder_collect_profile": (c_int, [c_void_p, c_float_p, ctypes.POINTER(c_int), c_int]),
     "aries_test_gemm": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "aries_test_layernorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "aries_test_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
 }
+
+KERNEL_CLASSES = ["logmel_tiles", "logmel_clamp", "mel_transpose", "conv1_gemm", "conv2_gemm", "layernorm", "qkv_gemm",
+                  "attention", "oproj_gemm", "fc1_gemm", "fc2_gemm"]
 
 _lib = None
 _lock = threading.Lock()

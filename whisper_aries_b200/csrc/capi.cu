@@ -14,6 +14,7 @@
 #include "gemm.h"
 #include "layernorm.h"
 #include "logmel.h"
+#include "profiler.h"
 
 namespace {
 
@@ -45,6 +46,7 @@ struct aries_mel {
     aries_ctx* ctx;
     aries::LogmelPlan* plan;
     int last_launches;
+    aries::Profiler* prof;      // borrowed from the encoder during aries_encode_pcm when profiling is on
     // scratch for the host-buffer variant
     float* d_pcm;
     size_t pcm_cap;
@@ -150,7 +152,7 @@ int aries_logmel_create(aries_ctx* ctx, int n_mels, const float* mel_filters, ar
         cudaGetLastError();
         return e == cudaErrorInvalidValue ? ARIES_EINVAL : ARIES_ECUDA;
     }
-    aries_mel* m = new (std::nothrow) aries_mel{kMagicMel, ctx, plan, 0, nullptr, 0, nullptr, 0};
+    aries_mel* m = new (std::nothrow) aries_mel{kMagicMel, ctx, plan, 0, nullptr, nullptr, 0, nullptr, 0};
     if (!m) {
         aries::logmel_plan_destroy(plan);
         return fail(ARIES_ENOMEM, "out of host memory");
@@ -186,7 +188,7 @@ int aries_logmel_run(aries_mel* mel, const float* pcm_dev, int batch, int64_t n_
                                   "pcm_stride >= n_samples and non-NULL buffers");
     if ((n_samples + padding) / 160 > (1 << 24)) return fail(ARIES_EINVAL, "aries_logmel_run: signal too long");
     cudaError_t e = aries::logmel_run(mel->plan, pcm_dev, batch, n_samples, pcm_stride, padding, out_dev, frames_out,
-                                      static_cast<cudaStream_t>(stream), &mel->last_launches);
+                                      static_cast<cudaStream_t>(stream), &mel->last_launches, mel->prof);
     if (e != cudaSuccess) return fail_cuda("aries_logmel_run", e);
     return ARIES_OK;
 }
@@ -334,12 +336,32 @@ int aries_encode_pcm(aries_encoder* enc, aries_mel* mel, const float* pcm_dev, i
     const size_t need = aries::encoder_workspace_bytes(enc->plan, batch);
     if (!workspace || workspace_bytes < need) return fail(ARIES_EINVAL, "aries_encode_pcm: workspace too small");
     float* mel_buf = aries::encoder_workspace_mel(enc->plan, workspace, batch);
-    if ((rc = aries_logmel_run(mel, pcm_dev, batch, n_samples, pcm_stride, 160, mel_buf, 3000, stream))) return rc;
+    aries::Profiler* prof = aries::encoder_plan_profiler(enc->plan);
+    mel->prof = prof->enabled() ? prof : nullptr;
+    rc = aries_logmel_run(mel, pcm_dev, batch, n_samples, pcm_stride, 160, mel_buf, 3000, stream);
+    mel->prof = nullptr;
+    if (rc) return rc;
     return aries_encoder_run(enc, mel_buf, batch, 3000, out_dev, workspace, workspace_bytes, stream);
 }
 
 int aries_encoder_last_launches(const aries_encoder* enc) {
     return (enc && enc->magic == kMagicEnc) ? aries::encoder_plan_last_launches(enc->plan) : -1;
+}
+
+int aries_encoder_set_profiling(aries_encoder* enc, int on) {
+    if (!enc || enc->magic != kMagicEnc) return fail(ARIES_ESTATE, "invalid encoder handle");
+    aries::encoder_plan_profiler(enc->plan)->enable(on != 0);
+    return ARIES_OK;
+}
+
+int aries_encoder_collect_profile(aries_encoder* enc, float* ms, int* counts, int n) {
+    if (!enc || enc->magic != kMagicEnc) return fail(ARIES_ESTATE, "invalid encoder handle");
+    if (!ms || !counts || n < aries::KC_COUNT) return fail(ARIES_EINVAL, "aries_encoder_collect_profile: need n >= 11");
+    int rc = use(enc->ctx);
+    if (rc) return rc;
+    cudaError_t e = aries::encoder_plan_profiler(enc->plan)->collect(ms, counts);
+    if (e != cudaSuccess) return fail_cuda("aries_encoder_collect_profile", e);
+    return ARIES_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ test hooks

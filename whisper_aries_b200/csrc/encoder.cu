@@ -23,6 +23,7 @@
 #include "gemm.h"
 #include "layernorm.h"
 #include "logmel.h"
+#include "profiler.h"
 
 namespace aries {
 
@@ -64,6 +65,7 @@ struct EncoderPlan {
     int cached_batch = 0;
     CUtensorMap a_mel{}, a_c1{}, a_y{}, a_ctx{}, a_h{}, a_qk{}, a_vt{};
     int last_launches = 0;
+    Profiler prof;
     std::string error;
 };
 
@@ -332,7 +334,9 @@ cudaError_t encoder_run(EncoderPlan* pl, const float* mel, int batch, int frames
     ARIES_TRY(cudaMemset2DAsync(static_cast<char*>(c1) + (size_t)(kRowsPadded - 1) * d * 2, (size_t)kRowsPadded * d * 2, 0,
                                 (size_t)d * 2, batch, stream), "memset");
 
+    pl->prof.begin(KC_TRANSPOSE, stream);
     ARIES_TRY(mel_to_time_major(mel, batch, c.n_mels, frames, melT, cp, stream), "mel transpose");
+    pl->prof.end(stream);
     ++launches;
 
     GemmParams g{};
@@ -341,14 +345,18 @@ cudaError_t encoder_run(EncoderPlan* pl, const float* mel, int batch, int frames
     g.M = batch * kRowsPadded; g.N = d; g.K = 3 * cp; g.a_cols = cp;
     g.p_in = kRowsPadded; g.t_valid = kFramesIn; g.p_out = kRowsPadded; g.row_off = 1; g.ldo = d;
     g.bias = pl->conv1_b; g.out = c1;
+    pl->prof.begin(KC_CONV1, stream);
     ARIES_TRY(gemm_launch(EPI_BIAS_GELU_BF16, pl->a_mel, pl->m_conv1, g, pl->sm_count, stream), "conv1");
+    pl->prof.end(stream);
     ++launches;
     // conv2 (stride 2): row r = b * 1501 + t reads the row PAIR t (taps 0, 1) and the first half of pair t + 1 (tap 2)
     g = GemmParams{};
     g.M = batch * (kRowsPadded / 2); g.N = d; g.K = 3 * d; g.a_cols = 2 * d;
     g.p_in = kRowsPadded / 2; g.t_valid = T; g.p_out = T; g.row_off = 0; g.ldo = d;
     g.bias = pl->conv2_b; g.pos = pl->pos; g.out = x;
+    pl->prof.begin(KC_CONV2, stream);
     ARIES_TRY(gemm_launch(EPI_BIAS_GELU_POS_F32, pl->a_c1, pl->m_conv2, g, pl->sm_count, stream), "conv2");
+    pl->prof.end(stream);
     ++launches;
 
     auto plain = [&](int N, int K) {
@@ -360,29 +368,47 @@ cudaError_t encoder_run(EncoderPlan* pl, const float* mel, int batch, int frames
     AttnParams ap{batch, T, d, c.n_heads, ctx};
     for (int i = 0; i < c.n_layers; ++i) {
         const LayerW& lw = pl->layers[i];
+        pl->prof.begin(KC_LAYERNORM, stream);
         ARIES_TRY(layernorm_launch(x, lw.ln1_g, lw.ln1_b, y, M, d, kLnEps, stream), "layer norm 1");
+        pl->prof.end(stream);
         g = plain(3 * d, d);
         g.p_in = T; g.t_valid = T; g.p_out = T; g.ldo = 2 * d;
         g.bias = lw.bqkv; g.out = qk; g.out2 = vt; g.n_split = 2 * d; g.t_pad = pl->t_pad;
+        pl->prof.begin(KC_QKV, stream);
         ARIES_TRY(gemm_launch(EPI_QKV_SPLIT_BF16, pl->a_y, lw.m_qkv, g, pl->sm_count, stream), "qkv projection");
+        pl->prof.end(stream);
+        pl->prof.begin(KC_ATTENTION, stream);
         ARIES_TRY(attention_launch(pl->a_qk, pl->a_vt, ap, stream), "attention");
+        pl->prof.end(stream);
         g = plain(d, d);
         g.bias = lw.bo; g.resid = x; g.out = x;
+        pl->prof.begin(KC_OPROJ, stream);
         ARIES_TRY(gemm_launch(EPI_BIAS_RESID_F32, pl->a_ctx, lw.m_o, g, pl->sm_count, stream), "output projection");
+        pl->prof.end(stream);
+        pl->prof.begin(KC_LAYERNORM, stream);
         ARIES_TRY(layernorm_launch(x, lw.ln2_g, lw.ln2_b, y, M, d, kLnEps, stream), "layer norm 2");
+        pl->prof.end(stream);
         g = plain(f, d);
         g.bias = lw.b1; g.out = h;
+        pl->prof.begin(KC_FC1, stream);
         ARIES_TRY(gemm_launch(EPI_BIAS_GELU_BF16, pl->a_y, lw.m_fc1, g, pl->sm_count, stream), "fc1");
+        pl->prof.end(stream);
         g = plain(d, f);
         g.bias = lw.b2; g.resid = x; g.out = x;
+        pl->prof.begin(KC_FC2, stream);
         ARIES_TRY(gemm_launch(EPI_BIAS_RESID_F32, pl->a_h, lw.m_fc2, g, pl->sm_count, stream), "fc2");
+        pl->prof.end(stream);
         launches += 7;
     }
+    pl->prof.begin(KC_LAYERNORM, stream);
     ARIES_TRY(layernorm_launch(x, pl->lnf_g, pl->lnf_b, out_bf16, M, d, kLnEps, stream), "final layer norm");
+    pl->prof.end(stream);
     ++launches;
     pl->last_launches = launches;
     return cudaSuccess;
 }
+
+Profiler* encoder_plan_profiler(EncoderPlan* pl) { return &pl->prof; }
 
 float* encoder_workspace_mel(const EncoderPlan* pl, void* workspace, int batch) {
     return reinterpret_cast<float*>(static_cast<char*>(workspace) + ws_layout(*pl, batch).mel);

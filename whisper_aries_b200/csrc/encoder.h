@@ -18,6 +18,7 @@ struct WeightView {
 };
 
 struct EncoderPlan;
+class Profiler;
 
 cudaError_t encoder_plan_create(int device, int sm_count, const EncoderShapeC& cfg, const WeightView* weights,
                                 int n_weights, EncoderPlan** out, std::string* why);
@@ -31,5 +32,6 @@ float* encoder_workspace_mel(const EncoderPlan* pl, void* workspace, int batch);
 const char* encoder_plan_error(const EncoderPlan* pl);
 int encoder_plan_last_launches(const EncoderPlan* pl);
 const EncoderShapeC* encoder_plan_cfg(const EncoderPlan* pl);
+Profiler* encoder_plan_profiler(EncoderPlan* pl);
 
 }  // namespace aries

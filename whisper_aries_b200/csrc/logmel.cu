@@ -20,6 +20,7 @@
 
 #include "logmel.h"
 #include "logmel_core.cuh"
+#include "profiler.h"
 
 namespace aries {
 
@@ -363,7 +364,7 @@ void logmel_plan_destroy(LogmelPlan* pl) {
 int logmel_plan_n_mels(const LogmelPlan* pl) { return pl->n_mels; }
 
 cudaError_t logmel_run(LogmelPlan* pl, const float* pcm, int batch, long long n_samples, long long pcm_stride,
-                       int padding, float* out, int frames_out, cudaStream_t stream, int* launches) {
+                       int padding, float* out, int frames_out, cudaStream_t stream, int* launches, Profiler* prof) {
     const long long padded = n_samples + padding;
     const int n_frames = (int)(padded / kHop);
     const int tiles = (n_frames + kTileFrames - 1) / kTileFrames;
@@ -407,14 +408,18 @@ cudaError_t logmel_run(LogmelPlan* pl, const float* pcm, int batch, long long n_
     const long long total = (long long)batch * tiles;
     if (total > 0) {
         const int grid = (int)(total < pl->sm_count ? total : pl->sm_count);
+        if (prof) prof->begin(KC_MEL, stream);
         logmel_tiles_kernel<<<grid, kThreads, sizeof(Smem), stream>>>(p);
+        if (prof) prof->end(stream);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         ++n_launch;
     }
     const int out_tiles = (frames_out + kTileFrames - 1) / kTileFrames;
     const int clamp_tiles = out_tiles > tiles ? out_tiles : tiles;
     if (clamp_tiles > 0 && frames_out > 0) {
+        if (prof) prof->begin(KC_MEL_CLAMP, stream);
         logmel_clamp_kernel<<<dim3(clamp_tiles, batch), 256, 0, stream>>>(p);
+        if (prof) prof->end(stream);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         ++n_launch;
     }

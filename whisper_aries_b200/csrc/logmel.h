@@ -7,6 +7,7 @@ namespace aries {
 namespace mel { struct Tables; }
 
 struct LogmelPlan;
+class Profiler;
 
 // filters: host f32 [n_mels, 201] (Slaney bank as FeatureExtractor.get_mel_filters builds it).
 cudaError_t logmel_plan_create(int device, int sm_count, int n_mels, const float* filters, LogmelPlan** out,
@@ -18,7 +19,8 @@ int logmel_plan_n_mels(const LogmelPlan* pl);
 // [batch, n_mels, frames_out]; frames beyond (n_samples + padding) / 160 are zero-filled, frames beyond frames_out
 // are computed (they count for the clamp maximum) but not stored.  Stream-ordered; no host sync in steady state.
 cudaError_t logmel_run(LogmelPlan* pl, const float* pcm, int batch, long long n_samples, long long pcm_stride,
-                       int padding, float* out, int frames_out, cudaStream_t stream, int* launches);
+                       int padding, float* out, int frames_out, cudaStream_t stream, int* launches,
+                       Profiler* prof = nullptr);
 
 // [B, n_mels, frames] f32 -> [B, 3002, c_pad] bf16 rows 1..3000 (time-major conv1 operand); pad rows untouched.
 cudaError_t mel_to_time_major(const float* mel, int batch, int n_mels, int frames, void* out_bf16, int c_pad,

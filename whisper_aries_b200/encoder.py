@@ -61,6 +61,17 @@ class WhisperEncoder:
     def last_launches(self) -> int:
         return self._ctx.lib.aries_encoder_last_launches(self._handle)
 
+    def set_profiling(self, on: bool) -> None:
+        """Bracket every kernel of the following calls with CUDA events (bench.py's per-kernel roofline numbers)."""
+        _lib.check(self._ctx.lib.aries_encoder_set_profiling(self._handle, int(bool(on))))
+
+    def collect_profile(self) -> dict:
+        """{kernel class: (milliseconds, launches)} accumulated since profiling was switched on / last collected."""
+        n = len(_lib.KERNEL_CLASSES)
+        ms, cnt = (ctypes.c_float * n)(), (ctypes.c_int * n)()
+        _lib.check(self._ctx.lib.aries_encoder_collect_profile(self._handle, ms, cnt, n))
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(_lib.KERNEL_CLASSES)}
+
     def workspace_bytes(self, batch: int) -> int:
         return int(self._ctx.lib.aries_encoder_workspace_bytes(self._handle, batch))
 
