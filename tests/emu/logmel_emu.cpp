@@ -34,18 +34,8 @@ extern "C" int emu_logmel(const float* pcm, long long n_samples, int padding, co
                           float* out, int frames_out) {
     Tables tb;
     build_tables(tb);
-    std::vector<float> w;
-    std::vector<short> start(n_mels), count(n_mels), offset(n_mels);
-    for (int m = 0; m < n_mels; ++m) {
-        int lo = -1, hi = -1;
-        for (int k = 0; k < kBins; ++k)
-            if (filters[m * kBins + k] != 0.0f) { if (lo < 0) lo = k; hi = k; }
-        start[m] = (short)(lo < 0 ? 0 : lo);
-        count[m] = (short)(lo < 0 ? 0 : hi - lo + 1);
-        offset[m] = (short)w.size();
-        for (int k = 0; k < count[m]; ++k) w.push_back(0.25f * filters[m * kBins + lo + k]);
-    }
-    MelBank bank{w.data(), start.data(), count.data(), offset.data()};
+    static MelBank bank;
+    if (n_mels > kMaxMels || !build_mel_bank(filters, n_mels, bank)) return -1;
     const long long padded = n_samples + padding;
     const int n_frames = (int)(padded / kHop);
     const int tiles = (n_frames + kTileFrames - 1) / kTileFrames;
@@ -68,14 +58,17 @@ extern "C" int emu_logmel(const float* pcm, long long n_samples, int padding, co
             }
         float tmin = INFINITY;
         for (int m = 0; m < n_mels; ++m)
-            for (int col = 0; col < kTileFrames; ++col) {
-                const int f = t * kTileFrames + col;
-                if (f >= n_frames) continue;
-                const float acc = mel_dot(P.data(), bank, m, col);
-                const float v = std::fmaf(std::log2(std::fmax(acc, 1e-10f)), 0.07525749891599529f, 1.0f);
-                gmax = std::fmax(gmax, v);
-                tmin = std::fmin(tmin, v);
-                if (f < frames_out) out[(long long)m * frames_out + f] = v;
+            for (int lane = 0; lane < 32; ++lane) {
+                float acc[2];
+                mel_dot2(P.data(), bank, m, lane, acc[0], acc[1]);
+                for (int h = 0; h < 2; ++h) {
+                    const int f = t * kTileFrames + lane + 32 * h;
+                    if (f >= n_frames) continue;
+                    const float v = std::fmaf(std::log2(std::fmax(acc[h], 1e-10f)), 0.07525749891599529f, 1.0f);
+                    gmax = std::fmax(gmax, v);
+                    tmin = std::fmin(tmin, v);
+                    if (f < frames_out) out[(long long)m * frames_out + f] = v;
+                }
             }
         tile_min[t] = tmin;
     }

@@ -1,0 +1,51 @@
+"""Small profiling targets for ncu (run under gpurun):  python tests/prof_target.py mel|attn|gemm-o|gemm-fc1|gemm-qkv"""
+import ctypes
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, ".")
+from whisper_aries_b200 import FeatureExtractor, _lib, synthetic   # noqa: E402
+
+dev = torch.device("cuda:0")
+what = sys.argv[1]
+ctx = _lib.Context.get(0)
+lib = ctx.lib
+
+
+def ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+if what == "mel":
+    B = 64
+    fe = FeatureExtractor(feature_size=128)
+    xs = torch.from_numpy(synthetic.batch_signals(6, 0)).to(dev).repeat(11, 1)[:B].contiguous()
+    out = torch.empty((B, 128, 3000), device=dev)
+    for _ in range(3):
+        fe(xs, frames_out=3000)
+    torch.cuda.synchronize()
+elif what == "attn":
+    B_, T_, H = 8, 1500, 20
+    d, t_pad = 64 * H, 1504
+    qk = (torch.randn(B_ * T_, 2 * d, device=dev) * 1.5).bfloat16()
+    vt = torch.randn(B_, H, 64, t_pad, device=dev).bfloat16()
+    out = torch.empty((B_ * T_, d), device=dev, dtype=torch.bfloat16)
+    for _ in range(3):
+        lib.aries_test_attention(ctx.handle, ptr(qk), ptr(vt), B_, T_, H, t_pad, ptr(out), None)
+    torch.cuda.synchronize()
+else:
+    M = 96000
+    N, K, epi = {"gemm-o": (1280, 1280, 2), "gemm-fc1": (5120, 1280, 1), "gemm-qkv": (3840, 1280, 0),
+                 "gemm-fc2": (1280, 5120, 2)}[what]
+    a = torch.randn(M, K, device=dev).bfloat16()
+    b = (torch.randn(N, K, device=dev) * 0.05).bfloat16()
+    bias = torch.randn(N, device=dev)
+    resid = torch.randn(M, N, device=dev) if epi == 2 else None
+    out = torch.empty((M, N), device=dev, dtype=torch.bfloat16 if epi < 2 else torch.float32)
+    for _ in range(3):
+        lib.aries_test_gemm(ctx.handle, epi, M, N, K, ptr(a), ptr(b), ptr(bias), ptr(resid), None, 0, ptr(out), None, 0,
+                            0, 0, None)
+    torch.cuda.synchronize()
+print("ok", what)

@@ -31,7 +31,8 @@ struct Cfg {
     static constexpr int kBBytes = BN * BK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kBarBytes = 256;
-    static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;   // +1024: manual 1 KB alignment
+    static constexpr int kEpiStageBytes = kEpiWarps * 32 * 32 * 4;                // 4 KB transpose buffer per warp
+    static constexpr int kSmemBytes = kStages * kStageBytes + kEpiStageBytes + kBarBytes + 1024;   // +1024: alignment
     static constexpr uint32_t kTmemCols = 2 * BN;
 };
 
@@ -43,7 +44,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+    uint8_t* epi_stage = smem + C::kStages * C::kStageBytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + C::kEpiStageBytes);
     uint64_t* empty_bar = full_bar + C::kStages;
     uint64_t* tfull_bar = empty_bar + C::kStages;      // [2] accumulator ready
     uint64_t* tempty_bar = tfull_bar + 2;              // [2] accumulator drained
@@ -129,21 +131,44 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         }
     } else {
         // ---------------------------------------------------------------- epilogue warps
+        // TMEM hands every thread one accumulator ROW (32 consecutive columns per load).  Storing that directly makes
+        // each warp-level access touch 32 different rows (32 half-used sectors), which made the f32 epilogues
+        // LSU-bound.  So each warp transposes its 32x32 chunk through a private, XOR-swizzled 4 KB shared buffer and
+        // then reads / writes global memory with 8 lanes per row: full 32-byte sectors, 4 rows per instruction.
         const int ew = warp - 2;
         const int quarter = warp & 3;          // TMEM lane quarter this warp may touch
         const int half = ew >> 2;              // which half of the tile's columns
         constexpr int kChunks = (BN / 2) / 32;
+        float4* stage = reinterpret_cast<float4*>(epi_stage + ew * 4096);
+        const int sub_row = lane >> 3;         // coalesced phase: row 4 i + sub_row, 16-byte column c4
+        const int c4 = lane & 7;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
             const int m0 = (tile / num_n) * BM;
             const int n0 = (tile % num_n) * BN + half * (BN / 2);
-            const int r = m0 + quarter * 32 + lane;
-            const int b = r / p.p_in;
-            const int t = r - b * p.p_in;
-            const bool valid = (r < p.M) && (t < p.t_valid);
-            const long long orow = (long long)b * p.p_out + t + p.row_off;
+            const int rbase = m0 + quarter * 32;
+            // output rows of the coalesced phase: element offset of the row start (32-bit: the largest activation
+            // is far below 2^32 elements), 0 for rows that must not be written (their loads stay in bounds)
+            unsigned row_off_c[8];
+            int t_c[8];
+            unsigned valid_c = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = rbase + 4 * i + sub_row;
+                const int b = r / p.p_in;
+                const int t = r - b * p.p_in;
+                const bool ok = (r < p.M) && (t < p.t_valid);
+                if (ok) valid_c |= 1u << i;
+                row_off_c[i] = ok ? (unsigned)(((long long)b * p.p_out + t + p.row_off) * p.ldo) : 0u;
+                t_c[i] = ok ? t : 0;
+            }
+            // this thread's own accumulator row (used by the transposed V store of the QKV epilogue)
+            const int r_own = rbase + lane;
+            const int b_own = r_own / p.p_in;
+            const int t_own = r_own - b_own * p.p_in;
+            const bool valid_own = (r_own < p.M) && (t_own < p.t_valid);
 
             mbar_wait(&tfull_bar[as], aphase);
             tc_fence_after();
@@ -152,55 +177,67 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 uint32_t acc[32];
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN + half * (BN / 2) + c * 32;
                 tmem_ld_32x32b_x32(taddr, acc);
-                tmem_ld_wait();
+                tmem_ld_wait_on(acc);
                 const int nc = n0 + c * 32;
-                float v[32];
-                const float4* bias4 = reinterpret_cast<const float4*>(p.bias + nc);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 bb = __ldg(bias4 + j);
-                    v[4 * j + 0] = __uint_as_float(acc[4 * j + 0]) + bb.x;
-                    v[4 * j + 1] = __uint_as_float(acc[4 * j + 1]) + bb.y;
-                    v[4 * j + 2] = __uint_as_float(acc[4 * j + 2]) + bb.z;
-                    v[4 * j + 3] = __uint_as_float(acc[4 * j + 3]) + bb.w;
-                }
-                if (EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_GELU_POS_F32) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-                }
                 if (EPI == EPI_QKV_SPLIT_BF16 && nc >= p.n_split) {
                     // values: out2[b][head][c][t]; for a fixed column the warp's 32 rows are 32 consecutive t
-                    if (valid) {
+                    if (valid_own) {
+                        const float4* bias4 = reinterpret_cast<const float4*>(p.bias + nc);
                         __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(p.out2) +
-                                            ((long long)b * (p.N - p.n_split) + (nc - p.n_split)) * p.t_pad + t;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) o2[(long long)j * p.t_pad] = __float2bfloat16_rn(v[j]);
-                    }
-                } else if (valid) {
-                    if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_QKV_SPLIT_BF16) {
-                        uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + nc);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            uint4 q;
-                            q.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-                            q.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-                            q.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-                            q.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-                            o[j] = q;
-                        }
-                    } else {
-                        const float* add = (EPI == EPI_BIAS_RESID_F32) ? (p.resid + orow * p.ldo + nc)
-                                                                       : (p.pos + (long long)t * p.N + nc);
-                        const float4* a4 = reinterpret_cast<const float4*>(add);
-                        float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + orow * p.ldo + nc);
+                                            ((long long)b_own * (p.N - p.n_split) + (nc - p.n_split)) * p.t_pad + t_own;
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            const float4 a = a4[j];
-                            o[j] = make_float4(v[4 * j + 0] + a.x, v[4 * j + 1] + a.y, v[4 * j + 2] + a.z,
-                                               v[4 * j + 3] + a.w);
+                            const float4 bb = __ldg(bias4 + j);
+                            o2[(long long)(4 * j + 0) * p.t_pad] = __float2bfloat16_rn(__uint_as_float(acc[4 * j + 0]) + bb.x);
+                            o2[(long long)(4 * j + 1) * p.t_pad] = __float2bfloat16_rn(__uint_as_float(acc[4 * j + 1]) + bb.y);
+                            o2[(long long)(4 * j + 2) * p.t_pad] = __float2bfloat16_rn(__uint_as_float(acc[4 * j + 2]) + bb.z);
+                            o2[(long long)(4 * j + 3) * p.t_pad] = __float2bfloat16_rn(__uint_as_float(acc[4 * j + 3]) + bb.w);
                         }
                     }
+                    continue;
                 }
+                // phase 1: own row -> staging, 16-byte column j stored at j ^ (row & 7)  (conflict-free both ways)
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    stage[lane * 8 + (j ^ (lane & 7))] =
+                        make_float4(__uint_as_float(acc[4 * j + 0]), __uint_as_float(acc[4 * j + 1]),
+                                    __uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3]));
+                __syncwarp();
+                // phase 2: 8 lanes per row; bias / activation / residual applied on the way out.  The residual /
+                // position loads of all 8 rows are issued together, before anything depends on them.
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + nc) + c4);
+                float4 add[8];
+                if (EPI == EPI_BIAS_RESID_F32) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        add[i] = *reinterpret_cast<const float4*>(p.resid + row_off_c[i] + nc + 4 * c4);
+                } else if (EPI == EPI_BIAS_GELU_POS_F32) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        add[i] = __ldg(reinterpret_cast<const float4*>(p.pos + (long long)t_c[i] * p.N + nc) + c4);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int rl = 4 * i + sub_row;
+                    float4 v = stage[rl * 8 + (c4 ^ (rl & 7))];
+                    v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+                    if (EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_GELU_POS_F32) {
+                        v.x = gelu_fast(v.x); v.y = gelu_fast(v.y); v.z = gelu_fast(v.z); v.w = gelu_fast(v.w);
+                    }
+                    const bool ok = (valid_c >> i) & 1u;
+                    const unsigned off = row_off_c[i] + nc + 4 * c4;
+                    if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_QKV_SPLIT_BF16) {
+                        uint2 q;
+                        q.x = pack_bf16x2(v.x, v.y);
+                        q.y = pack_bf16x2(v.z, v.w);
+                        if (ok) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off) = q;
+                    } else {
+                        if (ok)
+                            *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off) =
+                                make_float4(v.x + add[i].x, v.y + add[i].y, v.z + add[i].z, v.w + add[i].w);
+                    }
+                }
+                __syncwarp();
             }
             tc_fence_before();
             __syncwarp();

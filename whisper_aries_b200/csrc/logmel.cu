@@ -16,6 +16,7 @@
 
 #include <cmath>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "logmel.h"
@@ -30,21 +31,18 @@ namespace {
 
 constexpr int kThreads = 640;                                   // 20 warps = the 20 items of each stage
 constexpr int kPcmWordsPadded = (kPcmWords + 3) & ~3;
-constexpr int kMaxMelWeights = 1024;
-constexpr int kMaxMels = 256;
+constexpr int kBankSlots = 4;                                   // distinct filter banks resident per device
+constexpr int kMaxDevices = 64;
 constexpr int kFloat4PerTile = kTileSamples / 4;                // 2620
 constexpr int kPrefetch = (kFloat4PerTile + kThreads - 1) / kThreads;   // 5 float4 per thread
 
 __constant__ Tables c_tables;
+__constant__ MelBank c_bank[kBankSlots];       // warp-uniform reads: the tap loop runs on the uniform datapath
 
 struct Smem {
     float pcm[2][kPcmWordsPadded];
     float e_re[kExchangeFloat2];      // P (201 x 64 floats) aliases e_re/e_im
     float e_im[kExchangeFloat2];
-    float melw[kMaxMelWeights];
-    short mstart[kMaxMels];
-    short mcount[kMaxMels];
-    short moffset[kMaxMels];
     unsigned red_max;
     unsigned red_min;
 };
@@ -73,12 +71,14 @@ struct Params {
     long long out_stride;       // n_mels * frames_out
     unsigned* gmax;             // [batch], order_f32 encoded
     float* tile_min;            // [batch][tiles_per_item]
-    const float* melw;
-    const short* mstart;
-    const short* mcount;
-    const short* moffset;
-    int n_weights;
+    int bank_slot;
 };
+
+__device__ __forceinline__ float fast_log2(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 __device__ __forceinline__ void prefetch_tile(const Params& p, int tile, float4 (&r)[kPrefetch]) {
     const int b = tile / p.tiles_per_item;
@@ -131,17 +131,11 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_tiles_kernel(const Params 
     const int lane = threadIdx.x & 31;
     const int total_tiles = p.batch * p.tiles_per_item;
 
-    for (int i = threadIdx.x; i < p.n_weights; i += kThreads) sm.melw[i] = p.melw[i];
-    for (int i = threadIdx.x; i < p.n_mels; i += kThreads) {
-        sm.mstart[i] = p.mstart[i];
-        sm.mcount[i] = p.mcount[i];
-        sm.moffset[i] = p.moffset[i];
-    }
     if (threadIdx.x == 0) {
         sm.red_max = 0u;
         sm.red_min = 0xFFFFFFFFu;
     }
-    MelBank bank{sm.melw, sm.mstart, sm.mcount, sm.moffset};
+    const MelBank& bank = c_bank[p.bank_slot];
 
     int tile = blockIdx.x;
     if (tile < total_tiles) {
@@ -172,19 +166,36 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_tiles_kernel(const Params 
         float4 r[kPrefetch];
         if (has_next) prefetch_tile(p, next, r);
 
-        // ---- mel filters + log: warp item = (mel bin, half of the tile), lane = frame
+        // ---- mel filters + log: a warp owns mel bins warp, warp + 20, ...; lane = frame (and frame + 32)
         float vmax = -INFINITY, vmin = INFINITY;
-        float* out_b = p.out + (long long)b * p.out_stride;
-        for (int item = warp; item < 2 * p.n_mels; item += kThreads / 32) {
-            const int m = item >> 1;
-            const int col = lane + 32 * (item & 1);
-            const int f = t * kTileFrames + col;
-            const float acc = mel_dot(P, bank, m, col);
-            const float v = fmaf(__log2f(fmaxf(acc, 1e-10f)), 0.07525749891599529f, 1.0f);   // (log10 + 4) / 4
-            if (f < p.n_frames) {
-                vmax = fmaxf(vmax, v);
-                vmin = fminf(vmin, v);
-                if (f < p.frames_out) out_b[(long long)m * p.frames_out + f] = v;
+        {
+            const int f0 = t * kTileFrames + lane;
+            float* o0 = p.out + (long long)b * p.out_stride + f0;
+            const int lim = p.n_frames < p.frames_out ? p.n_frames : p.frames_out;
+            const bool full_tile = (t + 1) * kTileFrames <= lim;          // uniform: every frame is real and stored
+            for (int m = warp; m < p.n_mels; m += kThreads / 32) {
+                float a0, a1;
+                mel_dot2(P, bank, m, lane, a0, a1);
+                const float v0 = fmaf(fast_log2(fmaxf(a0, 1e-10f)), 0.07525749891599529f, 1.0f);   // (log10 + 4) / 4
+                const float v1 = fmaf(fast_log2(fmaxf(a1, 1e-10f)), 0.07525749891599529f, 1.0f);
+                float* om = o0 + (size_t)m * p.frames_out;
+                if (full_tile) {
+                    vmax = fmaxf(vmax, fmaxf(v0, v1));
+                    vmin = fminf(vmin, fminf(v0, v1));
+                    om[0] = v0;
+                    om[32] = v1;
+                } else {
+                    if (f0 < p.n_frames) {
+                        vmax = fmaxf(vmax, v0);
+                        vmin = fminf(vmin, v0);
+                        if (f0 < p.frames_out) om[0] = v0;
+                    }
+                    if (f0 + 32 < p.n_frames) {
+                        vmax = fmaxf(vmax, v1);
+                        vmin = fminf(vmin, v1);
+                        if (f0 + 32 < p.frames_out) om[32] = v1;
+                    }
+                }
             }
         }
         if (has_next) store_tile(nxt, r);
@@ -284,17 +295,53 @@ struct LogmelPlan {
     int device = 0;
     int n_mels = 0;
     int sm_count = 0;
-    int n_weights = 0;
-    float* d_melw = nullptr;
-    short* d_start = nullptr;
-    short* d_count = nullptr;
-    short* d_offset = nullptr;
+    int bank_slot = -1;
     // scratch, grown on demand
     unsigned* d_gmax = nullptr;
     float* d_tile_min = nullptr;
     int cap_batch = 0;
     long long cap_tiles = 0;
 };
+
+namespace {
+// Filter banks live in __constant__ memory (warp-uniform reads).  A device holds up to kBankSlots distinct banks;
+// handles with identical filters share a slot.
+struct BankSlot {
+    int refs = 0;
+    MelBank bank;
+};
+std::mutex g_bank_mutex;
+BankSlot* g_slots[kMaxDevices] = {};
+
+int acquire_bank_slot(int device, const MelBank& mb, cudaError_t* err) {
+    std::lock_guard<std::mutex> lock(g_bank_mutex);
+    *err = cudaSuccess;
+    if (device < 0 || device >= kMaxDevices) return -1;
+    if (!g_slots[device]) g_slots[device] = new BankSlot[kBankSlots];
+    BankSlot* slots = g_slots[device];
+    for (int i = 0; i < kBankSlots; ++i)
+        if (slots[i].refs > 0 && std::memcmp(&slots[i].bank, &mb, sizeof(MelBank)) == 0) {
+            ++slots[i].refs;
+            return i;
+        }
+    for (int i = 0; i < kBankSlots; ++i)
+        if (slots[i].refs == 0) {
+            *err = cudaMemcpyToSymbol(c_bank, &mb, sizeof(MelBank), (size_t)i * sizeof(MelBank));
+            if (*err != cudaSuccess) return -1;
+            slots[i].bank = mb;
+            slots[i].refs = 1;
+            return i;
+        }
+    return -1;
+}
+
+void release_bank_slot(int device, int slot) {
+    std::lock_guard<std::mutex> lock(g_bank_mutex);
+    if (device >= 0 && device < kMaxDevices && g_slots[device] && slot >= 0 && slot < kBankSlots &&
+        g_slots[device][slot].refs > 0)
+        --g_slots[device][slot].refs;
+}
+}  // namespace
 
 cudaError_t logmel_plan_create(int device, int sm_count, int n_mels, const float* filters, LogmelPlan** out,
                                const char** why) {
@@ -303,22 +350,8 @@ cudaError_t logmel_plan_create(int device, int sm_count, int n_mels, const float
         *why = "n_mels out of range (1..256)";
         return cudaErrorInvalidValue;
     }
-    std::vector<float> w;
-    std::vector<short> start(n_mels), count(n_mels), offset(n_mels);
-    for (int m = 0; m < n_mels; ++m) {
-        int lo = -1, hi = -1;
-        for (int k = 0; k < kBins; ++k) {
-            if (filters[m * kBins + k] != 0.0f) {
-                if (lo < 0) lo = k;
-                hi = k;
-            }
-        }
-        start[m] = (short)(lo < 0 ? 0 : lo);
-        count[m] = (short)(lo < 0 ? 0 : hi - lo + 1);
-        offset[m] = (short)w.size();
-        for (int k = 0; k < count[m]; ++k) w.push_back(0.25f * filters[m * kBins + lo + k]);   // power carries x4
-    }
-    if ((int)w.size() > kMaxMelWeights) {
+    static thread_local MelBank mb;
+    if (!build_mel_bank(filters, n_mels, mb)) {
         *why = "mel filter bank too dense for the sparse kernel (more than 1024 taps)";
         return cudaErrorInvalidValue;
     }
@@ -326,7 +359,6 @@ cudaError_t logmel_plan_create(int device, int sm_count, int n_mels, const float
     pl->device = device;
     pl->n_mels = n_mels;
     pl->sm_count = sm_count;
-    pl->n_weights = (int)w.size();
     cudaError_t e;
     Tables tb;
     build_tables(tb);
@@ -334,14 +366,13 @@ cudaError_t logmel_plan_create(int device, int sm_count, int n_mels, const float
     if ((e = cudaFuncSetAttribute(logmel_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)sizeof(Smem))) != cudaSuccess)
         goto fail;
-    if ((e = cudaMalloc(&pl->d_melw, sizeof(float) * (w.size() + 1))) != cudaSuccess) goto fail;
-    if ((e = cudaMalloc(&pl->d_start, sizeof(short) * n_mels)) != cudaSuccess) goto fail;
-    if ((e = cudaMalloc(&pl->d_count, sizeof(short) * n_mels)) != cudaSuccess) goto fail;
-    if ((e = cudaMalloc(&pl->d_offset, sizeof(short) * n_mels)) != cudaSuccess) goto fail;
-    if ((e = cudaMemcpy(pl->d_melw, w.data(), sizeof(float) * w.size(), cudaMemcpyHostToDevice)) != cudaSuccess) goto fail;
-    if ((e = cudaMemcpy(pl->d_start, start.data(), sizeof(short) * n_mels, cudaMemcpyHostToDevice)) != cudaSuccess) goto fail;
-    if ((e = cudaMemcpy(pl->d_count, count.data(), sizeof(short) * n_mels, cudaMemcpyHostToDevice)) != cudaSuccess) goto fail;
-    if ((e = cudaMemcpy(pl->d_offset, offset.data(), sizeof(short) * n_mels, cudaMemcpyHostToDevice)) != cudaSuccess) goto fail;
+    pl->bank_slot = acquire_bank_slot(device, mb, &e);
+    if (e != cudaSuccess) goto fail;
+    if (pl->bank_slot < 0) {
+        *why = "too many distinct mel filter banks on this device (at most 4 at a time)";
+        delete pl;
+        return cudaErrorInvalidValue;
+    }
     *out = pl;
     return cudaSuccess;
 fail:
@@ -352,10 +383,7 @@ fail:
 
 void logmel_plan_destroy(LogmelPlan* pl) {
     if (!pl) return;
-    cudaFree(pl->d_melw);
-    cudaFree(pl->d_start);
-    cudaFree(pl->d_count);
-    cudaFree(pl->d_offset);
+    release_bank_slot(pl->device, pl->bank_slot);
     cudaFree(pl->d_gmax);
     cudaFree(pl->d_tile_min);
     delete pl;
@@ -398,11 +426,7 @@ cudaError_t logmel_run(LogmelPlan* pl, const float* pcm, int batch, long long n_
     p.out_stride = (long long)pl->n_mels * frames_out;
     p.gmax = pl->d_gmax;
     p.tile_min = pl->d_tile_min;
-    p.melw = pl->d_melw;
-    p.mstart = pl->d_start;
-    p.mcount = pl->d_count;
-    p.moffset = pl->d_offset;
-    p.n_weights = pl->n_weights;
+    p.bank_slot = pl->bank_slot;
     int n_launch = 0;
     if ((e = cudaMemsetAsync(pl->d_gmax, 0, sizeof(unsigned) * batch, stream)) != cudaSuccess) return e;
     const long long total = (long long)batch * tiles;

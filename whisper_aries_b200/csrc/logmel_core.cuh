@@ -196,20 +196,53 @@ ARIES_HD void stage2_power(float* P, int q, int lane, float (&yr)[20], float (&y
 
 // ------------------------------------------------------------------------------------------- mel projection
 // Sparse triangular filters: filter m covers bins [start[m], start[m] + count[m]) with weights w[offset[m] + t]
-// (already multiplied by 0.25).  Returns sum_t w P[bin][col].
+// (already multiplied by 0.25).  One call does both halves of the tile for one lane: frames `lane` and `lane + 32`.
+constexpr int kMaxMelWeights = 1024;
+constexpr int kMaxMels = 256;
+
 struct MelBank {
-    const float* weights;
-    const short* start;
-    const short* count;
-    const short* offset;
+    float w[kMaxMelWeights];
+    short start[kMaxMels];
+    short count[kMaxMels];
+    short offset[kMaxMels];
 };
 
-ARIES_HD float mel_dot(const float* P, const MelBank& mb, int m, int col) {
-    const int s = mb.start[m], n = mb.count[m];
-    const float* w = mb.weights + mb.offset[m];
-    float acc = 0.0f;
-    for (int t = 0; t < n; ++t) acc += w[t] * P[(s + t) * kTileFrames + col];
-    return acc;
+ARIES_HD void mel_dot2(const float* P, const MelBank& mb, int m, int lane, float& acc0, float& acc1) {
+    const int n = mb.count[m];
+    const float* w = mb.w + mb.offset[m];
+    const float* pp = P + mb.start[m] * kTileFrames + lane;
+    float a0 = 0.0f, a1 = 0.0f;
+#pragma unroll 4
+    for (int t = 0; t < n; ++t) {
+        const float wt = w[t];
+        a0 = fmaf(wt, pp[t * kTileFrames], a0);
+        a1 = fmaf(wt, pp[t * kTileFrames + 32], a1);
+    }
+    acc0 = a0;
+    acc1 = a1;
+}
+
+// Fills a MelBank from a dense [n_mels, 201] filter matrix; returns false if it has more than 1024 taps.
+inline bool build_mel_bank(const float* filters, int n_mels, MelBank& mb) {
+    int used = 0;
+    for (int m = 0; m < kMaxMels; ++m) mb.start[m] = mb.count[m] = mb.offset[m] = 0;
+    for (int i = 0; i < kMaxMelWeights; ++i) mb.w[i] = 0.0f;
+    for (int m = 0; m < n_mels; ++m) {
+        int lo = -1, hi = -1;
+        for (int k = 0; k < kBins; ++k)
+            if (filters[m * kBins + k] != 0.0f) {
+                if (lo < 0) lo = k;
+                hi = k;
+            }
+        const int cnt = lo < 0 ? 0 : hi - lo + 1;
+        if (used + cnt > kMaxMelWeights) return false;
+        mb.start[m] = (short)(lo < 0 ? 0 : lo);
+        mb.count[m] = (short)cnt;
+        mb.offset[m] = (short)used;
+        for (int k = 0; k < cnt; ++k) mb.w[used + k] = 0.25f * filters[m * kBins + lo + k];   // power carries x4
+        used += cnt;
+    }
+    return true;
 }
 
 }  // namespace mel
