@@ -18,9 +18,13 @@ struct AttnParams {
 cudaError_t attention_init_device();
 // qk: bf16 [batch * T, 2 * d_model] (queries then keys, as the QKV GEMM writes them);
 // vt: bf16 [batch, n_heads, 64, t_pad] (values, transposed by the QKV GEMM's epilogue).
+struct AttnMaps {
+    CUtensorMap q;     // [batch, T, 2d] view, box 64 x 128 rows
+    CUtensorMap k;     // same tensor, box 64 x 64 rows
+    CUtensorMap vt;    // [batch, heads*64, T] view of the transposed values, box 64 keys x 64 rows
+};
 cudaError_t attention_make_maps(const void* qk, const void* vt, int batch, int T, int d_model, int n_heads, int t_pad,
-                                CUtensorMap* map_qk, CUtensorMap* map_vt);
-cudaError_t attention_launch(const CUtensorMap& map_qk, const CUtensorMap& map_vt, const AttnParams& p,
-                             cudaStream_t stream);
+                                AttnMaps* maps);
+cudaError_t attention_launch(const AttnMaps& maps, const AttnParams& p, cudaStream_t stream);
 
 }  // namespace aries

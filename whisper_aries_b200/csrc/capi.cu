@@ -407,11 +407,11 @@ int aries_test_attention(aries_ctx* ctx, const void* qk, const void* vt, int bat
     int rc = use(ctx);
     if (rc) return rc;
     if ((rc = ensure_kernels(ctx))) return rc;
-    CUtensorMap mq, mv;
-    cudaError_t e = aries::attention_make_maps(qk, vt, batch, T, n_heads * 64, n_heads, t_pad, &mq, &mv);
+    aries::AttnMaps maps;
+    cudaError_t e = aries::attention_make_maps(qk, vt, batch, T, n_heads * 64, n_heads, t_pad, &maps);
     if (e != cudaSuccess) return fail_cuda("attention tensor maps", e);
     aries::AttnParams p{batch, T, n_heads * 64, n_heads, out};
-    if ((e = aries::attention_launch(mq, mv, p, static_cast<cudaStream_t>(stream))) != cudaSuccess)
+    if ((e = aries::attention_launch(maps, p, static_cast<cudaStream_t>(stream))) != cudaSuccess)
         return fail_cuda("attention_launch", e);
     return ARIES_OK;
 }

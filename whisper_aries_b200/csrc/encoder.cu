@@ -63,7 +63,8 @@ struct EncoderPlan {
     // activation tensor maps, cached per (workspace, batch)
     const void* cached_ws = nullptr;
     int cached_batch = 0;
-    CUtensorMap a_mel{}, a_c1{}, a_y{}, a_ctx{}, a_h{}, a_qk{}, a_vt{};
+    CUtensorMap a_mel{}, a_c1{}, a_y{}, a_ctx{}, a_h{};
+    AttnMaps a_attn{};
     int last_launches = 0;
     Profiler prof;
     std::string error;
@@ -320,7 +321,7 @@ cudaError_t encoder_run(EncoderPlan* pl, const float* mel, int batch, int frames
         ARIES_TRY(map2d(&pl->a_y, y, d, M, 128), "tensor map (y)");
         ARIES_TRY(map2d(&pl->a_ctx, ctx, d, M, 128), "tensor map (ctx)");
         ARIES_TRY(map2d(&pl->a_h, h, f, M, 128), "tensor map (h)");
-        ARIES_TRY(attention_make_maps(qk, vt, batch, T, d, c.n_heads, pl->t_pad, &pl->a_qk, &pl->a_vt), "tensor map (attention)");
+        ARIES_TRY(attention_make_maps(qk, vt, batch, T, d, c.n_heads, pl->t_pad, &pl->a_attn), "tensor map (attention)");
         pl->cached_ws = workspace;
         pl->cached_batch = batch;
     }
@@ -378,7 +379,7 @@ cudaError_t encoder_run(EncoderPlan* pl, const float* mel, int batch, int frames
         ARIES_TRY(gemm_launch(EPI_QKV_SPLIT_BF16, pl->a_y, lw.m_qkv, g, pl->sm_count, stream), "qkv projection");
         pl->prof.end(stream);
         pl->prof.begin(KC_ATTENTION, stream);
-        ARIES_TRY(attention_launch(pl->a_qk, pl->a_vt, ap, stream), "attention");
+        ARIES_TRY(attention_launch(pl->a_attn, ap, stream), "attention");
         pl->prof.end(stream);
         g = plain(d, d);
         g.bias = lw.bo; g.resid = x; g.out = x;

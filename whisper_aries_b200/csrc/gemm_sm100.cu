@@ -170,9 +170,27 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             const int t_own = r_own - b_own * p.p_in;
             const bool valid_own = (r_own < p.M) && (t_own < p.t_valid);
 
+            // residual / position rows do not depend on the accumulator: fetch chunk 0's before waiting for the MMA
+            // and chunk c+1's while chunk c is transposed, so their DRAM latency is off the critical path
+            constexpr bool kHasAdd = (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_GELU_POS_F32);
+            float4 add[2][8];
+            auto load_add = [&](int c, float4 (&dst)[8]) {
+                const int nc = n0 + c * 32;
+                if (EPI == EPI_BIAS_RESID_F32) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        dst[i] = *reinterpret_cast<const float4*>(p.resid + row_off_c[i] + nc + 4 * c4);
+                } else if (EPI == EPI_BIAS_GELU_POS_F32) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        dst[i] = __ldg(reinterpret_cast<const float4*>(p.pos + (long long)t_c[i] * p.N + nc) + c4);
+                }
+            };
+            if (kHasAdd) load_add(0, add[0]);
+
             mbar_wait(&tfull_bar[as], aphase);
             tc_fence_after();
-#pragma unroll 1
+#pragma unroll
             for (int c = 0; c < kChunks; ++c) {
                 uint32_t acc[32];
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN + half * (BN / 2) + c * 32;
@@ -196,6 +214,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     }
                     continue;
                 }
+                if (kHasAdd && c + 1 < kChunks) load_add(c + 1, add[(c + 1) & 1]);
                 // phase 1: own row -> staging, 16-byte column j stored at j ^ (row & 7)  (conflict-free both ways)
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
@@ -206,16 +225,6 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 // phase 2: 8 lanes per row; bias / activation / residual applied on the way out.  The residual /
                 // position loads of all 8 rows are issued together, before anything depends on them.
                 const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + nc) + c4);
-                float4 add[8];
-                if (EPI == EPI_BIAS_RESID_F32) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        add[i] = *reinterpret_cast<const float4*>(p.resid + row_off_c[i] + nc + 4 * c4);
-                } else if (EPI == EPI_BIAS_GELU_POS_F32) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        add[i] = __ldg(reinterpret_cast<const float4*>(p.pos + (long long)t_c[i] * p.N + nc) + c4);
-                }
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int rl = 4 * i + sub_row;
@@ -234,7 +243,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     } else {
                         if (ok)
                             *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off) =
-                                make_float4(v.x + add[i].x, v.y + add[i].y, v.z + add[i].z, v.w + add[i].w);
+                                make_float4(v.x + add[c & 1][i].x, v.y + add[c & 1][i].y, v.z + add[c & 1][i].z,
+                                            v.w + add[c & 1][i].w);
                     }
                 }
                 __syncwarp();
