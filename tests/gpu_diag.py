@@ -178,10 +178,11 @@ def diag_ln():
 def diag_attn():
     ctx = _lib.Context.get(0)
     g = torch.Generator(device="cpu").manual_seed(1)
-    for (B_, T_, H) in ((1, 128, 1), (1, 256, 2), (2, 1500, 2), (1, 1500, 20)):
+    for (B_, T_, H, qs) in ((1, 128, 1, 1.0), (1, 256, 2, 1.0), (1, 300, 3, 1.0), (1, 77, 1, 3.0), (2, 1500, 2, 1.0),
+                            (2, 1500, 2, 5.0), (1, 1500, 20, 1.0), (8, 1500, 20, 1.5)):
         d = 64 * H
         t_pad = (T_ + 7) // 8 * 8
-        q = torch.randn(B_, T_, H, 64, generator=g).to(dev)
+        q = torch.randn(B_, T_, H, 64, generator=g).to(dev) * qs
         k = torch.randn(B_, T_, H, 64, generator=g).to(dev)
         v = torch.randn(B_, T_, H, 64, generator=g).to(dev)
         qk = torch.cat([q.reshape(B_ * T_, d), k.reshape(B_ * T_, d)], dim=1).bfloat16().contiguous()
@@ -194,7 +195,7 @@ def diag_attn():
         att = torch.softmax(qf @ kf.transpose(-1, -2) / 8.0, dim=-1)
         ref = (att @ vf).permute(0, 2, 1, 3).reshape(B_ * T_, d)
         err = (out.float() - ref).abs()
-        print(f"attn B={B_} T={T_} H={H} rc={rc} max_err={err.nan_to_num(1e9).max().item():.3e} "
+        print(f"attn B={B_} T={T_} H={H} qscale={qs} rc={rc} max_err={err.nan_to_num(1e9).max().item():.3e} "
               f"nan={torch.isnan(out.float()).sum().item()} ref_max={ref.abs().max().item():.2f}", flush=True)
         if B_ * H * T_ >= 30000:
             def run():

@@ -1,17 +1,21 @@
 // K6: fused non-causal self-attention for sm_100a (head_dim 64): softmax(Q K^T / 8) V without ever writing the
 // [T, T] score matrix to HBM (CT2 runs this as batched GEMM -> softmax kernel -> batched GEMM).
 //
-// One CTA per (128-query tile, head, batch item), two CTAs resident per SM (97 KB of shared memory and 256 TMEM
-// columns each).  Keys are walked in tiles of 64:
-//   warp 0   lane 0: TMA for Q and the K ring (3 x 8 KB); lane 1: TMA for the V^T ring (3 x 8 KB)
-//   warp 1   tcgen05.mma  S_j = Q K_j^T (M128 N64 K64) into one of TWO TMEM score buffers, issued two tiles ahead of
-//            the softmax, and O += P_j V_j (M128 N64 K64) as soon as P_j is published
-//   warps 2-5 one query row per thread: tcgen05.ld S_j (64 values, kept in registers), row max,
-//            p = exp2(s*c - m_ref*c) in f32 (every 4th one as an FMA-pipe polynomial to unload the MUFU), bf16 P_j
-//            into one of two 128B-swizzled K-major shared tiles.  O accumulates in TMEM and is rescaled
-//            (tcgen05.ld / st) only when a row's maximum grew by more than 2^8 since the last rescale.
-// Because S is double-buffered, the softmax warps never wait for the tensor pipe in steady state and the MMAs of
-// tile j overlap the exponentials of tile j+1; the kernel is bound by MUFU + issue slots of the softmax warps.
+// One CTA per (256-query block, head, batch item), one CTA per SM (all 512 TMEM columns, 145 KB of shared memory).
+// The 256 queries are two tiles A and B of 128 rows that share every K / V tile; keys are walked in tiles of 128:
+//   warps 0-3  softmax of tile A, warps 4-7 softmax of tile B: one query row per thread (row == TMEM lane).
+//              Pass 1 reads S_j (tcgen05.ld, 4 x 32 columns) for the row maximum, pass 2 re-reads it chunk by chunk,
+//              p = exp2(s*c - m_ref*c) in f32, and writes bf16 P_j back INTO the columns S_j occupied (tcgen05.st;
+//              chunk c of P covers columns [16c, 16c+16), which pass 2 has already consumed).  P never touches
+//              shared memory.  O accumulates in TMEM and is rescaled (tcgen05.ld / st) only when a row's maximum
+//              grew by more than 2^8 since the last rescale.
+//   warp 8     lane 0: TMA for both Q tiles and the K ring (3 x 16 KB); lane 1: TMA for the V^T ring (3 x 2 x 8 KB)
+//   warp 9     tcgen05.mma, one thread:  S_g = Q_g K_j^T (SS, M128 N128 K64) and O_g += P_g [V_j | 1] (TS: the A
+//              operand is P_g in tensor memory; M128 N80 K128).  Row 64 of the B operand is all ones, so column 64 of
+//              O accumulates the row sums of the bf16-rounded P on the tensor core.
+// Issue order QK_A(0) QK_B(0) | PV_A(j) QK_A(j+1) PV_B(j) QK_B(j+1) ...: while the tensor pipe turns P_A(j) into
+// S_A(j+1) the softmax warps of tile B (which share the four schedulers / MUFUs with those of tile A) are in their
+// exponential phase, and vice versa, so the MUFU -- the bound of this kernel at head_dim 64 -- stays busy.
 // Q and K are read straight out of the QKV GEMM's row-major [B*T, 2d] output through a 3-D tensor map; V arrives
 // pre-transposed ([B, h, 64, t_pad]) from that GEMM's epilogue so that both MMAs use K-major operands.
 // Keys >= T are zero-filled by TMA and masked to -inf here; query rows >= T are computed and dropped.
@@ -24,21 +28,26 @@ namespace aries {
 
 namespace {
 
-constexpr int kBlockQ = 128;
-constexpr int kBlockKV = 64;
+constexpr int kBlockQ = 128;                             // rows per query tile (= TMEM lanes)
+constexpr int kQTiles = 2;                               // query tiles per CTA
+constexpr int kBlockKV = 128;
 constexpr int kHeadDim = 64;
 constexpr int kOCols = 80;                               // 64 output columns + the row-sum column (+ 15 of padding)
-constexpr int kThreads = 192;
-constexpr int kSoftmaxThreads = 128;
-constexpr int kKVStages = 3;
+constexpr int kSoftmaxThreads = kBlockQ;                 // per query tile
+constexpr int kThreads = kQTiles * kSoftmaxThreads + 64;
+constexpr int kTmaWarp = kQTiles * 4;
+constexpr int kMmaWarp = kTmaWarp + 1;
+constexpr int kKStages = 3;
+constexpr int kVStages = 3;
 
-constexpr int kQBytes = kBlockQ * kHeadDim * 2;          // 16 KB
-constexpr int kKBytes = kBlockKV * kHeadDim * 2;         // 8 KB
-constexpr int kVTmaBytes = kHeadDim * kBlockKV * 2;      // 8 KB written by TMA ...
-constexpr int kVBytes = kOCols * kBlockKV * 2;           // ... + 2 KB constant tail: a row of ones and 15 rows of zeros
-constexpr int kPBytes = kBlockQ * kBlockKV * 2;          // 16 KB (one 128B-swizzled K-major tile)
-constexpr int kSmemBytes = kQBytes + kKVStages * (kKBytes + kVBytes) + 2 * kPBytes + 256 + 1024;   // 105,728 B
-constexpr uint32_t kTmemCols = 256;                      // S0 [0,64) S1 [64,128) O [128,208); two CTAs per SM
+constexpr int kQTileBytes = kBlockQ * kHeadDim * 2;      // 16 KB
+constexpr int kKBytes = kBlockKV * kHeadDim * 2;         // 16 KB (128 keys x 128 B, one 128B-swizzled K-major tile)
+constexpr int kVAtomTma = kHeadDim * 64 * 2;             // 8 KB written by TMA per 64-key swizzle atom ...
+constexpr int kVAtomBytes = kOCols * 64 * 2;             // ... + 2 KB constant tail: a row of ones and 15 rows of zeros
+constexpr int kVBytes = 2 * kVAtomBytes;                 // 20 KB per 128-key stage
+constexpr int kSmemBytes = kQTiles * kQTileBytes + kKStages * kKBytes + kVStages * kVBytes + 256 + 1024;   // 144,640 B
+constexpr uint32_t kTmemCols = 512;                      // S_A [0,128) S_B [128,256) O_A [256,336) O_B [336,416)
+constexpr uint32_t kTmemO = 256;
 constexpr float kScale = 0.18033688011112042f;           // log2(e) / sqrt(64)
 constexpr float kRescaleThreshold = 8.0f;                // lazy rescale: only when the row max grew by > 2^8
 
@@ -69,22 +78,23 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
         : "memory");
 }
 
-// Row maximum of the 64 scores of one tile (tree-shaped so the compares are independent).
-__device__ __forceinline__ float max64(const uint32_t (&s0)[32], const uint32_t (&s1)[32]) {
+// Maximum of 32 scores (tree-shaped so the compares are independent).
+__device__ __forceinline__ float max32(const uint32_t (&s)[32]) {
     float m[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const float a = fmaxf(__uint_as_float(s0[4 * k]), __uint_as_float(s0[4 * k + 1]));
-        const float b = fmaxf(__uint_as_float(s0[4 * k + 2]), __uint_as_float(s0[4 * k + 3]));
-        const float c = fmaxf(__uint_as_float(s1[4 * k]), __uint_as_float(s1[4 * k + 1]));
-        const float d = fmaxf(__uint_as_float(s1[4 * k + 2]), __uint_as_float(s1[4 * k + 3]));
-        m[k] = fmaxf(fmaxf(a, b), fmaxf(c, d));
-    }
+    for (int k = 0; k < 8; ++k)
+        m[k] = fmaxf(fmaxf(__uint_as_float(s[4 * k]), __uint_as_float(s[4 * k + 1])),
+                     fmaxf(__uint_as_float(s[4 * k + 2]), __uint_as_float(s[4 * k + 3])));
     return fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])), fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7])));
 }
 
-// p = exp2(s * c - m * c) for 32 scores -> 16 packed bf16x2.  The scale / offset is a packed f32x2 FMA (two scores per
-// instruction); with kPoly every 4th exponential runs on the FMA pipe instead of the MUFU.
+// keys >= kv_valid do not exist: score -> -inf (only the last key tile takes this path)
+__device__ __forceinline__ void mask32(uint32_t (&s)[32], int first_col, int kv_valid) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+        if (first_col + i >= kv_valid) s[i] = 0xFF800000u;
+}
+
 // Compiler-only join point: all 32 values must exist before anything after it may be scheduled.  Without it ptxas
 // interleaves every MUFU.EX2 pair with the F2FP that consumes it and, having only six scoreboard slots, keeps just a
 // few exponentials in flight per warp (measured: XU pipe 52 % busy).  With it the 32 MUFUs issue back to back.
@@ -97,8 +107,9 @@ __device__ __forceinline__ void join32(float (&e)[32]) {
                    "+f"(e[30]), "+f"(e[31]));
 }
 
-// p = exp2(s * c - m * c) for 32 scores -> 16 packed bf16x2.  The scale / offset is a packed f32x2 FMA (two scores per
-// instruction); with kPoly every 4th exponential runs on the FMA pipe instead of the MUFU.
+// p = exp2(s * c - m * c) for 32 scores -> 16 packed bf16x2 (low half = the lower key index).  The scale / offset is
+// a packed f32x2 FMA (two scores per instruction); with kPoly every 8th exponential runs on the FMA pipe instead of
+// the MUFU.
 template <bool kPoly>
 __device__ __forceinline__ void exp_pack(const uint32_t (&s)[32], float neg_m, uint32_t (&out)[16]) {
     const float2 c2 = make_float2(kScale, kScale);
@@ -118,214 +129,223 @@ __device__ __forceinline__ void exp_pack(const uint32_t (&s)[32], float neg_m, u
     for (int i = 0; i < 32; i += 2) out[i >> 1] = pack_bf16x2(e[i], e[i + 1]);
 }
 
-__device__ __forceinline__ void store_p(uint8_t* p_row, int swz, int chunk0, const uint32_t (&pk)[16]) {
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-        uint4 q;
-        q.x = pk[4 * g + 0]; q.y = pk[4 * g + 1]; q.z = pk[4 * g + 2]; q.w = pk[4 * g + 3];
-        *reinterpret_cast<uint4*>(p_row + (((chunk0 + g) ^ swz) << 4)) = q;      // 16-byte chunk = 8 keys
-    }
-}
-
 template <bool kPoly>
-__global__ void __launch_bounds__(kThreads, 2)
-attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                     const __grid_constant__ CUtensorMap tmap_vt, const AttnParams p) {
+__global__ void __launch_bounds__(kThreads, 1)
+attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_constant__ CUtensorMap tmap_vt,
+                     const AttnParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
-    uint8_t* sQ = smem;
-    uint8_t* sK = sQ + kQBytes;                          // [stage][8 KB]
-    uint8_t* sV = sK + kKVStages * kKBytes;              // [stage][10 KB]
-    uint8_t* sP = sV + kKVStages * kVBytes;              // [2][16 KB]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kPBytes);
+    uint8_t* sQ = smem;                                  // [tile][16 KB]
+    uint8_t* sK = sQ + kQTiles * kQTileBytes;            // [stage][16 KB]
+    uint8_t* sV = sK + kKStages * kKBytes;               // [stage][atom][10 KB]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kVStages * kVBytes);
     uint64_t* q_full = bars;                             // 1
     uint64_t* k_full = bars + 1;                         // [3]
     uint64_t* v_full = bars + 4;                         // [3]
     uint64_t* k_empty = bars + 7;                        // [3]
     uint64_t* v_empty = bars + 10;                       // [3]
-    uint64_t* s_full = bars + 13;                        // [2]
-    uint64_t* p_full = bars + 15;                        // [2]
-    uint64_t* pv_done = bars + 17;                       // [2]  O += P_j V_j retired (j & 1)
-    uint64_t* o_full = bars + 19;                        // 1
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+    uint64_t* s_full = bars + 13;                        // [tile]  S_g(j) written (and every earlier MMA retired)
+    uint64_t* p_full = bars + 15;                        // [tile]  P_g(j) published by the 128 softmax threads
+    uint64_t* o_full = bars + 17;                        // [tile]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int q0 = blockIdx.x * kBlockQ;
+    const int q0 = blockIdx.x * (kQTiles * kBlockQ);
     const int head = blockIdx.y;
     const int b = blockIdx.z;
     const int n_kv = (p.T + kBlockKV - 1) / kBlockKV;
 
     if (threadIdx.x == 0) {
-        tma_prefetch_desc(&tmap_q);
-        tma_prefetch_desc(&tmap_k);
+        tma_prefetch_desc(&tmap_qk);
         tma_prefetch_desc(&tmap_vt);
         mbar_init(q_full, 1);
-        for (int s = 0; s < kKVStages; ++s) {
+        for (int s = 0; s < kKStages; ++s) {
             mbar_init(&k_full[s], 1);
-            mbar_init(&v_full[s], 1);
             mbar_init(&k_empty[s], 1);
+        }
+        for (int s = 0; s < kVStages; ++s) {
+            mbar_init(&v_full[s], 1);
             mbar_init(&v_empty[s], 1);
         }
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(&s_full[s], 1);
-            mbar_init(&p_full[s], kSoftmaxThreads);
-            mbar_init(&pv_done[s], 1);
+        for (int g = 0; g < kQTiles; ++g) {
+            mbar_init(&s_full[g], 1);
+            mbar_init(&p_full[g], kSoftmaxThreads);
+            mbar_init(&o_full[g], 1);
         }
-        mbar_init(o_full, 1);
         fence_mbar_init();
     }
-    // Constant tail of every V stage: B-operand rows 64..79 of the O MMA.  Row 64 is all ones, so column 64 of O
+    // Constant tail of every V atom: B-operand rows 64..79 of the O MMA.  Row 64 is all ones, so column 64 of O
     // accumulates the row sums of (the bf16-rounded) P on the tensor core; rows 65..79 pad N to a legal 80.
-    for (int i = threadIdx.x; i < kKVStages * 512; i += kThreads) {
-        const int s = i >> 9, w = i & 511;               // 512 words per 2 KB tail
-        reinterpret_cast<uint32_t*>(sV + s * kVBytes + kVTmaBytes)[w] = (w < 32) ? 0x3F803F80u : 0u;
+    for (int i = threadIdx.x; i < kVStages * 2 * 512; i += kThreads) {
+        const int atom = i >> 9, w = i & 511;            // 512 words per 2 KB tail
+        reinterpret_cast<uint32_t*>(sV + atom * kVAtomBytes + kVAtomTma)[w] = (w < 32) ? 0x3F803F80u : 0u;
     }
     fence_proxy_async_smem();
-    if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+    if (warp == kMmaWarp) tmem_alloc<kTmemCols>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_o = tmem_base + 128;
 
-    if (warp == 0) {
+    if (warp == kTmaWarp) {
         // ---------------------------------------------------------------- TMA producers: lane 0 = Q + K, lane 1 = V
-        // (two independent rings: a K tile is consumed two softmax phases before the V tile of the same index)
         if (lane == 0) {
-            mbar_expect_tx(q_full, kQBytes);
-            tma_load_3d(sQ, &tmap_q, q_full, head * kHeadDim, q0, b);
+            mbar_expect_tx(q_full, kQTiles * kQTileBytes);
+            for (int g = 0; g < kQTiles; ++g)
+                tma_load_3d(sQ + g * kQTileBytes, &tmap_qk, q_full, head * kHeadDim, q0 + g * kBlockQ, b);
             for (int j = 0; j < n_kv; ++j) {
-                const int s = j % kKVStages;
-                if (j >= kKVStages) mbar_wait_relaxed(&k_empty[s], (j / kKVStages - 1) & 1);
+                const int s = j % kKStages;
+                if (j >= kKStages) mbar_wait_relaxed(&k_empty[s], (j / kKStages - 1) & 1);
                 mbar_expect_tx(&k_full[s], kKBytes);
-                tma_load_3d(sK + s * kKBytes, &tmap_k, &k_full[s], p.d_model + head * kHeadDim, j * kBlockKV, b);
+                tma_load_3d(sK + s * kKBytes, &tmap_qk, &k_full[s], p.d_model + head * kHeadDim, j * kBlockKV, b);
             }
         } else if (lane == 1) {
             for (int j = 0; j < n_kv; ++j) {
-                const int s = j % kKVStages;
-                if (j >= kKVStages) mbar_wait_relaxed(&v_empty[s], (j / kKVStages - 1) & 1);
-                mbar_expect_tx(&v_full[s], kVTmaBytes);
+                const int s = j % kVStages;
+                if (j >= kVStages) mbar_wait_relaxed(&v_empty[s], (j / kVStages - 1) & 1);
+                mbar_expect_tx(&v_full[s], 2 * kVAtomTma);
                 tma_load_3d(sV + s * kVBytes, &tmap_vt, &v_full[s], j * kBlockKV, head * kHeadDim, b);
+                tma_load_3d(sV + s * kVBytes + kVAtomBytes, &tmap_vt, &v_full[s], j * kBlockKV + 64, head * kHeadDim,
+                            b);
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == kMmaWarp) {
         if (lane == 0) {
             // ---------------------------------------------------------------- MMA issuer
             constexpr uint32_t idesc_s = umma_idesc_bf16(kBlockQ, kBlockKV, false, false);
             constexpr uint32_t idesc_o = umma_idesc_bf16(kBlockQ, kOCols, false, false);
             constexpr uint64_t desc_hi = umma_smem_desc_hi(16, 1024);
             const uint32_t aQ = base;
-            const uint32_t aK = aQ + kQBytes;
-            const uint32_t aV = aK + kKVStages * kKBytes;
-            const uint32_t aP = aV + kKVStages * kVBytes;
-            auto issue_qk = [&](int j) {
-                const int s = j % kKVStages;
-                mbar_wait(&k_full[s], (j / kKVStages) & 1);
-                tc_fence_after();
+            const uint32_t aK = aQ + kQTiles * kQTileBytes;
+            const uint32_t aV = aK + kKStages * kKBytes;
+            auto issue_qk = [&](int g, int j) {          // S_g = Q_g K_j^T
+                const int s = j % kKStages;
+                if (g == 0) {
+                    mbar_wait(&k_full[s], (j / kKStages) & 1);
+                    tc_fence_after();
+                }
 #pragma unroll
                 for (int k = 0; k < kHeadDim / 16; ++k)
-                    umma_bf16_ss(tmem_base + (j & 1) * kBlockKV, umma_smem_desc(aQ + k * 32, desc_hi),
+                    umma_bf16_ss(tmem_base + g * kBlockKV, umma_smem_desc(aQ + g * kQTileBytes + k * 32, desc_hi),
                                  umma_smem_desc(aK + s * kKBytes + k * 32, desc_hi), idesc_s, k != 0);
-                umma_commit(&k_empty[s]);
-                umma_commit(&s_full[j & 1]);
+                if (g == kQTiles - 1) umma_commit(&k_empty[s]);
+                umma_commit(&s_full[g]);
             };
             mbar_wait(q_full, 0);
-            issue_qk(0);
-            if (n_kv > 1) issue_qk(1);
+            for (int g = 0; g < kQTiles; ++g) issue_qk(g, 0);
             for (int j = 0; j < n_kv; ++j) {
-                const int s = j % kKVStages;
-                // O (+)= P_j [V_j | 1]: P published (so S_j is fully read and O rescaled if it had to be)
-                mbar_wait(&p_full[j & 1], (j >> 1) & 1);
-                mbar_wait(&v_full[s], (j / kKVStages) & 1);
-                tc_fence_after();
+                const int s = j % kVStages;
+                for (int g = 0; g < kQTiles; ++g) {
+                    // O_g (+)= P_g(j) [V_j | 1]: P published (so S_g(j) is fully consumed and O_g rescaled if needed)
+                    mbar_wait(&p_full[g], j & 1);
+                    if (g == 0) mbar_wait(&v_full[s], (j / kVStages) & 1);
+                    tc_fence_after();
 #pragma unroll
-                for (int k = 0; k < kBlockKV / 16; ++k)
-                    umma_bf16_ss(tmem_o, umma_smem_desc(aP + (j & 1) * kPBytes + k * 32, desc_hi),
-                                 umma_smem_desc(aV + s * kVBytes + k * 32, desc_hi), idesc_o, (j > 0) || (k != 0));
-                umma_commit(&v_empty[s]);
-                umma_commit(&pv_done[j & 1]);
-                if (j == n_kv - 1) umma_commit(o_full);
-                if (j + 2 < n_kv) issue_qk(j + 2);       // S buffer j & 1 is free again
+                    for (int k = 0; k < kBlockKV / 16; ++k)
+                        umma_bf16_ts(tmem_base + kTmemO + g * kOCols, tmem_base + g * kBlockKV + k * 8,
+                                     umma_smem_desc(aV + s * kVBytes + (k >> 2) * kVAtomBytes + (k & 3) * 32, desc_hi),
+                                     idesc_o, (j > 0) || (k != 0));
+                    if (g == kQTiles - 1) umma_commit(&v_empty[s]);
+                    // S_g(j+1) overwrites P_g(j): the tensor pipe executes in issue order, so PV_g(j) has read it
+                    if (j + 1 < n_kv) issue_qk(g, j + 1);
+                    else umma_commit(&o_full[g]);
+                }
             }
         }
     } else {
         // -------------------------------------------------------------------- softmax warps: one query row per thread
+        const int g = warp >> 2;                             // query tile
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;                 // query row inside the tile == TMEM lane
         const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+        const uint32_t tmem_s = tmem_base + lane_addr + g * kBlockKV;          // S_g, and P_g on top of it
+        const uint32_t tmem_o = tmem_base + lane_addr + kTmemO + g * kOCols;
         float m_ref = 0.0f;
-        const int swz = row & 7;
-        uint8_t* p_row0 = sP + (row >> 3) * 1024 + (row & 7) * 128;
 
+#pragma unroll 1
         for (int j = 0; j < n_kv; ++j) {
-            const int buf = j & 1;
-            // S_j ready.  The tensor pipe retires in issue order and S_j was issued after O += P_{j-2} V_{j-2}, so the
-            // P buffer this tile overwrites is no longer being read.
-            mbar_wait(&s_full[buf], (j >> 1) & 1);
+            // S_g(j) ready; the commit also covers O_g += P_g(j-1) V_(j-1), so O_g may be rescaled below
+            mbar_wait(&s_full[g], j & 1);
             tc_fence_after();
-            uint32_t s0[32], s1[32];
-            tmem_ld_32x32b_x32(tmem_base + lane_addr + buf * kBlockKV, s0);
-            tmem_ld_32x32b_x32(tmem_base + lane_addr + buf * kBlockKV + 32, s1);
-            tmem_ld_wait_on(s0);
-            tmem_ld_wait_on(s1);
             const int kv_valid = p.T - j * kBlockKV;
-            if (kv_valid < kBlockKV) {                       // only the last tile: keys >= T do not exist
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    if (i >= kv_valid) s0[i] = 0xFF800000u;  // -inf
-                    if (32 + i >= kv_valid) s1[i] = 0xFF800000u;
+            const bool tail = kv_valid < kBlockKV;
+            // ---- pass 1: row maximum of the 128 scores
+            float m_tile;
+            {
+                uint32_t s0[32], s1[32];
+                tmem_ld_32x32b_x32(tmem_s, s0);
+                tmem_ld_32x32b_x32(tmem_s + 32, s1);
+                tmem_ld_wait_on(s0);
+                tmem_ld_wait_on(s1);
+                if (tail) {
+                    mask32(s0, 0, kv_valid);
+                    mask32(s1, 32, kv_valid);
                 }
+                m_tile = fmaxf(max32(s0), max32(s1));
+                tmem_ld_32x32b_x32(tmem_s + 64, s0);
+                tmem_ld_32x32b_x32(tmem_s + 96, s1);
+                tmem_ld_wait_on(s0);
+                tmem_ld_wait_on(s1);
+                if (tail) {
+                    mask32(s0, 64, kv_valid);
+                    mask32(s1, 96, kv_valid);
+                }
+                m_tile = fmaxf(m_tile, fmaxf(max32(s0), max32(s1)));
             }
-            uint32_t pk0[16], pk1[16];
-            bool redo = (j == 0);
-            if (j > 0) {
-                // speculate that the running reference maximum still holds (it almost always does)
-                exp_pack<kPoly>(s0, -m_ref * kScale, pk0);
-                exp_pack<kPoly>(s1, -m_ref * kScale, pk1);
-            }
-            const float m_tile = max64(s0, s1);
             if (j == 0) {
                 m_ref = m_tile;
             } else {
                 // lazy rescale: keep exponentiating against a stale maximum until it is off by more than 2^8
                 const bool need = (m_tile - m_ref) * kScale > kRescaleThreshold;
                 if (__any_sync(0xffffffffu, need)) {
-                    redo = true;
-                    mbar_wait(&pv_done[buf ^ 1], ((j - 1) >> 1) & 1);      // O += P_{j-1} V_{j-1} has retired
-                    tc_fence_after();
                     const float f = need ? fast_exp2((m_ref - m_tile) * kScale) : 1.0f;
                     if (need) m_ref = m_tile;
-#pragma unroll 1
-                    for (int c = 0; c < 3; ++c) {            // 96 columns cover the 80 of O (incl. the row sums)
+                    {
                         uint32_t o[32];
-                        tmem_ld_32x32b_x32(tmem_o + lane_addr + c * 32, o);
-                        tmem_ld_wait_on(o);
+#pragma unroll 1
+                        for (int c = 0; c < 2; ++c) {
+                            tmem_ld_32x32b_x32(tmem_o + c * 32, o);
+                            tmem_ld_wait_on(o);
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
-                        tmem_st_32x32b_x32(tmem_o + lane_addr + c * 32, o);
+                            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+                            tmem_st_32x32b_x32(tmem_o + c * 32, o);
+                        }
                     }
-                    tmem_st_wait();
+                    uint32_t o16[16];                        // columns 64..79 (the row sums live in column 64)
+                    tmem_ld_32x32b_x16(tmem_o + 64, o16);
+                    tmem_ld_wait_on(o16);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) o16[i] = __float_as_uint(__uint_as_float(o16[i]) * f);
+                    tmem_st_32x32b_x16(tmem_o + 64, o16);
                 }
             }
-            if (redo) {
-                exp_pack<false>(s0, -m_ref * kScale, pk0);
-                exp_pack<false>(s1, -m_ref * kScale, pk1);
+            // ---- pass 2: exponentials, P written over the consumed part of S
+            const float neg_m = -m_ref * kScale;
+            uint32_t sa[32], sb[32];
+            tmem_ld_32x32b_x32(tmem_s, sa);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t (&cur)[32] = (c & 1) ? sb : sa;
+                uint32_t (&nxt)[32] = (c & 1) ? sa : sb;
+                tmem_ld_wait_on(cur);
+                if (c < 3) tmem_ld_32x32b_x32(tmem_s + (c + 1) * 32, nxt);
+                if (tail) mask32(cur, c * 32, kv_valid);
+                uint32_t pk[16];
+                exp_pack<kPoly>(cur, neg_m, pk);
+                tmem_st_32x32b_x16(tmem_s + c * 16, pk);
             }
-            uint8_t* p_row = p_row0 + buf * kPBytes;
-            store_p(p_row, swz, 0, pk0);
-            store_p(p_row, swz, 4, pk1);
+            tmem_st_wait();
             tc_fence_before();              // our TMEM reads / writes are complete and ordered before the arrive
-            fence_proxy_async_smem();       // P visible to the tensor core's (async-proxy) reads
-            mbar_arrive(&p_full[buf]);
+            mbar_arrive(&p_full[g]);
         }
 
-        mbar_wait(o_full, 0);
+        mbar_wait(&o_full[g], 0);
         tc_fence_after();
-        const int t = q0 + row;
-        uint32_t osum[32];
-        tmem_ld_32x32b_x32(tmem_o + lane_addr + 64, osum);       // column 64 = row sum of P
+        const int t = q0 + g * kBlockQ + row;
+        uint32_t osum[16];
+        tmem_ld_32x32b_x16(tmem_o + 64, osum);                   // column 64 = row sum of P
         tmem_ld_wait_on(osum);
         const float inv = 1.0f / __uint_as_float(osum[0]);
         __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + ((long long)b * p.T + t) * p.d_model +
@@ -333,18 +353,18 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
             uint32_t o[32];
-            tmem_ld_32x32b_x32(tmem_o + lane_addr + c * 32, o);
+            tmem_ld_32x32b_x32(tmem_o + c * 32, o);
             tmem_ld_wait_on(o);
             if (t < p.T) {
                 uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
+                for (int i = 0; i < 4; ++i) {
                     uint4 q;
-                    q.x = pack_bf16x2(__uint_as_float(o[8 * g + 0]) * inv, __uint_as_float(o[8 * g + 1]) * inv);
-                    q.y = pack_bf16x2(__uint_as_float(o[8 * g + 2]) * inv, __uint_as_float(o[8 * g + 3]) * inv);
-                    q.z = pack_bf16x2(__uint_as_float(o[8 * g + 4]) * inv, __uint_as_float(o[8 * g + 5]) * inv);
-                    q.w = pack_bf16x2(__uint_as_float(o[8 * g + 6]) * inv, __uint_as_float(o[8 * g + 7]) * inv);
-                    d4[g] = q;
+                    q.x = pack_bf16x2(__uint_as_float(o[8 * i + 0]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
+                    q.y = pack_bf16x2(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
+                    q.z = pack_bf16x2(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
+                    q.w = pack_bf16x2(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
+                    d4[i] = q;
                 }
             }
         }
@@ -353,7 +373,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == kMmaWarp) {
         tc_fence_after();
         tmem_dealloc<kTmemCols>(tmem_base);
     }
@@ -382,26 +402,24 @@ cudaError_t attention_make_maps(const void* qk, const void* vt, int batch, int T
                                         (unsigned long long)batch};
     const unsigned long long strides[3] = {2, (unsigned long long)(2 * d_model) * 2,
                                            (unsigned long long)T * (2 * d_model) * 2};
-    const unsigned box_q[3] = {64, (unsigned)kBlockQ, 1};
-    const unsigned box_k[3] = {64, (unsigned)kBlockKV, 1};
-    cudaError_t e = make_tmap_bf16(&maps->q, qk, 3, dims, strides, box_q);
+    const unsigned box_qk[3] = {64, 128, 1};             // one query tile == one key tile: 128 rows x 64 columns
+    cudaError_t e = make_tmap_bf16(&maps->qk, qk, 3, dims, strides, box_qk);
     if (e != cudaSuccess) return e;
-    if ((e = make_tmap_bf16(&maps->k, qk, 3, dims, strides, box_k)) != cudaSuccess) return e;
     const unsigned long long vdims[3] = {(unsigned long long)T, (unsigned long long)(n_heads * 64),
                                          (unsigned long long)batch};
     const unsigned long long vstrides[3] = {2, (unsigned long long)t_pad * 2,
                                             (unsigned long long)(n_heads * 64) * t_pad * 2};
-    const unsigned box_v[3] = {(unsigned)kBlockKV, 64, 1};
+    const unsigned box_v[3] = {64, 64, 1};               // one swizzle atom: 64 keys x 64 value rows
     return make_tmap_bf16(&maps->vt, vt, 3, vdims, vstrides, box_v);
 }
 
 cudaError_t attention_launch(const AttnMaps& maps, const AttnParams& p, cudaStream_t stream) {
     if (p.d_model != p.n_heads * kHeadDim || p.T <= 0 || p.batch <= 0) return cudaErrorInvalidValue;
-    dim3 grid((p.T + kBlockQ - 1) / kBlockQ, p.n_heads, p.batch);
+    dim3 grid((p.T + kQTiles * kBlockQ - 1) / (kQTiles * kBlockQ), p.n_heads, p.batch);
     if (use_poly_exp())
-        attention_fwd_kernel<true><<<grid, kThreads, kSmemBytes, stream>>>(maps.q, maps.k, maps.vt, p);
+        attention_fwd_kernel<true><<<grid, kThreads, kSmemBytes, stream>>>(maps.qk, maps.vt, p);
     else
-        attention_fwd_kernel<false><<<grid, kThreads, kSmemBytes, stream>>>(maps.q, maps.k, maps.vt, p);
+        attention_fwd_kernel<false><<<grid, kThreads, kSmemBytes, stream>>>(maps.qk, maps.vt, p);
     return cudaGetLastError();
 }
 
