@@ -19,7 +19,8 @@ cudaError_t attention_init_device();
 // qk: bf16 [batch * T, 2 * d_model] (queries then keys, as the QKV GEMM writes them);
 // vt: bf16 [batch, n_heads, 64, t_pad] (values, transposed by the QKV GEMM's epilogue).
 struct AttnMaps {
-    CUtensorMap qk;    // [batch, T, 2d] view, box 64 columns x 128 rows (one query tile or one key tile)
+    CUtensorMap q;     // [batch, T, 2d] view, box 64 columns x 128 rows (one query tile)
+    CUtensorMap k;     // same tensor, box 64 columns x 64 rows (one key tile)
     CUtensorMap vt;    // [batch, heads*64, T] view of the transposed values, box 64 keys x 64 rows
 };
 cudaError_t attention_make_maps(const void* qk, const void* vt, int batch, int T, int d_model, int n_heads, int t_pad,

@@ -1,21 +1,23 @@
 // K6: fused non-causal self-attention for sm_100a (head_dim 64): softmax(Q K^T / 8) V without ever writing the
 // [T, T] score matrix to HBM (CT2 runs this as batched GEMM -> softmax kernel -> batched GEMM).
 //
-// One CTA per (256-query block, head, batch item), one CTA per SM (all 512 TMEM columns, 145 KB of shared memory).
-// The 256 queries are two tiles A and B of 128 rows that share every K / V tile; keys are walked in tiles of 128:
-//   warps 0-3  softmax of tile A, warps 4-7 softmax of tile B: one query row per thread (row == TMEM lane).
-//              Pass 1 reads S_j (tcgen05.ld, 4 x 32 columns) for the row maximum, pass 2 re-reads it chunk by chunk,
-//              p = exp2(s*c - m_ref*c) in f32, and writes bf16 P_j back INTO the columns S_j occupied (tcgen05.st;
-//              chunk c of P covers columns [16c, 16c+16), which pass 2 has already consumed).  P never touches
+// One CTA per (256-query block, head, batch item), one CTA per SM (416 of the 512 TMEM columns, 138 KB of shared
+// memory).  The 256 queries are two tiles A and B of 128 rows that share every K / V tile; keys are walked in tiles
+// of 64 and every query tile owns TWO score buffers in tensor memory:
+//   warps 0-3  softmax of tile A, warps 4-7 softmax of tile B: one query row per thread (row == TMEM lane):
+//              tcgen05.ld S_j (64 values, kept in registers), row max, p = exp2(s*c - m_ref*c) in f32, bf16 P_j
+//              written back INTO the first 32 columns of the buffer S_j occupied (tcgen05.st) -- P never touches
 //              shared memory.  O accumulates in TMEM and is rescaled (tcgen05.ld / st) only when a row's maximum
 //              grew by more than 2^8 since the last rescale.
-//   warp 8     lane 0: TMA for both Q tiles and the K ring (3 x 16 KB); lane 1: TMA for the V^T ring (3 x 2 x 8 KB)
-//   warp 9     tcgen05.mma, one thread:  S_g = Q_g K_j^T (SS, M128 N128 K64) and O_g += P_g [V_j | 1] (TS: the A
-//              operand is P_g in tensor memory; M128 N80 K128).  Row 64 of the B operand is all ones, so column 64 of
-//              O accumulates the row sums of the bf16-rounded P on the tensor core.
-// Issue order QK_A(0) QK_B(0) | PV_A(j) QK_A(j+1) PV_B(j) QK_B(j+1) ...: while the tensor pipe turns P_A(j) into
-// S_A(j+1) the softmax warps of tile B (which share the four schedulers / MUFUs with those of tile A) are in their
-// exponential phase, and vice versa, so the MUFU -- the bound of this kernel at head_dim 64 -- stays busy.
+//   warp 8     lane 0: TMA for both Q tiles and the K ring (4 x 8 KB); lane 1: TMA for the V^T ring (4 x 8 KB)
+//   warp 9     tcgen05.mma, one thread:  S_g = Q_g K_j^T (SS, M128 N64 K64), issued TWO key tiles ahead of the
+//              softmax, and O_g += P_g [V_j | 1] (TS: the A operand is P_g in tensor memory; M128 N80 K64).  Row 64
+//              of the B operand is all ones, so column 64 of O accumulates the row sums of the bf16-rounded P on
+//              the tensor core.
+// Because S is double-buffered the softmax warps never wait for the tensor pipe in steady state.  Warp i of tile A
+// and warp i of tile B share one scheduler and its MUFU -- the bound of this kernel at head_dim 64 -- so they pass a
+// token (two named barriers per pair): one runs its 64 exponentials while the other does everything else (TMEM
+// loads, maxima, packing, stores, barrier traffic), instead of both stalling in the same phase.
 // Q and K are read straight out of the QKV GEMM's row-major [B*T, 2d] output through a 3-D tensor map; V arrives
 // pre-transposed ([B, h, 64, t_pad]) from that GEMM's epilogue so that both MMAs use K-major operands.
 // Keys >= T are zero-filled by TMA and masked to -inf here; query rows >= T are computed and dropped.
@@ -30,30 +32,43 @@ namespace {
 
 constexpr int kBlockQ = 128;                             // rows per query tile (= TMEM lanes)
 constexpr int kQTiles = 2;                               // query tiles per CTA
-constexpr int kBlockKV = 128;
+constexpr int kBlockKV = 64;
 constexpr int kHeadDim = 64;
 constexpr int kOCols = 80;                               // 64 output columns + the row-sum column (+ 15 of padding)
 constexpr int kSoftmaxThreads = kBlockQ;                 // per query tile
-constexpr int kThreads = kQTiles * kSoftmaxThreads + 64;
+constexpr int kThreads = kQTiles * kSoftmaxThreads + 32 + kQTiles * 32;
 constexpr int kTmaWarp = kQTiles * 4;
-constexpr int kMmaWarp = kTmaWarp + 1;
-constexpr int kKStages = 3;
-constexpr int kVStages = 3;
+constexpr int kMmaWarp = kTmaWarp + 1;                   // + g: one issuing warp per query tile
+constexpr int kKStages = 4;
+constexpr int kVStages = 4;
 
 constexpr int kQTileBytes = kBlockQ * kHeadDim * 2;      // 16 KB
-constexpr int kKBytes = kBlockKV * kHeadDim * 2;         // 16 KB (128 keys x 128 B, one 128B-swizzled K-major tile)
-constexpr int kVAtomTma = kHeadDim * 64 * 2;             // 8 KB written by TMA per 64-key swizzle atom ...
-constexpr int kVAtomBytes = kOCols * 64 * 2;             // ... + 2 KB constant tail: a row of ones and 15 rows of zeros
-constexpr int kVBytes = 2 * kVAtomBytes;                 // 20 KB per 128-key stage
-constexpr int kSmemBytes = kQTiles * kQTileBytes + kKStages * kKBytes + kVStages * kVBytes + 256 + 1024;   // 144,640 B
-constexpr uint32_t kTmemCols = 512;                      // S_A [0,128) S_B [128,256) O_A [256,336) O_B [336,416)
+constexpr int kKBytes = kBlockKV * kHeadDim * 2;         // 8 KB (64 keys x 128 B, one 128B-swizzled K-major tile)
+constexpr int kVTmaBytes = kHeadDim * kBlockKV * 2;      // 8 KB written by TMA ...
+constexpr int kVBytes = kOCols * kBlockKV * 2;           // ... + 2 KB constant tail: a row of ones and 15 rows of zeros
+constexpr int kSmemBytes = kQTiles * kQTileBytes + kKStages * kKBytes + kVStages * kVBytes + 256 + 1024;   // 107,776 B
+constexpr uint32_t kTmemCols = 512;                      // per tile g: S0 [128g, +64) S1 [128g+64, +64); O_g [256+80g, +80)
 constexpr uint32_t kTmemO = 256;
 constexpr float kScale = 0.18033688011112042f;           // log2(e) / sqrt(64)
 constexpr float kRescaleThreshold = 8.0f;                // lazy rescale: only when the row max grew by > 2^8
 
+// Named barriers (ids 1..8): token for the MUFU phase of the softmax-warp pair that shares a scheduler.
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int threads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
 __device__ __forceinline__ float fast_exp2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// volatile twin: stays between the named-barrier token operations that bracket the MUFU phase
+__device__ __forceinline__ float fast_exp2_ordered(float x) {
+    float y;
+    asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
 
@@ -110,7 +125,7 @@ __device__ __forceinline__ void join32(float (&e)[32]) {
 // p = exp2(s * c - m * c) for 32 scores -> 16 packed bf16x2 (low half = the lower key index).  The scale / offset is
 // a packed f32x2 FMA (two scores per instruction); with kPoly every 8th exponential runs on the FMA pipe instead of
 // the MUFU.
-template <bool kPoly>
+template <bool kPoly, bool kOrdered>
 __device__ __forceinline__ void exp_pack(const uint32_t (&s)[32], float neg_m, uint32_t (&out)[16]) {
     const float2 c2 = make_float2(kScale, kScale);
     const float2 m2 = make_float2(neg_m, neg_m);
@@ -123,32 +138,34 @@ __device__ __forceinline__ void exp_pack(const uint32_t (&s)[32], float neg_m, u
     }
     join32(e);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) e[i] = (kPoly && (i & 7) == 7) ? poly_exp2(e[i]) : fast_exp2(e[i]);
+    for (int i = 0; i < 32; ++i)
+        e[i] = (kPoly && (i & 7) == 7) ? poly_exp2(e[i]) : (kOrdered ? fast_exp2_ordered(e[i]) : fast_exp2(e[i]));
     join32(e);
 #pragma unroll
     for (int i = 0; i < 32; i += 2) out[i >> 1] = pack_bf16x2(e[i], e[i + 1]);
 }
 
-template <bool kPoly>
+template <bool kPoly, bool kToken>
 __global__ void __launch_bounds__(kThreads, 1)
-attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_constant__ CUtensorMap tmap_vt,
-                     const AttnParams p) {
+attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                     const __grid_constant__ CUtensorMap tmap_vt, const AttnParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
     uint8_t* sQ = smem;                                  // [tile][16 KB]
-    uint8_t* sK = sQ + kQTiles * kQTileBytes;            // [stage][16 KB]
-    uint8_t* sV = sK + kKStages * kKBytes;               // [stage][atom][10 KB]
+    uint8_t* sK = sQ + kQTiles * kQTileBytes;            // [stage][8 KB]
+    uint8_t* sV = sK + kKStages * kKBytes;               // [stage][10 KB]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kVStages * kVBytes);
     uint64_t* q_full = bars;                             // 1
-    uint64_t* k_full = bars + 1;                         // [3]
-    uint64_t* v_full = bars + 4;                         // [3]
-    uint64_t* k_empty = bars + 7;                        // [3]
-    uint64_t* v_empty = bars + 10;                       // [3]
-    uint64_t* s_full = bars + 13;                        // [tile]  S_g(j) written (and every earlier MMA retired)
-    uint64_t* p_full = bars + 15;                        // [tile]  P_g(j) published by the 128 softmax threads
-    uint64_t* o_full = bars + 17;                        // [tile]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+    uint64_t* k_full = bars + 1;                         // [4]
+    uint64_t* v_full = bars + 5;                         // [4]
+    uint64_t* k_empty = bars + 9;                        // [4]
+    uint64_t* v_empty = bars + 13;                       // [4]
+    uint64_t* s_full = bars + 17;                        // [tile][buffer]  S_g(j) written
+    uint64_t* p_full = bars + 21;                        // [tile][buffer]  P_g(j) published by the 128 softmax threads
+    uint64_t* pv_done = bars + 25;                       // [tile]  O_g += P_g(n-2) V_(n-2) retired
+    uint64_t* o_full = bars + 27;                        // [tile]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 29);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -158,29 +175,33 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_c
     const int n_kv = (p.T + kBlockKV - 1) / kBlockKV;
 
     if (threadIdx.x == 0) {
-        tma_prefetch_desc(&tmap_qk);
+        tma_prefetch_desc(&tmap_q);
+        tma_prefetch_desc(&tmap_k);
         tma_prefetch_desc(&tmap_vt);
         mbar_init(q_full, 1);
         for (int s = 0; s < kKStages; ++s) {
             mbar_init(&k_full[s], 1);
-            mbar_init(&k_empty[s], 1);
+            mbar_init(&k_empty[s], kQTiles);
         }
         for (int s = 0; s < kVStages; ++s) {
             mbar_init(&v_full[s], 1);
-            mbar_init(&v_empty[s], 1);
+            mbar_init(&v_empty[s], kQTiles);
         }
         for (int g = 0; g < kQTiles; ++g) {
-            mbar_init(&s_full[g], 1);
-            mbar_init(&p_full[g], kSoftmaxThreads);
+            mbar_init(&s_full[2 * g], 1);
+            mbar_init(&s_full[2 * g + 1], 1);
+            mbar_init(&p_full[2 * g], kSoftmaxThreads);
+            mbar_init(&p_full[2 * g + 1], kSoftmaxThreads);
+            mbar_init(&pv_done[g], 1);
             mbar_init(&o_full[g], 1);
         }
         fence_mbar_init();
     }
-    // Constant tail of every V atom: B-operand rows 64..79 of the O MMA.  Row 64 is all ones, so column 64 of O
+    // Constant tail of every V stage: B-operand rows 64..79 of the O MMA.  Row 64 is all ones, so column 64 of O
     // accumulates the row sums of (the bf16-rounded) P on the tensor core; rows 65..79 pad N to a legal 80.
-    for (int i = threadIdx.x; i < kVStages * 2 * 512; i += kThreads) {
-        const int atom = i >> 9, w = i & 511;            // 512 words per 2 KB tail
-        reinterpret_cast<uint32_t*>(sV + atom * kVAtomBytes + kVAtomTma)[w] = (w < 32) ? 0x3F803F80u : 0u;
+    for (int i = threadIdx.x; i < kVStages * 512; i += kThreads) {
+        const int s = i >> 9, w = i & 511;               // 512 words per 2 KB tail
+        reinterpret_cast<uint32_t*>(sV + s * kVBytes + kVTmaBytes)[w] = (w < 32) ? 0x3F803F80u : 0u;
     }
     fence_proxy_async_smem();
     if (warp == kMmaWarp) tmem_alloc<kTmemCols>(tmem_slot);
@@ -194,63 +215,69 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_c
         if (lane == 0) {
             mbar_expect_tx(q_full, kQTiles * kQTileBytes);
             for (int g = 0; g < kQTiles; ++g)
-                tma_load_3d(sQ + g * kQTileBytes, &tmap_qk, q_full, head * kHeadDim, q0 + g * kBlockQ, b);
+                tma_load_3d(sQ + g * kQTileBytes, &tmap_q, q_full, head * kHeadDim, q0 + g * kBlockQ, b);
             for (int j = 0; j < n_kv; ++j) {
                 const int s = j % kKStages;
                 if (j >= kKStages) mbar_wait_relaxed(&k_empty[s], (j / kKStages - 1) & 1);
                 mbar_expect_tx(&k_full[s], kKBytes);
-                tma_load_3d(sK + s * kKBytes, &tmap_qk, &k_full[s], p.d_model + head * kHeadDim, j * kBlockKV, b);
+                tma_load_3d(sK + s * kKBytes, &tmap_k, &k_full[s], p.d_model + head * kHeadDim, j * kBlockKV, b);
             }
         } else if (lane == 1) {
             for (int j = 0; j < n_kv; ++j) {
                 const int s = j % kVStages;
                 if (j >= kVStages) mbar_wait_relaxed(&v_empty[s], (j / kVStages - 1) & 1);
-                mbar_expect_tx(&v_full[s], 2 * kVAtomTma);
+                mbar_expect_tx(&v_full[s], kVTmaBytes);
                 tma_load_3d(sV + s * kVBytes, &tmap_vt, &v_full[s], j * kBlockKV, head * kHeadDim, b);
-                tma_load_3d(sV + s * kVBytes + kVAtomBytes, &tmap_vt, &v_full[s], j * kBlockKV + 64, head * kHeadDim,
-                            b);
             }
         }
-    } else if (warp == kMmaWarp) {
-        if (lane == 0) {
-            // ---------------------------------------------------------------- MMA issuer
+    } else if (warp >= kMmaWarp) {
+        {
+            // ---------------------------------------------------------------- MMA issuer of query tile g
+            // tcgen05.mma is issued by one thread and these MMAs are small (~40 tensor-pipe cycles each), so the
+            // instruction count per MMA of the issuing warp bounds the kernel: one issuing warp per query tile, the
+            // whole warp runs this loop convergently (the MMA itself is predicated on elect.sync, see ptx.cuh), and
+            // the key loop is unrolled by the ring depth so that every descriptor is "base + compile-time constant".
+            static_assert(kKStages == 4 && kVStages == 4, "the issue loop is unrolled by the ring depth");
+            const int g = warp - kMmaWarp;
             constexpr uint32_t idesc_s = umma_idesc_bf16(kBlockQ, kBlockKV, false, false);
             constexpr uint32_t idesc_o = umma_idesc_bf16(kBlockQ, kOCols, false, false);
-            constexpr uint64_t desc_hi = umma_smem_desc_hi(16, 1024);
-            const uint32_t aQ = base;
-            const uint32_t aK = aQ + kQTiles * kQTileBytes;
-            const uint32_t aV = aK + kKStages * kKBytes;
-            auto issue_qk = [&](int g, int j) {          // S_g = Q_g K_j^T
-                const int s = j % kKStages;
-                if (g == 0) {
-                    mbar_wait(&k_full[s], (j / kKStages) & 1);
-                    tc_fence_after();
-                }
-#pragma unroll
-                for (int k = 0; k < kHeadDim / 16; ++k)
-                    umma_bf16_ss(tmem_base + g * kBlockKV, umma_smem_desc(aQ + g * kQTileBytes + k * 32, desc_hi),
-                                 umma_smem_desc(aK + s * kKBytes + k * 32, desc_hi), idesc_s, k != 0);
-                if (g == kQTiles - 1) umma_commit(&k_empty[s]);
-                umma_commit(&s_full[g]);
+            constexpr uint64_t desc_hi64 = umma_smem_desc_hi(16, 1024);
+            constexpr uint32_t desc_hi = (uint32_t)(desc_hi64 >> 32);
+            const uint32_t dQ = (uint32_t)(desc_hi64 & 0xFFFFFFFFu) | (((base + g * kQTileBytes) >> 4) & 0x3FFF);
+            const uint32_t dK = (uint32_t)(desc_hi64 & 0xFFFFFFFFu) | (((base + kQTiles * kQTileBytes) >> 4) & 0x3FFF);
+            const uint32_t dV = dK + ((kKStages * kKBytes) >> 4);
+            const uint32_t tS = tmem_base + g * 128;     // two score buffers of 64 columns
+            const uint32_t tO = tmem_base + kTmemO + g * kOCols;
+            auto issue_qk = [&](int s, int buf, uint32_t k_parity) {     // S_g = Q_g K^T into score buffer buf
+                mbar_wait(&k_full[s], k_parity);
+                tc_fence_after();
+                static_assert(kHeadDim == 64, "one x4 group per QK tile");
+                umma_bf16_ss_x4_elect(tS + buf * kBlockKV, dQ, dK + ((s * kKBytes) >> 4), desc_hi, idesc_s, 0);
+                umma_commit_elect(&k_empty[s]);
+                umma_commit_elect(&s_full[2 * g + buf]);
             };
             mbar_wait(q_full, 0);
-            for (int g = 0; g < kQTiles; ++g) issue_qk(g, 0);
-            for (int j = 0; j < n_kv; ++j) {
-                const int s = j % kVStages;
-                for (int g = 0; g < kQTiles; ++g) {
-                    // O_g (+)= P_g(j) [V_j | 1]: P published (so S_g(j) is fully consumed and O_g rescaled if needed)
-                    mbar_wait(&p_full[g], j & 1);
-                    if (g == 0) mbar_wait(&v_full[s], (j / kVStages) & 1);
-                    tc_fence_after();
+            issue_qk(0, 0, 0);
+            if (n_kv > 1) issue_qk(1, 1, 0);
+            for (int j0 = 0; j0 < n_kv; j0 += 4) {
+                const uint32_t ring_parity = (j0 >> 2) & 1;
 #pragma unroll
-                    for (int k = 0; k < kBlockKV / 16; ++k)
-                        umma_bf16_ts(tmem_base + kTmemO + g * kOCols, tmem_base + g * kBlockKV + k * 8,
-                                     umma_smem_desc(aV + s * kVBytes + (k >> 2) * kVAtomBytes + (k & 3) * 32, desc_hi),
-                                     idesc_o, (j > 0) || (k != 0));
-                    if (g == kQTiles - 1) umma_commit(&v_empty[s]);
-                    // S_g(j+1) overwrites P_g(j): the tensor pipe executes in issue order, so PV_g(j) has read it
-                    if (j + 1 < n_kv) issue_qk(g, j + 1);
-                    else umma_commit(&o_full[g]);
+                for (int u = 0; u < 4; ++u) {
+                    const int j = j0 + u;
+                    if (j >= n_kv) break;
+                    // O_g (+)= P_g(j) [V_j | 1]: P published (so S_g(j) is fully read and O_g rescaled if needed).
+                    // One barrier per score buffer: the softmax may run two tiles ahead of this thread, which a
+                    // single parity bit could not tell apart.
+                    mbar_wait(&p_full[2 * g + (u & 1)], (j >> 1) & 1);
+                    mbar_wait(&v_full[u], ring_parity);
+                    tc_fence_after();
+                    umma_bf16_ts_x4_elect(tO, tS + (u & 1) * kBlockKV, dV + ((u * kVBytes) >> 4), desc_hi, idesc_o,
+                                          j > 0);
+                    umma_commit_elect(&v_empty[u]);
+                    if (j == n_kv - 2) umma_commit_elect(&pv_done[g]);
+                    if (j == n_kv - 1) umma_commit_elect(&o_full[g]);
+                    // S_g(j+2) overwrites P_g(j): the tensor pipe executes in issue order, so PV_g(j) has read it
+                    if (j + 2 < n_kv) issue_qk((u + 2) & 3, u & 1, u < 2 ? ring_parity : ring_parity ^ 1);
                 }
             }
         }
@@ -260,46 +287,40 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_c
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;                 // query row inside the tile == TMEM lane
         const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-        const uint32_t tmem_s = tmem_base + lane_addr + g * kBlockKV;          // S_g, and P_g on top of it
+        const uint32_t tmem_s = tmem_base + lane_addr + g * 128;               // S_g buffers, P_g on top of them
         const uint32_t tmem_o = tmem_base + lane_addr + kTmemO + g * kOCols;
+        const int bar_mine = 1 + quarter * 2 + g;            // token: "the MUFU of this scheduler is yours"
+        const int bar_other = 1 + quarter * 2 + (g ^ 1);
         float m_ref = 0.0f;
+        if (kToken && g == 1) named_bar_arrive(bar_other, 64);                 // tile A goes first
 
 #pragma unroll 1
         for (int j = 0; j < n_kv; ++j) {
-            // S_g(j) ready; the commit also covers O_g += P_g(j-1) V_(j-1), so O_g may be rescaled below
-            mbar_wait(&s_full[g], j & 1);
+            const int buf = j & 1;
+            mbar_wait(&s_full[2 * g + buf], (j >> 1) & 1);
             tc_fence_after();
+            uint32_t s0[32], s1[32];
+            tmem_ld_32x32b_x32(tmem_s + buf * kBlockKV, s0);
+            tmem_ld_32x32b_x32(tmem_s + buf * kBlockKV + 32, s1);
+            tmem_ld_wait_on(s0);
+            tmem_ld_wait_on(s1);
             const int kv_valid = p.T - j * kBlockKV;
-            const bool tail = kv_valid < kBlockKV;
-            // ---- pass 1: row maximum of the 128 scores
-            float m_tile;
-            {
-                uint32_t s0[32], s1[32];
-                tmem_ld_32x32b_x32(tmem_s, s0);
-                tmem_ld_32x32b_x32(tmem_s + 32, s1);
-                tmem_ld_wait_on(s0);
-                tmem_ld_wait_on(s1);
-                if (tail) {
-                    mask32(s0, 0, kv_valid);
-                    mask32(s1, 32, kv_valid);
-                }
-                m_tile = fmaxf(max32(s0), max32(s1));
-                tmem_ld_32x32b_x32(tmem_s + 64, s0);
-                tmem_ld_32x32b_x32(tmem_s + 96, s1);
-                tmem_ld_wait_on(s0);
-                tmem_ld_wait_on(s1);
-                if (tail) {
-                    mask32(s0, 64, kv_valid);
-                    mask32(s1, 96, kv_valid);
-                }
-                m_tile = fmaxf(m_tile, fmaxf(max32(s0), max32(s1)));
+            if (kv_valid < kBlockKV) {                       // only the last tile: keys >= T do not exist
+                mask32(s0, 0, kv_valid);
+                mask32(s1, 32, kv_valid);
             }
+            const float m_tile = fmaxf(max32(s0), max32(s1));
             if (j == 0) {
                 m_ref = m_tile;
             } else {
                 // lazy rescale: keep exponentiating against a stale maximum until it is off by more than 2^8
                 const bool need = (m_tile - m_ref) * kScale > kRescaleThreshold;
                 if (__any_sync(0xffffffffu, need)) {
+                    // O_g += P_g(j-1) V_(j-1) must have retired: S_g(j+1) was issued after it, so its commit
+                    // covers it; the last tile has no successor and uses a commit of its own
+                    if (j + 1 < n_kv) mbar_wait(&s_full[2 * g + (buf ^ 1)], ((j + 1) >> 1) & 1);
+                    else mbar_wait(&pv_done[g], 0);
+                    tc_fence_after();
                     const float f = need ? fast_exp2((m_ref - m_tile) * kScale) : 1.0f;
                     if (need) m_ref = m_tile;
                     {
@@ -321,24 +342,17 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_c
                     tmem_st_32x32b_x16(tmem_o + 64, o16);
                 }
             }
-            // ---- pass 2: exponentials, P written over the consumed part of S
             const float neg_m = -m_ref * kScale;
-            uint32_t sa[32], sb[32];
-            tmem_ld_32x32b_x32(tmem_s, sa);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                uint32_t (&cur)[32] = (c & 1) ? sb : sa;
-                uint32_t (&nxt)[32] = (c & 1) ? sa : sb;
-                tmem_ld_wait_on(cur);
-                if (c < 3) tmem_ld_32x32b_x32(tmem_s + (c + 1) * 32, nxt);
-                if (tail) mask32(cur, c * 32, kv_valid);
-                uint32_t pk[16];
-                exp_pack<kPoly>(cur, neg_m, pk);
-                tmem_st_32x32b_x16(tmem_s + c * 16, pk);
-            }
+            uint32_t pk0[16], pk1[16];
+            if (kToken) named_bar_sync(bar_mine, 64);
+            exp_pack<kPoly, kToken>(s0, neg_m, pk0);
+            exp_pack<kPoly, kToken>(s1, neg_m, pk1);
+            if (kToken && !(g == 1 && j == n_kv - 1)) named_bar_arrive(bar_other, 64);
+            tmem_st_32x32b_x16(tmem_s + buf * kBlockKV, pk0);
+            tmem_st_32x32b_x16(tmem_s + buf * kBlockKV + 16, pk1);
             tmem_st_wait();
             tc_fence_before();              // our TMEM reads / writes are complete and ordered before the arrive
-            mbar_arrive(&p_full[g]);
+            mbar_arrive(&p_full[2 * g + buf]);
         }
 
         mbar_wait(&o_full[g], 0);
@@ -379,21 +393,27 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_c
     }
 }
 
-bool use_poly_exp() {
-    static const bool on = [] {
+int attn_variant() {                                     // bit 0: polynomial exp2 on every 8th element; bit 1: no token
+    static const int v = [] {
         const char* e = getenv("ARIES_ATTN_POLY");
-        return e ? (e[0] != '0') : false;
+        const char* t = getenv("ARIES_ATTN_TOKEN");
+        return ((e && e[0] != '0') ? 1 : 0) | ((t && t[0] != '0') ? 0 : 2);
     }();
-    return on;
+    return v;
 }
 
 }  // namespace
 
 cudaError_t attention_init_device() {
-    cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         kSmemBytes);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(attention_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(attention_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  kSmemBytes)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(attention_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  kSmemBytes)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(attention_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  kSmemBytes)) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(attention_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                kSmemBytes);
 }
 
 cudaError_t attention_make_maps(const void* qk, const void* vt, int batch, int T, int d_model, int n_heads, int t_pad,
@@ -402,24 +422,28 @@ cudaError_t attention_make_maps(const void* qk, const void* vt, int batch, int T
                                         (unsigned long long)batch};
     const unsigned long long strides[3] = {2, (unsigned long long)(2 * d_model) * 2,
                                            (unsigned long long)T * (2 * d_model) * 2};
-    const unsigned box_qk[3] = {64, 128, 1};             // one query tile == one key tile: 128 rows x 64 columns
-    cudaError_t e = make_tmap_bf16(&maps->qk, qk, 3, dims, strides, box_qk);
+    const unsigned box_q[3] = {64, (unsigned)kBlockQ, 1};
+    const unsigned box_k[3] = {64, (unsigned)kBlockKV, 1};
+    cudaError_t e = make_tmap_bf16(&maps->q, qk, 3, dims, strides, box_q);
     if (e != cudaSuccess) return e;
+    if ((e = make_tmap_bf16(&maps->k, qk, 3, dims, strides, box_k)) != cudaSuccess) return e;
     const unsigned long long vdims[3] = {(unsigned long long)T, (unsigned long long)(n_heads * 64),
                                          (unsigned long long)batch};
     const unsigned long long vstrides[3] = {2, (unsigned long long)t_pad * 2,
                                             (unsigned long long)(n_heads * 64) * t_pad * 2};
-    const unsigned box_v[3] = {64, 64, 1};               // one swizzle atom: 64 keys x 64 value rows
+    const unsigned box_v[3] = {(unsigned)kBlockKV, 64, 1};
     return make_tmap_bf16(&maps->vt, vt, 3, vdims, vstrides, box_v);
 }
 
 cudaError_t attention_launch(const AttnMaps& maps, const AttnParams& p, cudaStream_t stream) {
     if (p.d_model != p.n_heads * kHeadDim || p.T <= 0 || p.batch <= 0) return cudaErrorInvalidValue;
     dim3 grid((p.T + kQTiles * kBlockQ - 1) / (kQTiles * kBlockQ), p.n_heads, p.batch);
-    if (use_poly_exp())
-        attention_fwd_kernel<true><<<grid, kThreads, kSmemBytes, stream>>>(maps.qk, maps.vt, p);
-    else
-        attention_fwd_kernel<false><<<grid, kThreads, kSmemBytes, stream>>>(maps.qk, maps.vt, p);
+    switch (attn_variant()) {
+        case 0: attention_fwd_kernel<false, true><<<grid, kThreads, kSmemBytes, stream>>>(maps.q, maps.k, maps.vt, p); break;
+        case 1: attention_fwd_kernel<true, true><<<grid, kThreads, kSmemBytes, stream>>>(maps.q, maps.k, maps.vt, p); break;
+        case 2: attention_fwd_kernel<false, false><<<grid, kThreads, kSmemBytes, stream>>>(maps.q, maps.k, maps.vt, p); break;
+        default: attention_fwd_kernel<true, false><<<grid, kThreads, kSmemBytes, stream>>>(maps.q, maps.k, maps.vt, p); break;
+    }
     return cudaGetLastError();
 }
 

@@ -47,14 +47,22 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Every wait is bounded: a protocol bug must surface as a launch failure ("unspecified launch failure" through the C
+// ABI), never as a hung GPU.  A legitimate wait lasts microseconds; the bound is on the order of seconds.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 26)) __trap();
     }
 }
 // For roles that are not latency critical (TMA producer): back off between probes so the spin does not eat issue
 // slots of the compute warps sharing the scheduler.
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) __nanosleep(64);
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(64);
+        if (++spins > (1u << 24)) __trap();
+    }
 }
 
 // ---------------------------------------------------------------- proxies / fences
@@ -138,6 +146,100 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
         "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// Variants taking the shared-memory descriptors as (low word, high word): the high word is a per-kernel constant and
+// the low word advances by (byte offset >> 4), so the issuing thread spends one integer add per operand per MMA.
+__device__ __forceinline__ void umma_bf16_ss_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
+                                                  uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(tmem_d),
+        "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ts_lohi(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t desc_hi,
+                                                  uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}" ::"r"(tmem_d),
+        "r"(tmem_a), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// Warp-convergent issue: EVERY lane of the issuing warp executes these (with identical, warp-uniform operands) and the
+// instruction itself is predicated on elect.sync.  Under an ordinary divergent `if (lane == 0)` ptxas wraps each
+// tcgen05 instruction in a loop over the active lanes (~13 instructions per MMA); attention's MMAs are small enough
+// for that to bound the kernel.
+__device__ __forceinline__ void umma_bf16_ss_elect(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
+                                                   uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(tmem_d),
+        "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ts_elect(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t desc_hi,
+                                                   uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t.reg .b64 db;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}" ::"r"(tmem_d),
+        "r"(tmem_a), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
+    asm volatile(
+        "{\n\t.reg .pred e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
+        : "memory");
+}
+// Four K = 16 steps of one 64-deep contraction in a single statement (one elect.sync for all of them): the operands
+// advance by 32 bytes (descriptor low word += 2) / 8 TMEM columns per step.  Steps 1..3 always accumulate.
+__device__ __forceinline__ void umma_bf16_ss_x4_elect(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
+                                                      uint32_t idesc, uint32_t accumulate_first) {
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t.reg .b32 a, b;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t"
+        "add.u32 a, %1, 2;\n\tadd.u32 b, %2, 2;\n\tmov.b64 da, {a, %3};\n\tmov.b64 db, {b, %3};\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, 1;\n\t"
+        "add.u32 a, %1, 4;\n\tadd.u32 b, %2, 4;\n\tmov.b64 da, {a, %3};\n\tmov.b64 db, {b, %3};\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, 1;\n\t"
+        "add.u32 a, %1, 6;\n\tadd.u32 b, %2, 6;\n\tmov.b64 da, {a, %3};\n\tmov.b64 db, {b, %3};\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, 1;\n\t}" ::"r"(tmem_d),
+        "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate_first)
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ts_x4_elect(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo,
+                                                      uint32_t desc_hi, uint32_t idesc, uint32_t accumulate_first) {
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t.reg .b64 db;\n\t.reg .b32 a, b;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t"
+        "add.u32 a, %1, 8;\n\tadd.u32 b, %2, 2;\n\tmov.b64 db, {b, %3};\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a], db, %4, 1;\n\t"
+        "add.u32 a, %1, 16;\n\tadd.u32 b, %2, 4;\n\tmov.b64 db, {b, %3};\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a], db, %4, 1;\n\t"
+        "add.u32 a, %1, 24;\n\tadd.u32 b, %2, 6;\n\tmov.b64 db, {b, %3};\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a], db, %4, 1;\n\t}" ::"r"(tmem_d),
+        "r"(tmem_a), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate_first)
         : "memory");
 }
 // Arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed.
