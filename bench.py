@@ -131,8 +131,10 @@ def run_reference(args, rank: int, world: int) -> int:
         return 0
     import torch
     kind = reference_backend()
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm is rank 0 alone and owns the host
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
     # (a real faster-whisper leg would need CT2-format weights; with random-init weights only the port can run)
-    sample_windows = 1
+    sample_windows = 2
     for _ in range(args.warmup):
         cpu_reference_step(sample_windows, args.model)
     t0 = time.perf_counter()
@@ -141,13 +143,13 @@ def run_reference(args, rank: int, world: int) -> int:
     dt = time.perf_counter() - t0
     value = args.steps * sample_windows * WINDOW_SECONDS / dt
     cores = torch.get_num_threads()
-    sample = (f"{sample_windows} synthetic 30-s window per step (numpy log-mel + torch fp32 encoder, {args.model} shape, "
+    sample = (f"{sample_windows} synthetic 30-s windows per step (numpy log-mel + torch fp32 encoder, {args.model} shape, "
               f"random-init weights); faster-whisper/ctranslate2 importable: {kind == 'reference'}")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.model} log-mel+encoder, {args.windows} x 30-s windows per GPU per step "
-                                   f"(reference arm: bounded sample of {sample_windows} window per step on the host CPU)",
+                                   f"(reference arm: bounded sample of {sample_windows} windows per step on the host CPU)",
                        "windows_per_gpu": args.windows, "window_seconds": 30, "sample_rate": 16000},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -302,6 +304,7 @@ def main() -> int:
     cpu_baseline = None
     if not args.no_cpu_baseline:
         import torch as _t
+        _t.set_num_threads(max(1, os.cpu_count() or 1))              # torchrun pins OMP_NUM_THREADS=1 per rank
         n_sample = 2 if args.model == "large-v3" else 4
         cpu_reference_step(1, args.model)                             # warm the weights / thread pool
         r = cpu_reference_step(n_sample, args.model)

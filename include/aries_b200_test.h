@@ -28,6 +28,9 @@ ARIES_API int aries_test_layernorm(aries_ctx* ctx, const float* x, const float* 
 ARIES_API int aries_test_attention(aries_ctx* ctx, const void* qk, const void* vt, int batch, int T, int n_heads, int t_pad,
                          void* out, void* stream);
 
+/* Timeline of the ARIES_ATTN_TRACE=1 attention variant: [16 CTAs][11 warps][160 clock64 stamps] (0 = unused). */
+ARIES_API int aries_test_attention_trace(aries_ctx* ctx, unsigned long long* host, size_t count);
+
 #ifdef __cplusplus
 }
 #endif

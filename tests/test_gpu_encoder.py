@@ -103,3 +103,48 @@ def test_scheduler_on_one_gpu_matches_direct_call():
     out = torch.empty((5, 1500, shape.d_model), dtype=torch.bfloat16).pin_memory()
     res = ChunkScheduler([gpu_worker(model, micro_batch=2)]).run(torch.from_numpy(pcm).pin_memory(), out)
     assert all(r.success for r in res) and torch.equal(out, direct)
+
+
+def test_medium_alt_shape_vs_oracle():
+    """BASELINE config 5 (alt-shape path): Whisper medium -- 80 mel bins, d = 1024, 16 heads, 24 layers, K tiles of
+    1024 / 4096 -- one window against the fp32 CPU oracle, through the fused PCM entry point."""
+    model, shape, w = model_for("medium")
+    pcm = osynth.batch_signals(2, 20)
+    feats = np.stack([omel.log_mel_window(x, shape.n_mels) for x in pcm])
+    out = model.encode_audio(torch.from_numpy(pcm).cuda())
+    assert out.shape == (2, 1500, 1024)
+    ref = oenc.encoder_forward(feats[:1], w, shape)
+    cmp = oenc.compare(out[:1].cpu(), ref)
+    assert cmp["cosine"] >= COS and cmp["min_row_cosine"] >= 0.995 and cmp["max_abs"] <= 0.2, cmp
+    two_step = model.encode(model.feature_extractor(torch.from_numpy(pcm).cuda(), frames_out=3000))
+    assert torch.equal(out, two_step)
+
+
+def test_one_hour_stream_sharded_like_config4():
+    """BASELINE config 4 at full size: a 1-hour synthetic stream (57.6 M samples, seed 7) cut into 120 windows and run
+    through the chunk scheduler.  The CPU oracle cannot cover 120 large-v3 windows in seconds, so the full-size run is
+    checked through size-independent properties: the result of a window does not depend on which block / micro-batch
+    it was sharded into (2-, 4- and 8-way block partitions of the same 120 windows give identical bytes, which is what
+    lets N GPUs reproduce the 1-GPU answer), every state is finite and LayerNorm-scaled, and one window picked from
+    the middle of the stream matches the fp32 oracle."""
+    from whisper_aries_b200.scheduler import ChunkScheduler, gpu_worker, partition_windows, split_into_windows
+    model, shape, w = model_for("large-v3")
+    stream = np.concatenate([osynth.window_signal(7000 + i) for i in range(120)])
+    assert stream.shape[0] == 57_600_000
+    windows = torch.from_numpy(split_into_windows(stream)).pin_memory()
+    assert windows.shape == (120, 480000)
+    out = torch.empty((120, 1500, shape.d_model), dtype=torch.bfloat16).pin_memory()
+    res = ChunkScheduler([gpu_worker(model, micro_batch=16)]).run(windows, out)
+    assert all(r.success for r in res)
+    assert torch.isfinite(out.float()).all()
+    rms = out.float().pow(2).mean(dim=-1).sqrt()
+    assert 0.5 < float(rms.mean()) < 2.0
+    for parts in (2, 4, 8):                                   # 60 / 30 / 15 windows per GPU, as in config 4
+        for (a, b) in partition_windows(120, parts)[::max(1, parts // 2)]:
+            shard = torch.empty((b - a, 1500, shape.d_model), dtype=torch.bfloat16).pin_memory()
+            r2 = ChunkScheduler([gpu_worker(model, micro_batch=15)]).run(windows[a:b], shard)
+            assert all(r.success for r in r2) and torch.equal(shard, out[a:b]), (parts, a, b)
+    k = 77
+    feats = omel.log_mel_window(windows[k].numpy(), shape.n_mels)[None]
+    cmp = oenc.compare(out[k:k + 1], oenc.encoder_forward(feats, w, shape))
+    assert cmp["cosine"] >= COS and cmp["max_abs"] <= 0.2, cmp

@@ -57,6 +57,7 @@ PROTOTYPES = {
                                 c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "aries_test_layernorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "aries_test_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "aries_test_attention_trace": (c_int, [c_void_p, c_void_p, c_size_t]),
 }
 
 KERNEL_CLASSES = ["logmel_tiles", "logmel_clamp", "mel_transpose", "conv1_gemm", "conv2_gemm", "layernorm", "qkv_gemm",

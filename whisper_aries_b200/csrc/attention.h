@@ -26,5 +26,7 @@ struct AttnMaps {
 cudaError_t attention_make_maps(const void* qk, const void* vt, int batch, int T, int d_model, int n_heads, int t_pad,
                                 AttnMaps* maps);
 cudaError_t attention_launch(const AttnMaps& maps, const AttnParams& p, cudaStream_t stream);
+// Test-only: clock64 timeline written by the ARIES_ATTN_TRACE=1 variant ([16 CTAs][11 warps][160 stamps]).
+cudaError_t attention_read_trace(unsigned long long* host, size_t count);
 
 }  // namespace aries

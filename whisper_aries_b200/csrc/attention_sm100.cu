@@ -10,14 +10,16 @@
 //              shared memory.  O accumulates in TMEM and is rescaled (tcgen05.ld / st) only when a row's maximum
 //              grew by more than 2^8 since the last rescale.
 //   warp 8     lane 0: TMA for both Q tiles and the K ring (4 x 8 KB); lane 1: TMA for the V^T ring (4 x 8 KB)
-//   warp 9     tcgen05.mma, one thread:  S_g = Q_g K_j^T (SS, M128 N64 K64), issued TWO key tiles ahead of the
+//   warps 9-10 tcgen05.mma, one elected thread per query tile:  S_g = Q_g K_j^T (SS, M128 N64 K64), issued TWO key tiles ahead of the
 //              softmax, and O_g += P_g [V_j | 1] (TS: the A operand is P_g in tensor memory; M128 N80 K64).  Row 64
 //              of the B operand is all ones, so column 64 of O accumulates the row sums of the bf16-rounded P on
 //              the tensor core.
 // Because S is double-buffered the softmax warps never wait for the tensor pipe in steady state.  Warp i of tile A
-// and warp i of tile B share one scheduler and its MUFU -- the bound of this kernel at head_dim 64 -- so they pass a
-// token (two named barriers per pair): one runs its 64 exponentials while the other does everything else (TMEM
-// loads, maxima, packing, stores, barrier traffic), instead of both stalling in the same phase.
+// and warp i of tile B share one scheduler and its MUFU -- the bound of this kernel at head_dim 64.  Measured with the
+// clock64 timeline (tests/attn_trace.py): the two run in lockstep, ~950 cycles in which their 128 MUFU instructions
+// saturate the unit (7.4 cycles each) and ~630 cycles of barrier / TMEM round trips (each ~170 cycles through the
+// scheduler's in-order MIO queue) with the MUFU idle.  Forcing them into anti-phase with a token (named barriers or
+// mbarriers, early hand-off) was tried and is slower: ONE warp cannot keep the MUFU busy (13 cycles per instruction).
 // Q and K are read straight out of the QKV GEMM's row-major [B*T, 2d] output through a 3-D tensor map; V arrives
 // pre-transposed ([B, h, 64, t_pad]) from that GEMM's epilogue so that both MMAs use K-major operands.
 // Keys >= T are zero-filled by TMA and masked to -inf here; query rows >= T are computed and dropped.
@@ -52,26 +54,23 @@ constexpr uint32_t kTmemO = 256;
 constexpr float kScale = 0.18033688011112042f;           // log2(e) / sqrt(64)
 constexpr float kRescaleThreshold = 8.0f;                // lazy rescale: only when the row max grew by > 2^8
 
-// Named barriers (ids 1..8): token for the MUFU phase of the softmax-warp pair that shares a scheduler.
-__device__ __forceinline__ void named_bar_sync(int id, int threads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
-__device__ __forceinline__ void named_bar_arrive(int id, int threads) {
-    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
+// Test-only timeline (variant bit 2, ARIES_ATTN_TRACE=1): clock64 stamps of lane 0 of every warp of a few CTAs.
+constexpr int kTraceCtas = 16, kTraceWarps = 11, kTraceEvents = 160;
+__device__ unsigned long long g_attn_trace[kTraceCtas * kTraceWarps * kTraceEvents];
+
+struct Tracer {
+    unsigned long long* p;
+    int n;
+    __device__ __forceinline__ void stamp() {
+        if (p != nullptr && n < kTraceEvents) p[n++] = clock64();
+    }
+};
 
 __device__ __forceinline__ float fast_exp2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-// volatile twin: stays between the named-barrier token operations that bracket the MUFU phase
-__device__ __forceinline__ float fast_exp2_ordered(float x) {
-    float y;
-    asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-
 // 2^x on the FMA / ALU pipes (no MUFU): round-to-nearest split x = n + f, |f| <= 0.5, degree-4 polynomial for 2^f
 // (relative error < 5e-5, far below the bf16 rounding of P), exponent patched in with an integer add.
 __device__ __forceinline__ float poly_exp2(float x) {
@@ -125,7 +124,7 @@ __device__ __forceinline__ void join32(float (&e)[32]) {
 // p = exp2(s * c - m * c) for 32 scores -> 16 packed bf16x2 (low half = the lower key index).  The scale / offset is
 // a packed f32x2 FMA (two scores per instruction); with kPoly every 8th exponential runs on the FMA pipe instead of
 // the MUFU.
-template <bool kPoly, bool kOrdered>
+template <bool kPoly>
 __device__ __forceinline__ void exp_pack(const uint32_t (&s)[32], float neg_m, uint32_t (&out)[16]) {
     const float2 c2 = make_float2(kScale, kScale);
     const float2 m2 = make_float2(neg_m, neg_m);
@@ -138,14 +137,13 @@ __device__ __forceinline__ void exp_pack(const uint32_t (&s)[32], float neg_m, u
     }
     join32(e);
 #pragma unroll
-    for (int i = 0; i < 32; ++i)
-        e[i] = (kPoly && (i & 7) == 7) ? poly_exp2(e[i]) : (kOrdered ? fast_exp2_ordered(e[i]) : fast_exp2(e[i]));
+    for (int i = 0; i < 32; ++i) e[i] = (kPoly && (i & 7) == 7) ? poly_exp2(e[i]) : fast_exp2(e[i]);
     join32(e);
 #pragma unroll
     for (int i = 0; i < 32; i += 2) out[i >> 1] = pack_bf16x2(e[i], e[i + 1]);
 }
 
-template <bool kPoly, bool kToken>
+template <bool kPoly, bool kTrace>
 __global__ void __launch_bounds__(kThreads, 1)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                      const __grid_constant__ CUtensorMap tmap_vt, const AttnParams p) {
@@ -173,6 +171,13 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     const int head = blockIdx.y;
     const int b = blockIdx.z;
     const int n_kv = (p.T + kBlockKV - 1) / kBlockKV;
+    Tracer tr{nullptr, 0};
+    if (kTrace) {
+        const int cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+        if (lane == 0 && (cta % 61) == 5 && cta / 61 < kTraceCtas)
+            tr.p = g_attn_trace + ((cta / 61) * kTraceWarps + warp) * kTraceEvents;
+        if (kTrace) tr.stamp();
+    }
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmap_q);
@@ -268,7 +273,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                     // O_g (+)= P_g(j) [V_j | 1]: P published (so S_g(j) is fully read and O_g rescaled if needed).
                     // One barrier per score buffer: the softmax may run two tiles ahead of this thread, which a
                     // single parity bit could not tell apart.
+                    if (kTrace) tr.stamp();
                     mbar_wait(&p_full[2 * g + (u & 1)], (j >> 1) & 1);
+                    if (kTrace) tr.stamp();
                     mbar_wait(&v_full[u], ring_parity);
                     tc_fence_after();
                     umma_bf16_ts_x4_elect(tO, tS + (u & 1) * kBlockKV, dV + ((u * kVBytes) >> 4), desc_hi, idesc_o,
@@ -277,7 +284,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                     if (j == n_kv - 2) umma_commit_elect(&pv_done[g]);
                     if (j == n_kv - 1) umma_commit_elect(&o_full[g]);
                     // S_g(j+2) overwrites P_g(j): the tensor pipe executes in issue order, so PV_g(j) has read it
+                    if (kTrace) tr.stamp();
                     if (j + 2 < n_kv) issue_qk((u + 2) & 3, u & 1, u < 2 ? ring_parity : ring_parity ^ 1);
+                    if (kTrace) tr.stamp();
                 }
             }
         }
@@ -289,16 +298,15 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
         const uint32_t tmem_s = tmem_base + lane_addr + g * 128;               // S_g buffers, P_g on top of them
         const uint32_t tmem_o = tmem_base + lane_addr + kTmemO + g * kOCols;
-        const int bar_mine = 1 + quarter * 2 + g;            // token: "the MUFU of this scheduler is yours"
-        const int bar_other = 1 + quarter * 2 + (g ^ 1);
         float m_ref = 0.0f;
-        if (kToken && g == 1) named_bar_arrive(bar_other, 64);                 // tile A goes first
 
 #pragma unroll 1
         for (int j = 0; j < n_kv; ++j) {
             const int buf = j & 1;
+            if (kTrace) tr.stamp();
             mbar_wait(&s_full[2 * g + buf], (j >> 1) & 1);
             tc_fence_after();
+            if (kTrace) tr.stamp();
             uint32_t s0[32], s1[32];
             tmem_ld_32x32b_x32(tmem_s + buf * kBlockKV, s0);
             tmem_ld_32x32b_x32(tmem_s + buf * kBlockKV + 32, s1);
@@ -344,10 +352,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             }
             const float neg_m = -m_ref * kScale;
             uint32_t pk0[16], pk1[16];
-            if (kToken) named_bar_sync(bar_mine, 64);
-            exp_pack<kPoly, kToken>(s0, neg_m, pk0);
-            exp_pack<kPoly, kToken>(s1, neg_m, pk1);
-            if (kToken && !(g == 1 && j == n_kv - 1)) named_bar_arrive(bar_other, 64);
+            if (kTrace) tr.stamp();
+            exp_pack<kPoly>(s0, neg_m, pk0);
+            exp_pack<kPoly>(s1, neg_m, pk1);
+            if (kTrace) tr.stamp();
             tmem_st_32x32b_x16(tmem_s + buf * kBlockKV, pk0);
             tmem_st_32x32b_x16(tmem_s + buf * kBlockKV + 16, pk1);
             tmem_st_wait();
@@ -355,8 +363,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             mbar_arrive(&p_full[2 * g + buf]);
         }
 
+        if (kTrace) tr.stamp();
         mbar_wait(&o_full[g], 0);
         tc_fence_after();
+        if (kTrace) tr.stamp();
         const int t = q0 + g * kBlockQ + row;
         uint32_t osum[16];
         tmem_ld_32x32b_x16(tmem_o + 64, osum);                   // column 64 = row sum of P
@@ -385,35 +395,44 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         tc_fence_before();
     }
 
+    if (kTrace) tr.stamp();
     tc_fence_before();
     __syncthreads();
     if (warp == kMmaWarp) {
         tc_fence_after();
         tmem_dealloc<kTmemCols>(tmem_base);
     }
+    if (kTrace) tr.stamp();
 }
 
-int attn_variant() {                                     // bit 0: polynomial exp2 on every 8th element; bit 1: no token
+int attn_variant() {               // bit 0: polynomial exp2 on every 8th element; bit 2: trace
     static const int v = [] {
         const char* e = getenv("ARIES_ATTN_POLY");
-        const char* t = getenv("ARIES_ATTN_TOKEN");
-        return ((e && e[0] != '0') ? 1 : 0) | ((t && t[0] != '0') ? 0 : 2);
+        const char* r = getenv("ARIES_ATTN_TRACE");
+        if (r && r[0] != '0') return 4;
+        return (e && e[0] != '0') ? 1 : 0;
     }();
     return v;
+}
+
+template <bool kPoly, bool kTrace>
+cudaError_t set_smem() {
+    return cudaFuncSetAttribute(attention_fwd_kernel<kPoly, kTrace>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                kSmemBytes);
 }
 
 }  // namespace
 
 cudaError_t attention_init_device() {
     cudaError_t e;
-    if ((e = cudaFuncSetAttribute(attention_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  kSmemBytes)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(attention_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  kSmemBytes)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(attention_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  kSmemBytes)) != cudaSuccess) return e;
-    return cudaFuncSetAttribute(attention_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                kSmemBytes);
+    if ((e = set_smem<false, false>()) != cudaSuccess) return e;
+    if ((e = set_smem<true, false>()) != cudaSuccess) return e;
+    return set_smem<false, true>();
+}
+
+cudaError_t attention_read_trace(unsigned long long* host, size_t count) {
+    if (count > sizeof(g_attn_trace) / sizeof(unsigned long long)) count = sizeof(g_attn_trace) / sizeof(unsigned long long);
+    return cudaMemcpyFromSymbol(host, g_attn_trace, count * sizeof(unsigned long long));
 }
 
 cudaError_t attention_make_maps(const void* qk, const void* vt, int batch, int T, int d_model, int n_heads, int t_pad,
@@ -439,10 +458,9 @@ cudaError_t attention_launch(const AttnMaps& maps, const AttnParams& p, cudaStre
     if (p.d_model != p.n_heads * kHeadDim || p.T <= 0 || p.batch <= 0) return cudaErrorInvalidValue;
     dim3 grid((p.T + kQTiles * kBlockQ - 1) / (kQTiles * kBlockQ), p.n_heads, p.batch);
     switch (attn_variant()) {
-        case 0: attention_fwd_kernel<false, true><<<grid, kThreads, kSmemBytes, stream>>>(maps.q, maps.k, maps.vt, p); break;
-        case 1: attention_fwd_kernel<true, true><<<grid, kThreads, kSmemBytes, stream>>>(maps.q, maps.k, maps.vt, p); break;
-        case 2: attention_fwd_kernel<false, false><<<grid, kThreads, kSmemBytes, stream>>>(maps.q, maps.k, maps.vt, p); break;
-        default: attention_fwd_kernel<true, false><<<grid, kThreads, kSmemBytes, stream>>>(maps.q, maps.k, maps.vt, p); break;
+        case 1: attention_fwd_kernel<true, false><<<grid, kThreads, kSmemBytes, stream>>>(maps.q, maps.k, maps.vt, p); break;
+        case 4: attention_fwd_kernel<false, true><<<grid, kThreads, kSmemBytes, stream>>>(maps.q, maps.k, maps.vt, p); break;
+        default: attention_fwd_kernel<false, false><<<grid, kThreads, kSmemBytes, stream>>>(maps.q, maps.k, maps.vt, p); break;
     }
     return cudaGetLastError();
 }

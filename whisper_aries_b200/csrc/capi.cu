@@ -416,4 +416,13 @@ int aries_test_attention(aries_ctx* ctx, const void* qk, const void* vt, int bat
     return ARIES_OK;
 }
 
+int aries_test_attention_trace(aries_ctx* ctx, unsigned long long* host, size_t count) {
+    int rc = use(ctx);
+    if (rc) return rc;
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = aries::attention_read_trace(host, count);
+    if (e != cudaSuccess) return fail_cuda("attention_read_trace", e);
+    return ARIES_OK;
+}
+
 }  // extern "C"
