@@ -165,7 +165,7 @@ def main() -> int:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--windows", type=int, default=64, help="30-s windows per GPU per step")
-    ap.add_argument("--micro-batch", type=int, default=16, help="windows per H2D/compute/D2H micro-batch (e2e leg)")
+    ap.add_argument("--micro-batch", type=int, default=32, help="windows per H2D/compute/D2H micro-batch (e2e leg)")
     ap.add_argument("--model", default="large-v3")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

@@ -33,7 +33,11 @@ namespace aries {
 namespace {
 
 constexpr int kBlockQ = 128;                             // rows per query tile (= TMEM lanes)
-constexpr int kQTiles = 2;                               // query tiles per CTA
+#ifndef ARIES_ATTN_QTILES
+#define ARIES_ATTN_QTILES 1
+#endif
+constexpr int kQTiles = ARIES_ATTN_QTILES;               // query tiles per CTA (1: two CTAs per SM, 2: one)
+constexpr int kCtasPerSm = 2 / kQTiles;
 constexpr int kBlockKV = 64;
 constexpr int kHeadDim = 64;
 constexpr int kOCols = 80;                               // 64 output columns + the row-sum column (+ 15 of padding)
@@ -49,9 +53,10 @@ constexpr int kKBytes = kBlockKV * kHeadDim * 2;         // 8 KB (64 keys x 128 
 constexpr int kVTmaBytes = kHeadDim * kBlockKV * 2;      // 8 KB written by TMA ...
 constexpr int kVBytes = kOCols * kBlockKV * 2;           // ... + 2 KB constant tail: a row of ones and 15 rows of zeros
 constexpr int kSmemBytes = kQTiles * kQTileBytes + kKStages * kKBytes + kVStages * kVBytes + 256 + 1024;   // 107,776 B
-constexpr uint32_t kTmemCols = 512;                      // per tile g: S0 [128g, +64) S1 [128g+64, +64); O_g [256+80g, +80)
-constexpr uint32_t kTmemO = 256;
+constexpr uint32_t kTmemCols = 256 * kQTiles;            // per tile g: S0 [128g, +64) S1 [128g+64, +64); O_g [kTmemO+80g, +80)
+constexpr uint32_t kTmemO = 128 * kQTiles;
 constexpr float kScale = 0.18033688011112042f;           // log2(e) / sqrt(64)
+constexpr int kDefaultPoly = 0;                          // ARIES_ATTN_POLY overrides (0, 4 or 8)
 constexpr float kRescaleThreshold = 8.0f;                // lazy rescale: only when the row max grew by > 2^8
 
 // Test-only timeline (variant bit 2, ARIES_ATTN_TRACE=1): clock64 stamps of lane 0 of every warp of a few CTAs.
@@ -124,7 +129,7 @@ __device__ __forceinline__ void join32(float (&e)[32]) {
 // p = exp2(s * c - m * c) for 32 scores -> 16 packed bf16x2 (low half = the lower key index).  The scale / offset is
 // a packed f32x2 FMA (two scores per instruction); with kPoly every 8th exponential runs on the FMA pipe instead of
 // the MUFU.
-template <bool kPoly>
+template <int kPoly>
 __device__ __forceinline__ void exp_pack(const uint32_t (&s)[32], float neg_m, uint32_t (&out)[16]) {
     const float2 c2 = make_float2(kScale, kScale);
     const float2 m2 = make_float2(neg_m, neg_m);
@@ -137,14 +142,14 @@ __device__ __forceinline__ void exp_pack(const uint32_t (&s)[32], float neg_m, u
     }
     join32(e);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) e[i] = (kPoly && (i & 7) == 7) ? poly_exp2(e[i]) : fast_exp2(e[i]);
+    for (int i = 0; i < 32; ++i) e[i] = (kPoly > 0 && (i % (kPoly > 0 ? kPoly : 1)) == (kPoly - 1)) ? poly_exp2(e[i]) : fast_exp2(e[i]);
     join32(e);
 #pragma unroll
     for (int i = 0; i < 32; i += 2) out[i >> 1] = pack_bf16x2(e[i], e[i + 1]);
 }
 
-template <bool kPoly, bool kTrace>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int kPoly, bool kTrace>
+__global__ void __launch_bounds__(kThreads, kCtasPerSm)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                      const __grid_constant__ CUtensorMap tmap_vt, const AttnParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -405,17 +410,18 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     if (kTrace) tr.stamp();
 }
 
-int attn_variant() {               // bit 0: polynomial exp2 on every 8th element; bit 2: trace
+int attn_variant() {               // 0: all exponentials on the MUFU; 8 / 4: every 8th / 4th on the FMA pipe; -1: trace
     static const int v = [] {
         const char* e = getenv("ARIES_ATTN_POLY");
         const char* r = getenv("ARIES_ATTN_TRACE");
-        if (r && r[0] != '0') return 4;
-        return (e && e[0] != '0') ? 1 : 0;
+        if (r && r[0] != '0') return -1;
+        const int n = e ? atoi(e) : kDefaultPoly;
+        return (n == 4 || n == 8) ? n : 0;
     }();
     return v;
 }
 
-template <bool kPoly, bool kTrace>
+template <int kPoly, bool kTrace>
 cudaError_t set_smem() {
     return cudaFuncSetAttribute(attention_fwd_kernel<kPoly, kTrace>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 kSmemBytes);
@@ -425,9 +431,10 @@ cudaError_t set_smem() {
 
 cudaError_t attention_init_device() {
     cudaError_t e;
-    if ((e = set_smem<false, false>()) != cudaSuccess) return e;
-    if ((e = set_smem<true, false>()) != cudaSuccess) return e;
-    return set_smem<false, true>();
+    if ((e = set_smem<0, false>()) != cudaSuccess) return e;
+    if ((e = set_smem<8, false>()) != cudaSuccess) return e;
+    if ((e = set_smem<4, false>()) != cudaSuccess) return e;
+    return set_smem<0, true>();
 }
 
 cudaError_t attention_read_trace(unsigned long long* host, size_t count) {
@@ -458,9 +465,10 @@ cudaError_t attention_launch(const AttnMaps& maps, const AttnParams& p, cudaStre
     if (p.d_model != p.n_heads * kHeadDim || p.T <= 0 || p.batch <= 0) return cudaErrorInvalidValue;
     dim3 grid((p.T + kQTiles * kBlockQ - 1) / (kQTiles * kBlockQ), p.n_heads, p.batch);
     switch (attn_variant()) {
-        case 1: attention_fwd_kernel<true, false><<<grid, kThreads, kSmemBytes, stream>>>(maps.q, maps.k, maps.vt, p); break;
-        case 4: attention_fwd_kernel<false, true><<<grid, kThreads, kSmemBytes, stream>>>(maps.q, maps.k, maps.vt, p); break;
-        default: attention_fwd_kernel<false, false><<<grid, kThreads, kSmemBytes, stream>>>(maps.q, maps.k, maps.vt, p); break;
+        case 8: attention_fwd_kernel<8, false><<<grid, kThreads, kSmemBytes, stream>>>(maps.q, maps.k, maps.vt, p); break;
+        case 4: attention_fwd_kernel<4, false><<<grid, kThreads, kSmemBytes, stream>>>(maps.q, maps.k, maps.vt, p); break;
+        case -1: attention_fwd_kernel<0, true><<<grid, kThreads, kSmemBytes, stream>>>(maps.q, maps.k, maps.vt, p); break;
+        default: attention_fwd_kernel<0, false><<<grid, kThreads, kSmemBytes, stream>>>(maps.q, maps.k, maps.vt, p); break;
     }
     return cudaGetLastError();
 }

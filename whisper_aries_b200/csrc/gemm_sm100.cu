@@ -3,7 +3,7 @@
 //   C[M,N] = A[M,K] * B[N,K]^T  (A, B bf16 K-major; f32 accumulate in TMEM)
 //
 // One CTA per SM loops over 128 x BN output tiles (n fastest so the weight matrix stays L2-resident while an
-// A panel is swept).  Roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warps 2..9 =
+// A panel is swept).  Roles: warp 0 = TMA producer, warp 1 = MMA issuer (convergent, one elected lane per instruction), warps 2..9 =
 // epilogue (two warps per TMEM lane quarter, each owning half of the tile's columns).  The accumulator is
 // double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the main loop of tile i+1.
 //
@@ -100,10 +100,17 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
             // ------------------------------------------------------------ MMA issuer
+            // The whole warp runs this loop convergently and every tcgen05 instruction is predicated on elect.sync
+            // (ptx.cuh): under a divergent `if (lane == 0)` ptxas wraps each one in a loop over the active lanes,
+            // ~13 instructions and ~80 cycles of issue per MMA -- more than half of the 135 cycles a 128x256x16 MMA
+            // occupies the tensor pipe.  The four K = 16 steps of a stage go out as one statement.
+            static_assert(BK == 64, "one x4 group per stage");
             constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, false, false);
-            constexpr uint64_t desc_hi = umma_smem_desc_hi(16, 1024);   // K-major SW128: SBO = 8 rows * 128 B
+            constexpr uint64_t desc_hi64 = umma_smem_desc_hi(16, 1024);   // K-major SW128: SBO = 8 rows * 128 B
+            constexpr uint32_t desc_hi = (uint32_t)(desc_hi64 >> 32);
+            const uint32_t desc_lo0 = (uint32_t)(desc_hi64 & 0xFFFFFFFFu) | ((base >> 4) & 0x3FFF);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -116,15 +123,10 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint32_t sa = base + stage * C::kStageBytes;
-                    const uint32_t sb = sa + C::kABytes;
-#pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        umma_bf16_ss(d_tmem, umma_smem_desc(sa + k * 32, desc_hi), umma_smem_desc(sb + k * 32, desc_hi),
-                                     idesc, (kb | k) != 0);
-                    }
-                    umma_commit(&empty_bar[stage]);          // frees the smem slot once these MMAs retire
-                    if (kb == num_kb - 1) umma_commit(&tfull_bar[as]);
+                    const uint32_t a_lo = desc_lo0 + ((uint32_t)(stage * C::kStageBytes) >> 4);
+                    umma_bf16_ss_x4_elect(d_tmem, a_lo, a_lo + (C::kABytes >> 4), desc_hi, idesc, kb != 0);
+                    umma_commit_elect(&empty_bar[stage]);    // frees the smem slot once these MMAs retire
+                    if (kb == num_kb - 1) umma_commit_elect(&tfull_bar[as]);
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                 }
             }
