@@ -1,4 +1,4 @@
-"""Small profiling targets for ncu (run under gpurun):  python tests/prof_target.py mel|attn|gemm-o|gemm-fc1|gemm-qkv"""
+"""Small profiling targets for ncu (run under gpurun):  python tests/prof_target.py mel|attn|ln|gemm-o|gemm-fc1|gemm-fc2|gemm-qkv"""
 import ctypes
 import sys
 
@@ -34,6 +34,14 @@ elif what == "attn":
     out = torch.empty((B_ * T_, d), device=dev, dtype=torch.bfloat16)
     for _ in range(3):
         lib.aries_test_attention(ctx.handle, ptr(qk), ptr(vt), B_, T_, H, t_pad, ptr(out), None)
+    torch.cuda.synchronize()
+elif what == "ln":
+    rows, d = 96000, 1280
+    x = torch.randn(rows, d, device=dev)
+    gm, bt = torch.randn(d, device=dev), torch.randn(d, device=dev)
+    y = torch.empty((rows, d), device=dev, dtype=torch.bfloat16)
+    for _ in range(3):
+        lib.aries_test_layernorm(ctx.handle, ptr(x), ptr(gm), ptr(bt), ptr(y), rows, d, None)
     torch.cuda.synchronize()
 else:
     M = 96000

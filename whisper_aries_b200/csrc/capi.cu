@@ -375,7 +375,7 @@ int aries_test_gemm(aries_ctx* ctx, int epi, int M, int N, int K, const void* a,
     CUtensorMap ta, tb;
     const unsigned long long da[2] = {(unsigned long long)K, (unsigned long long)M}, sa[2] = {2, (unsigned long long)K * 2};
     const unsigned long long db[2] = {(unsigned long long)K, (unsigned long long)N};
-    const unsigned ba[2] = {64, 128}, bb[2] = {64, (unsigned)aries::gemm_block_n(N)};
+    const unsigned ba[2] = {64, 128}, bb[2] = {64, (unsigned)aries::gemm_b_box_rows()};
     cudaError_t e;
     if ((e = aries::make_tmap_bf16(&ta, a, 2, da, sa, ba)) != cudaSuccess) return fail_cuda("tensor map A", e);
     if ((e = aries::make_tmap_bf16(&tb, b, 2, db, sa, bb)) != cudaSuccess) return fail_cuda("tensor map B", e);

@@ -266,17 +266,17 @@ cudaError_t encoder_plan_create(int device, int sm_count, const EncoderShapeC& c
     pl->pos = F(o_pos);
     pl->lnf_g = F(o_lnf_g);
     pl->lnf_b = F(o_lnf_b);
-    if ((e = map2d(&pl->m_conv1, base + o_conv1w, 3ull * cp, d, gemm_block_n(d))) != cudaSuccess) return fail(e);
-    if ((e = map2d(&pl->m_conv2, base + o_conv2w, 3ull * d, d, gemm_block_n(d))) != cudaSuccess) return fail(e);
+    if ((e = map2d(&pl->m_conv1, base + o_conv1w, 3ull * cp, d, gemm_b_box_rows())) != cudaSuccess) return fail(e);
+    if ((e = map2d(&pl->m_conv2, base + o_conv2w, 3ull * d, d, gemm_b_box_rows())) != cudaSuccess) return fail(e);
     for (int i = 0; i < L; ++i) {
         LayerW& lw = pl->layers[i];
         const Offs& o = offs[i];
         lw.ln1_g = F(o.ln1_g); lw.ln1_b = F(o.ln1_b); lw.bqkv = F(o.bqkv); lw.bo = F(o.bo);
         lw.ln2_g = F(o.ln2_g); lw.ln2_b = F(o.ln2_b); lw.b1 = F(o.b1); lw.b2 = F(o.b2);
-        if ((e = map2d(&lw.m_qkv, base + o.wqkv, d, 3ull * d, gemm_block_n(3 * d))) != cudaSuccess) return fail(e);
-        if ((e = map2d(&lw.m_o, base + o.wo, d, d, gemm_block_n(d))) != cudaSuccess) return fail(e);
-        if ((e = map2d(&lw.m_fc1, base + o.w1, d, f, gemm_block_n(f))) != cudaSuccess) return fail(e);
-        if ((e = map2d(&lw.m_fc2, base + o.w2, f, d, gemm_block_n(d))) != cudaSuccess) return fail(e);
+        if ((e = map2d(&lw.m_qkv, base + o.wqkv, d, 3ull * d, gemm_b_box_rows())) != cudaSuccess) return fail(e);
+        if ((e = map2d(&lw.m_o, base + o.wo, d, d, gemm_b_box_rows())) != cudaSuccess) return fail(e);
+        if ((e = map2d(&lw.m_fc1, base + o.w1, d, f, gemm_b_box_rows())) != cudaSuccess) return fail(e);
+        if ((e = map2d(&lw.m_fc2, base + o.w2, f, d, gemm_b_box_rows())) != cudaSuccess) return fail(e);
     }
     *out = pl;
     return cudaSuccess;

@@ -33,6 +33,7 @@ struct GemmParams {
 };
 
 int gemm_block_n(int N);
+int gemm_b_box_rows();      // rows of the B (weight) tensor map's box: 128 for every kernel variant
 cudaError_t gemm_init_device();
 cudaError_t gemm_launch(int epi, const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const GemmParams& p,
                         int sm_count, cudaStream_t stream);

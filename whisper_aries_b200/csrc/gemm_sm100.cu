@@ -12,6 +12,8 @@
 // (CT2 ref: layers::WhisperEncoder conv1/conv2).  Epilogues fuse bias, exact-erf GELU,
 // the residual add and the positional-embedding add and remap GEMM rows to output
 // rows so padded rows are never written.
+#include <cstdlib>
+
 #include "gemm.h"
 #include "ptx.cuh"
 
@@ -23,12 +25,20 @@ constexpr int BM = 128;
 constexpr int BK = 64;                       // 64 bf16 = 128 B = one SWIZZLE_128B atom row
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 64 + kEpiWarps * 32;
+constexpr bool kDefaultPair = true;          // CTA-pair kernel for BN = 256 (ARIES_GEMM_PAIR overrides)
 
-template <int BN>
+constexpr int kBBoxRows = 128;               // rows of one B TMA box (the tensor maps are built with this box)
+
+// CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, the two SMs of a TPC) per 256 x BN tile with
+// tcgen05 cta_group::2 -- each CTA stages its own 128 rows of A and HALF of the B tile, so the shared-memory operand
+// traffic per SM (the limiter of the 1-CTA 128 x 256 tile: 48 KB per 64-deep stage) drops by a third and two more
+// stages fit.
+template <int BN, int CG>
 struct Cfg {
-    static constexpr int kStages = (BN == 256) ? 4 : 6;
+    static_assert(CG == 1 || (CG == 2 && BN == 256), "the CTA-pair kernel is built for BN = 256 only");
+    static constexpr int kStages = (BN == 256 && CG == 1) ? 4 : 6;
     static constexpr int kABytes = BM * BK * 2;
-    static constexpr int kBBytes = BN * BK * 2;
+    static constexpr int kBBytes = (BN / CG) * BK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kBarBytes = 256;
     static constexpr int kEpiStageBytes = kEpiWarps * 32 * 32 * 4;                // 4 KB transpose buffer per warp
@@ -36,11 +46,11 @@ struct Cfg {
     static constexpr uint32_t kTmemCols = 2 * BN;
 };
 
-template <int BN, int EPI>
+template <int BN, int EPI, int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const GemmParams p) {
-    using C = Cfg<BN>;
+    using C = Cfg<BN, CG>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
@@ -54,7 +64,10 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
-    const int num_m = (p.M + BM - 1) / BM;
+    const int cta_rank = (CG == 2) ? (int)cluster_ctarank() : 0;
+    const int first_tile = blockIdx.x / CG;            // tiles are dealt to CTAs (CG = 1) or CTA pairs (CG = 2)
+    const int tile_step = gridDim.x / CG;
+    const int num_m = (p.M + BM * CG - 1) / (BM * CG);
     const int num_n = p.N / BN;
     const int num_tiles = num_m * num_n;
     const int num_kb = p.K / BK;
@@ -68,13 +81,17 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tfull_bar[s], 1);
-            mbar_init(&tempty_bar[s], kEpiWarps);
+            mbar_init(&tempty_bar[s], kEpiWarps * CG);   // CG = 2: the epilogue warps of both CTAs report to rank 0
         }
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc<C::kTmemCols>(tmem_slot);
+    if (warp == 1) {
+        if (CG == 2) tmem_alloc_pair<C::kTmemCols>(tmem_slot);
+        else tmem_alloc<C::kTmemCols>(tmem_slot);
+    }
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all();                     // the peer's barriers exist before anything signals them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -83,38 +100,47 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             // ------------------------------------------------------------ TMA producer
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (tile / num_n) * BM;
+            for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+                const int m0 = (tile / num_n) * (BM * CG) + cta_rank * BM;
                 const int n0 = (tile % num_n) * BN;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * C::kStageBytes;
                     uint8_t* sb = sa + C::kABytes;
-                    mbar_expect_tx(&full_bar[stage], C::kStageBytes);
                     const int kk = kb * BK;
                     const int roff = kk / p.a_cols;
-                    tma_load_2d(sa, &tmap_a, &full_bar[stage], kk - roff * p.a_cols, m0 + roff);
-                    tma_load_2d(sb, &tmap_b, &full_bar[stage], kk, n0);
+                    if (CG == 2) {
+                        // both CTAs' bytes are counted on rank 0's barrier, which rank 0 arms for the pair
+                        if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * C::kStageBytes);
+                        tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], kk - roff * p.a_cols, m0 + roff);
+                        tma_load_2d_pair(sb, &tmap_b, &full_bar[stage], kk, n0 + cta_rank * kBBoxRows);
+                    } else {
+                        mbar_expect_tx(&full_bar[stage], C::kStageBytes);
+                        tma_load_2d(sa, &tmap_a, &full_bar[stage], kk - roff * p.a_cols, m0 + roff);
+#pragma unroll
+                        for (int h = 0; h < BN / kBBoxRows; ++h)
+                            tma_load_2d(sb + h * kBBoxRows * BK * 2, &tmap_b, &full_bar[stage], kk, n0 + h * kBBoxRows);
+                    }
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        {
-            // ------------------------------------------------------------ MMA issuer
+        if (cta_rank == 0) {
+            // ------------------------------------------------------------ MMA issuer (rank 0 of a pair issues for both)
             // The whole warp runs this loop convergently and every tcgen05 instruction is predicated on elect.sync
             // (ptx.cuh): under a divergent `if (lane == 0)` ptxas wraps each one in a loop over the active lanes,
             // ~13 instructions and ~80 cycles of issue per MMA -- more than half of the 135 cycles a 128x256x16 MMA
             // occupies the tensor pipe.  The four K = 16 steps of a stage go out as one statement.
             static_assert(BK == 64, "one x4 group per stage");
-            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, false, false);
+            constexpr uint32_t idesc = umma_idesc_bf16(BM * CG, BN, false, false);
             constexpr uint64_t desc_hi64 = umma_smem_desc_hi(16, 1024);   // K-major SW128: SBO = 8 rows * 128 B
             constexpr uint32_t desc_hi = (uint32_t)(desc_hi64 >> 32);
             const uint32_t desc_lo0 = (uint32_t)(desc_hi64 & 0xFFFFFFFFu) | ((base >> 4) & 0x3FFF);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
                 const int as = it & 1;
                 const uint32_t aphase = (it >> 1) & 1;
                 mbar_wait(&tempty_bar[as], aphase ^ 1);
@@ -124,9 +150,15 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t a_lo = desc_lo0 + ((uint32_t)(stage * C::kStageBytes) >> 4);
-                    umma_bf16_ss_x4_elect(d_tmem, a_lo, a_lo + (C::kABytes >> 4), desc_hi, idesc, kb != 0);
-                    umma_commit_elect(&empty_bar[stage]);    // frees the smem slot once these MMAs retire
-                    if (kb == num_kb - 1) umma_commit_elect(&tfull_bar[as]);
+                    if (CG == 2) {
+                        umma_bf16_ss_x4_elect_pair(d_tmem, a_lo, a_lo + (C::kABytes >> 4), desc_hi, idesc, kb != 0);
+                        umma_commit_elect_pair(&empty_bar[stage]);           // frees the slot in BOTH CTAs
+                        if (kb == num_kb - 1) umma_commit_elect_pair(&tfull_bar[as]);
+                    } else {
+                        umma_bf16_ss_x4_elect(d_tmem, a_lo, a_lo + (C::kABytes >> 4), desc_hi, idesc, kb != 0);
+                        umma_commit_elect(&empty_bar[stage]);    // frees the smem slot once these MMAs retire
+                        if (kb == num_kb - 1) umma_commit_elect(&tfull_bar[as]);
+                    }
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -145,10 +177,10 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         const int sub_row = lane >> 3;         // coalesced phase: row 4 i + sub_row, 16-byte column c4
         const int c4 = lane & 7;
         int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
-            const int m0 = (tile / num_n) * BM;
+            const int m0 = (tile / num_n) * (BM * CG) + cta_rank * BM;
             const int n0 = (tile % num_n) * BN + half * (BN / 2);
             const int rbase = m0 + quarter * 32;
             // output rows of the coalesced phase: element offset of the row start (32-bit: the largest activation
@@ -253,23 +285,54 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+            if (lane == 0) {
+                if (CG == 2) mbar_arrive_rank0(&tempty_bar[as]);
+                else mbar_arrive(&tempty_bar[as]);
+            }
         }
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all();                     // neither CTA may retire while its peer still uses it
+    else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<C::kTmemCols>(tmem_base);
+        if (CG == 2) tmem_dealloc_pair<C::kTmemCols>(tmem_base);
+        else tmem_dealloc<C::kTmemCols>(tmem_base);
     }
+}
+
+bool use_cta_pairs() {                     // ARIES_GEMM_PAIR=0 falls back to the 1-CTA kernel (A/B comparisons)
+    static const bool on = [] {
+        const char* e = getenv("ARIES_GEMM_PAIR");
+        return e ? (e[0] != '0') : kDefaultPair;
+    }();
+    return on;
 }
 
 template <int BN, int EPI>
 cudaError_t launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int sm_count,
                        cudaStream_t stream) {
-    using C = Cfg<BN>;
-    auto kern = gemm_bf16_tcgen05<BN, EPI>;
+    if (BN == 256 && use_cta_pairs() && p.M > BM) {
+        using C = Cfg<256, 2>;
+        const int tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * (p.N / 256);
+        const int pairs = tiles < sm_count / 2 ? tiles : sm_count / 2;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * pairs);
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = C::kSmemBytes;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05<256, EPI, 2>, ta, tb, p);
+    }
+    using C = Cfg<BN, 1>;
+    auto kern = gemm_bf16_tcgen05<BN, EPI, 1>;
     const int tiles = ((p.M + BM - 1) / BM) * (p.N / BN);
     const int grid = tiles < sm_count ? tiles : sm_count;
     kern<<<grid, kThreads, C::kSmemBytes, stream>>>(ta, tb, p);
@@ -292,12 +355,16 @@ cudaError_t launch_bn(int epi, const CUtensorMap& ta, const CUtensorMap& tb, con
 }  // namespace
 
 int gemm_block_n(int N) { return (N % 256 == 0) ? 256 : 128; }
+int gemm_b_box_rows() { return kBBoxRows; }
 
 namespace {
 template <int BN, int EPI>
 cudaError_t set_smem() {
-    return cudaFuncSetAttribute(gemm_bf16_tcgen05<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                Cfg<BN>::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05<BN, EPI, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg<BN, 1>::kSmemBytes);
+    if (e != cudaSuccess || BN != 256) return e;
+    return cudaFuncSetAttribute(gemm_bf16_tcgen05<256, EPI, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                Cfg<256, 2>::kSmemBytes);
 }
 template <int BN>
 cudaError_t set_smem_bn() {

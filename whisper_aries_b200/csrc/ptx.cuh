@@ -248,6 +248,72 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                  : "memory");
 }
 
+// ---------------------------------------------------------------- CTA pairs (cta_group::2)
+// Two CTAs of one cluster (the two SMs of a TPC) execute ONE tcgen05.mma with M = 256: each holds its own 128 rows of
+// A and of the accumulator, and HALF of the B tile, which the instruction reads from both shared memories.  Only the
+// rank-0 CTA issues MMAs; both issue TMA loads that signal rank 0's mbarrier, and the commit is multicast to both.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;      // clears the CTA-rank bit of a shared::cluster address -> rank 0
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+}
+// TMA load whose completion bytes are counted on the RANK-0 CTA's barrier at the same shared-memory offset.
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+        "[%2];" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+        : "memory");
+}
+// arrive on the rank-0 CTA's copy of a barrier (from either CTA of the pair)
+__device__ __forceinline__ void mbar_arrive_rank0(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_slot) {   // one warp (same index) in BOTH CTAs
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)),
+                 "n"(kCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+// Four K = 16 steps, M = 256 over the CTA pair (see umma_bf16_ss_x4_elect).
+__device__ __forceinline__ void umma_bf16_ss_x4_elect_pair(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo,
+                                                           uint32_t desc_hi, uint32_t idesc, uint32_t accumulate_first) {
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t.reg .b32 a, b;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "@e tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t"
+        "add.u32 a, %1, 2;\n\tadd.u32 b, %2, 2;\n\tmov.b64 da, {a, %3};\n\tmov.b64 db, {b, %3};\n\t"
+        "@e tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, 1;\n\t"
+        "add.u32 a, %1, 4;\n\tadd.u32 b, %2, 4;\n\tmov.b64 da, {a, %3};\n\tmov.b64 db, {b, %3};\n\t"
+        "@e tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, 1;\n\t"
+        "add.u32 a, %1, 6;\n\tadd.u32 b, %2, 6;\n\tmov.b64 da, {a, %3};\n\tmov.b64 db, {b, %3};\n\t"
+        "@e tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, 1;\n\t}" ::"r"(tmem_d),
+        "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate_first)
+        : "memory");
+}
+// commit of the pair's MMAs, arriving on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_elect_pair(uint64_t* bar) {
+    asm volatile(
+        "{\n\t.reg .pred e;\n\t.reg .b16 m;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "mov.b16 m, 3;\n\t"
+        "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}"
+        ::"r"(smem_u32(bar))
+        : "memory");
+}
+
 // ---------------------------------------------------------------- TMEM -> registers
 // 32 lanes x 32 consecutive 32-bit columns: thread i of the warp gets lane (base+i), r[j] = column (base+j).
 __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
