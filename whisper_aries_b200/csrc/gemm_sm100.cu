@@ -263,9 +263,12 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 for (int i = 0; i < 8; ++i) {
                     const int rl = 4 * i + sub_row;
                     float4 v = stage[rl * 8 + (c4 ^ (rl & 7))];
-                    v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
                     if (EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_GELU_POS_F32) {
-                        v.x = gelu_fast(v.x); v.y = gelu_fast(v.y); v.z = gelu_fast(v.z); v.w = gelu_fast(v.w);
+                        const float2 lo = gelu_poly2(__fadd2_rn(make_float2(v.x, v.y), make_float2(bb.x, bb.y)));
+                        const float2 hi = gelu_poly2(__fadd2_rn(make_float2(v.z, v.w), make_float2(bb.z, bb.w)));
+                        v = make_float4(lo.x, lo.y, hi.x, hi.y);
+                    } else {
+                        v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
                     }
                     const bool ok = (valid_c >> i) & 1u;
                     const unsigned off = row_off_c[i] + nc + 4 * c4;
