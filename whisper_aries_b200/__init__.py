@@ -2,10 +2,11 @@
 
 Python host code over a C-ABI CUDA library (include/aries_b200.h).  No CPU fallback: the CUDA library must be built
 (``__graft_entry__.build()``) and a B200 must be present for anything but construction-time host logic."""
+from . import ct2_model
 from .encoder import WhisperEncoder, WhisperModel
 from .feature_extractor import FeatureExtractor
 from .scheduler import ChunkResult, ChunkScheduler, ChunkWork, partition_windows
 from .synthetic import SHAPES, EncoderShape
 
 __all__ = ["FeatureExtractor", "WhisperEncoder", "WhisperModel", "ChunkScheduler", "ChunkWork", "ChunkResult",
-           "partition_windows", "SHAPES", "EncoderShape"]
+           "partition_windows", "SHAPES", "EncoderShape", "ct2_model"]

@@ -136,11 +136,21 @@ class WhisperModel:
     B200 path always computes in bf16 with f32 accumulation.  Decoding (``transcribe`` / ``generate``) is out of
     scope for this library."""
 
-    def __init__(self, model_size_or_shape, weights: dict, device: str = "cuda", device_index: int = 0,
+    def __init__(self, model_size_or_shape, weights: dict | None = None, device: str = "cuda", device_index: int = 0,
                  compute_type: str = "bfloat16", **_ignored):
         if device not in ("cuda", "auto"):
             raise ValueError("whisper_aries_b200 has no CPU path: device must be 'cuda'")
         dev = f"cuda:{device_index}"
+        self.model_info = None
+        if weights is None:
+            # upstream's first argument is "size or path of a converted model directory" (model.bin + config.json);
+            # there is no network here, so only the path form can supply weights (SURVEY.md row f2)
+            import os
+            from .ct2_model import load_encoder_weights
+            if not (isinstance(model_size_or_shape, str) and os.path.isdir(model_size_or_shape)):
+                raise ValueError("weights=None needs the path of a CTranslate2 model directory (model.bin); "
+                                 f"got {model_size_or_shape!r}")
+            model_size_or_shape, weights, self.model_info = load_encoder_weights(model_size_or_shape)
         shape = SHAPES[model_size_or_shape] if isinstance(model_size_or_shape, str) else model_size_or_shape
         self.shape = shape
         self.compute_type = compute_type
