@@ -5,6 +5,7 @@
 Prints, for a few traced CTAs, the average clock64 cycles the softmax warps spend per key tile in each phase
 (wait S | load+max | exponentials+pack | store+publish) and what the MMA-issue warps spend (wait P | PV issue | QK issue)."""
 import ctypes
+import os
 import sys
 
 import numpy as np
@@ -27,6 +28,9 @@ for _ in range(3):
     lib.aries_test_attention(ctx.handle, p(qk), p(vt), B_, T_, H, t_pad, p(out), None)
 torch.cuda.synchronize()
 CT, W, E = 16, 11, 160
+QTILES = int(os.environ.get('ARIES_ATTN_QTILES', '1'))          # must match the library build
+SOFTMAX_WARPS = (0, 3) if QTILES == 1 else (0, 3, 4, 7)
+MMA_WARPS = (5,) if QTILES == 1 else (9, 10)
 buf = np.zeros(CT * W * E, dtype=np.uint64)
 rc = lib.aries_test_attention_trace(ctx.handle, buf.ctypes.data_as(ctypes.c_void_p), buf.size)
 assert rc == 0
@@ -38,7 +42,7 @@ for c in range(CT):
         continue
     t0 = tr[c, :, 0].min()
     print(f"--- traced CTA slot {c}: lifetime {tr[c].max() - t0} clk")
-    for w in (0, 3, 4, 7):                       # softmax stamps: entry, 4 per tile, 2 (o_full), 2 (exit)
+    for w in SOFTMAX_WARPS:                       # softmax stamps: entry, 4 per tile, 2 (o_full), 2 (exit)
         s = tr[c, w]
         ev = s[1:1 + 4 * n_kv].reshape(n_kv, 4)
         nxt = np.concatenate([ev[1:, 0], s[1 + 4 * n_kv:2 + 4 * n_kv]])
@@ -49,7 +53,7 @@ for c in range(CT):
               f"ld+max {ldmax[sl].mean():.0f} exp+pack {exp[sl].mean():.0f} st+publish {stpub[sl].mean():.0f} "
               f"total {(ev[n_kv - 2, 0] - ev[3, 0]) / (n_kv - 5):.0f}; o_full wait {s[k + 1] - s[k]}; "
               f"epilogue {s[k + 2] - s[k + 1]}; exit at +{s[k + 3] - t0}")
-    for w in (9, 10):                            # MMA issue: 1 + 4 per tile
+    for w in MMA_WARPS:                            # MMA issue: 1 + 4 per tile
         s = tr[c, w]
         ev = s[1:1 + 4 * n_kv].reshape(n_kv, 4)
         sl = slice(3, n_kv - 3)
