@@ -13,3 +13,6 @@ for t in mel attn ln gemm-fc1 gemm-qkv gemm-o; do
   timeout -s KILL 400 ncu --set full --clock-control none --import-source on -k regex:"$k" -s 2 -c 1 -o gpurun_out/final_$t -f python tests/prof_target.py $t > gpurun_out/ncu_final_$t.log 2>&1
   echo "ncu $t exit $?"
 done
+timeout -s KILL 400 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_final.log 2> gpurun_out/bench_final.err; echo "bench final exit $?"
+timeout -s KILL 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_final.log 2> gpurun_out/bench_ref_final.err; echo "bench ref exit $?"
+timeout -s KILL 200 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke exit $?"; tail -n 2 gpurun_out/smoke.log
