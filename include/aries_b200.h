@@ -83,7 +83,7 @@ ARIES_API int aries_logmel_run_host(aries_mel* mel, const float* pcm_host, int b
 /* ---------------------------------------------------------------------------------------------- encoder
  * Replaces ctranslate2.models.Whisper.encode (layers::WhisperEncoder): conv1(k3,s1,p1)+GELU, conv2(k3,s2,p1)+GELU,
  * + position encodings, n_layers pre-norm blocks (MHA with q scaled by head_dim^-0.5 and no key bias, GELU MLP),
- * final LayerNorm (eps 1e-5).  bf16 tensor-core arithmetic, f32 accumulation / residual stream / LN / softmax. */
+ * final LayerNorm (eps 1e-5).  bf16 tensor-core arithmetic, f32 accumulation / LN statistics / softmax, f16 residual stream. */
 typedef struct aries_encoder_cfg {
     int32_t n_mels;     /* 80 | 128 */
     int32_t d_model;    /* multiple of 128 */

@@ -96,11 +96,11 @@ def diag_gemm():
         a = (torch.randn(M, K, generator=g) * 0.5).to(dev).bfloat16()
         b = (torch.randn(N, K, generator=g) * 0.05).to(dev).bfloat16()
         bias = torch.randn(N, generator=g).to(dev)
-        resid = torch.randn(M, N, generator=g).to(dev)
+        resid = torch.randn(M, N, generator=g).to(dev).half()
         pos_rows = 100
         pos = torch.randn(pos_rows, N, generator=g).to(dev)
         for epi in (0, 1, 2, 3):
-            out = torch.full((M, N), float("nan"), device=dev, dtype=torch.bfloat16 if epi < 2 else torch.float32)
+            out = torch.full((M, N), float("nan"), device=dev, dtype=torch.bfloat16 if epi < 2 else torch.float16)
             Mx = (M // pos_rows) * pos_rows if epi == 3 else M
             rc = lib.aries_test_gemm(ctx.handle, epi, Mx, N, K, ptr(a), ptr(b), ptr(bias), ptr(resid), ptr(pos), pos_rows,
                                      ptr(out), None, 0, 0, 0, None)
@@ -108,7 +108,7 @@ def diag_gemm():
             if rc:
                 print(f"gemm M={M} N={N} K={K} epi={epi} rc={rc} {_lib.last_error()}", flush=True)
                 continue
-            ref = gemm_ref(a[:Mx], b, bias, epi, resid[:Mx], pos, pos_rows)
+            ref = gemm_ref(a[:Mx], b, bias, epi, resid[:Mx].float(), pos, pos_rows)
             err = (out[:Mx].float() - ref).abs()
             bad = torch.isnan(out[:Mx].float()).sum().item()
             print(f"gemm M={Mx} N={N} K={K} epi={epi} max_err={err.nan_to_num(1e9).max().item():.3e} "
@@ -146,8 +146,8 @@ def diag_gemmperf():
         a = torch.randn(M, K, device=dev).bfloat16()
         b = (torch.randn(N, K, device=dev) * 0.05).bfloat16()
         bias = torch.randn(N, device=dev)
-        resid = torch.randn(M, N, device=dev) if epi == 2 else None
-        out = torch.empty((M, N), device=dev, dtype=torch.bfloat16 if epi < 2 else torch.float32)
+        resid = torch.randn(M, N, device=dev).half() if epi == 2 else None
+        out = torch.empty((M, N), device=dev, dtype=torch.bfloat16 if epi < 2 else torch.float16)
 
         def run():
             lib.aries_test_gemm(ctx.handle, epi, M, N, K, ptr(a), ptr(b), ptr(bias), ptr(resid), None, 0, ptr(out), None,
@@ -165,12 +165,12 @@ def diag_gemmperf():
 def diag_ln():
     ctx = _lib.Context.get(0)
     for d in (128, 384, 1024, 1280):
-        x = torch.randn(1000, d, device=dev) * 3 + 0.5
+        x = (torch.randn(1000, d, device=dev) * 3 + 0.5).half()
         gm, bt = torch.randn(d, device=dev), torch.randn(d, device=dev)
         y = torch.empty((1000, d), device=dev, dtype=torch.bfloat16)
         rc = ctx.lib.aries_test_layernorm(ctx.handle, ptr(x), ptr(gm), ptr(bt), ptr(y), 1000, d, None)
         torch.cuda.synchronize()
-        ref = torch.nn.functional.layer_norm(x, (d,), gm, bt, 1e-5)
+        ref = torch.nn.functional.layer_norm(x.float(), (d,), gm, bt, 1e-5)
         print(f"ln d={d} rc={rc} max_err={(y.float() - ref).abs().max().item():.3e} (bf16 out, ref_max={ref.abs().max().item():.1f})",
               flush=True)
 

@@ -47,7 +47,7 @@ traffic = {}
 names = {"mel": "logmel_tiles_kernel", "attn": "attention_fwd_kernel", "ln": "layernorm_kernel",
          "gemm-fc1": "gemm_bf16_tcgen05 (fc1: M=96000 N=5120 K=1280, bias+GELU epilogue)",
          "gemm-qkv": "gemm_bf16_tcgen05 (QKV: M=96000 N=3840 K=1280, bias epilogue)",
-         "gemm-o": "gemm_bf16_tcgen05 (out-proj: M=96000 N=1280 K=1280, bias+residual f32 epilogue)"}
+         "gemm-o": "gemm_bf16_tcgen05 (out-proj: M=96000 N=1280 K=1280, bias + f16 residual epilogue)"}
 for tag, name in names.items():
     rep = os.path.join(G, f"final_{tag}.ncu-rep")
     if not os.path.exists(rep):

@@ -37,7 +37,7 @@ elif what == "attn":
     torch.cuda.synchronize()
 elif what == "ln":
     rows, d = 96000, 1280
-    x = torch.randn(rows, d, device=dev)
+    x = torch.randn(rows, d, device=dev).half()
     gm, bt = torch.randn(d, device=dev), torch.randn(d, device=dev)
     y = torch.empty((rows, d), device=dev, dtype=torch.bfloat16)
     for _ in range(3):
@@ -50,8 +50,8 @@ else:
     a = torch.randn(M, K, device=dev).bfloat16()
     b = (torch.randn(N, K, device=dev) * 0.05).bfloat16()
     bias = torch.randn(N, device=dev)
-    resid = torch.randn(M, N, device=dev) if epi == 2 else None
-    out = torch.empty((M, N), device=dev, dtype=torch.bfloat16 if epi < 2 else torch.float32)
+    resid = torch.randn(M, N, device=dev).half() if epi == 2 else None
+    out = torch.empty((M, N), device=dev, dtype=torch.bfloat16 if epi < 2 else torch.float16)
     for _ in range(3):
         lib.aries_test_gemm(ctx.handle, epi, M, N, K, ptr(a), ptr(b), ptr(bias), ptr(resid), None, 0, ptr(out), None, 0,
                             0, 0, None)

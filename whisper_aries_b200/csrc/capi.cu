@@ -366,7 +366,7 @@ int aries_encoder_collect_profile(aries_encoder* enc, float* ms, int* counts, in
 
 // ------------------------------------------------------------------------------------------------ test hooks
 int aries_test_gemm(aries_ctx* ctx, int epi, int M, int N, int K, const void* a, const void* b, const float* bias,
-                    const float* resid, const float* pos, int pos_rows, void* out, void* out2, int n_split,
+                    const void* resid, const float* pos, int pos_rows, void* out, void* out2, int n_split,
                     int t_rows, int t_pad, void* stream) {
     int rc = use(ctx);
     if (rc) return rc;
@@ -383,7 +383,7 @@ int aries_test_gemm(aries_ctx* ctx, int epi, int M, int N, int K, const void* a,
     p.M = M; p.N = N; p.K = K; p.a_cols = K;
     p.p_in = M; p.t_valid = M; p.p_out = M; p.row_off = 0; p.ldo = N;
     p.bias = bias; p.resid = resid; p.pos = pos; p.out = out;
-    if (epi == aries::EPI_BIAS_GELU_POS_F32) { p.p_in = pos_rows; p.t_valid = pos_rows; p.p_out = pos_rows; }
+    if (epi == aries::EPI_BIAS_GELU_POS_F16) { p.p_in = pos_rows; p.t_valid = pos_rows; p.p_out = pos_rows; }
     if (epi == aries::EPI_QKV_SPLIT_BF16) {
         p.p_in = t_rows; p.t_valid = t_rows; p.p_out = t_rows; p.ldo = n_split;
         p.out2 = out2; p.n_split = n_split; p.t_pad = t_pad;
@@ -393,7 +393,7 @@ int aries_test_gemm(aries_ctx* ctx, int epi, int M, int N, int K, const void* a,
     return ARIES_OK;
 }
 
-int aries_test_layernorm(aries_ctx* ctx, const float* x, const float* gamma, const float* beta, void* y, int64_t rows,
+int aries_test_layernorm(aries_ctx* ctx, const void* x, const float* gamma, const float* beta, void* y, int64_t rows,
                          int d, void* stream) {
     int rc = use(ctx);
     if (rc) return rc;

@@ -8,8 +8,8 @@ namespace aries {
 enum GemmEpilogue {
     EPI_BIAS_BF16 = 0,          // out bf16 = acc + bias                       (QKV projection)
     EPI_BIAS_GELU_BF16 = 1,     // out bf16 = gelu_erf(acc + bias)             (MLP fc1, conv1)
-    EPI_BIAS_RESID_F32 = 2,     // out f32  = acc + bias + resid               (attention out-proj, MLP fc2)
-    EPI_BIAS_GELU_POS_F32 = 3,  // out f32  = gelu_erf(acc + bias) + pos[t]    (conv2 + positional table)
+    EPI_BIAS_RESID_F16 = 2,     // out f16  = acc + bias + resid (f16)         (attention out-proj, MLP fc2)
+    EPI_BIAS_GELU_POS_F16 = 3,  // out f16  = gelu_erf(acc + bias) + pos[t]    (conv2 + positional table)
     EPI_QKV_SPLIT_BF16 = 4,     // acc + bias: columns < n_split -> out (row-major, ld = ldo, queries | keys);
                                 // columns >= n_split -> out2[b][head][c][t] (values, transposed for attention)
     EPI_COUNT = 5,
@@ -24,8 +24,8 @@ struct GemmParams {
     int row_off;
     int ldo;            // leading dimension of out / resid (elements)
     const float* bias;  // [N]
-    const float* resid; // f32, indexed like out (EPI_BIAS_RESID_F32; may alias out)
-    const float* pos;   // f32 [t_valid, N] (EPI_BIAS_GELU_POS_F32)
+    const void* resid;  // f16, indexed like out (EPI_BIAS_RESID_F16; may alias out): the residual stream
+    const float* pos;   // f32 [t_valid, N] (EPI_BIAS_GELU_POS_F16)
     void* out;
     void* out2;         // EPI_QKV_SPLIT_BF16: bf16 [batch, (N - n_split) / 64, 64, t_pad]
     int n_split;        // EPI_QKV_SPLIT_BF16: first column of the transposed part (2 * d_model)

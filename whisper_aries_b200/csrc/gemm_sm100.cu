@@ -10,8 +10,10 @@
 // The A operand's K index may wrap onto following rows ("a_cols" < K): that is how the encoder's two Conv1d
 // layers (k=3) run as implicit GEMMs over a zero-padded time-major activation without materialising im2col
 // (CT2 ref: layers::WhisperEncoder conv1/conv2).  Epilogues fuse bias, exact-erf GELU,
-// the residual add and the positional-embedding add and remap GEMM rows to output
+// the residual add (f16 residual stream) and the positional-embedding add and remap GEMM rows to output
 // rows so padded rows are never written.
+#include <cuda_fp16.h>
+
 #include <cstdlib>
 
 #include "gemm.h"
@@ -206,15 +208,20 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 
             // residual / position rows do not depend on the accumulator: fetch chunk 0's before waiting for the MMA
             // and chunk c+1's while chunk c is transposed, so their DRAM latency is off the critical path
-            constexpr bool kHasAdd = (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_GELU_POS_F32);
+            constexpr bool kHasAdd = (EPI == EPI_BIAS_RESID_F16 || EPI == EPI_BIAS_GELU_POS_F16);
             float4 add[2][8];
             auto load_add = [&](int c, float4 (&dst)[8]) {
                 const int nc = n0 + c * 32;
-                if (EPI == EPI_BIAS_RESID_F32) {
+                if (EPI == EPI_BIAS_RESID_F16) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        dst[i] = *reinterpret_cast<const float4*>(p.resid + row_off_c[i] + nc + 4 * c4);
-                } else if (EPI == EPI_BIAS_GELU_POS_F32) {
+                    for (int i = 0; i < 8; ++i) {
+                        const uint2 h4 = *reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(p.resid) +
+                                                                         row_off_c[i] + nc + 4 * c4);
+                        const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&h4.x));
+                        const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&h4.y));
+                        dst[i] = make_float4(lo.x, lo.y, hi.x, hi.y);
+                    }
+                } else if (EPI == EPI_BIAS_GELU_POS_F16) {
 #pragma unroll
                     for (int i = 0; i < 8; ++i)
                         dst[i] = __ldg(reinterpret_cast<const float4*>(p.pos + (long long)t_c[i] * p.N + nc) + c4);
@@ -263,7 +270,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 for (int i = 0; i < 8; ++i) {
                     const int rl = 4 * i + sub_row;
                     float4 v = stage[rl * 8 + (c4 ^ (rl & 7))];
-                    if (EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_GELU_POS_F32) {
+                    if (EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_GELU_POS_F16) {
                         const float2 lo = gelu_poly2(__fadd2_rn(make_float2(v.x, v.y), make_float2(bb.x, bb.y)));
                         const float2 hi = gelu_poly2(__fadd2_rn(make_float2(v.z, v.w), make_float2(bb.z, bb.w)));
                         v = make_float4(lo.x, lo.y, hi.x, hi.y);
@@ -278,10 +285,17 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                         q.y = pack_bf16x2(v.z, v.w);
                         if (ok) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off) = q;
                     } else {
-                        if (ok)
-                            *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off) =
-                                make_float4(v.x + add[c & 1][i].x, v.y + add[c & 1][i].y, v.z + add[c & 1][i].z,
-                                            v.w + add[c & 1][i].w);
+                        // residual stream in f16 (as CTranslate2's float16 mode keeps it): saturate instead of inf
+                        const float kMaxHalf = 65504.0f;
+                        const float r0 = fminf(fmaxf(v.x + add[c & 1][i].x, -kMaxHalf), kMaxHalf);
+                        const float r1 = fminf(fmaxf(v.y + add[c & 1][i].y, -kMaxHalf), kMaxHalf);
+                        const float r2 = fminf(fmaxf(v.z + add[c & 1][i].z, -kMaxHalf), kMaxHalf);
+                        const float r3 = fminf(fmaxf(v.w + add[c & 1][i].w, -kMaxHalf), kMaxHalf);
+                        const __half2 lo = __floats2half2_rn(r0, r1), hi = __floats2half2_rn(r2, r3);
+                        uint2 q;
+                        q.x = *reinterpret_cast<const unsigned*>(&lo);
+                        q.y = *reinterpret_cast<const unsigned*>(&hi);
+                        if (ok) *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.out) + off) = q;
                     }
                 }
                 __syncwarp();
@@ -348,8 +362,8 @@ cudaError_t launch_bn(int epi, const CUtensorMap& ta, const CUtensorMap& tb, con
     switch (epi) {
         case EPI_BIAS_BF16: return launch_one<BN, EPI_BIAS_BF16>(ta, tb, p, sm_count, stream);
         case EPI_BIAS_GELU_BF16: return launch_one<BN, EPI_BIAS_GELU_BF16>(ta, tb, p, sm_count, stream);
-        case EPI_BIAS_RESID_F32: return launch_one<BN, EPI_BIAS_RESID_F32>(ta, tb, p, sm_count, stream);
-        case EPI_BIAS_GELU_POS_F32: return launch_one<BN, EPI_BIAS_GELU_POS_F32>(ta, tb, p, sm_count, stream);
+        case EPI_BIAS_RESID_F16: return launch_one<BN, EPI_BIAS_RESID_F16>(ta, tb, p, sm_count, stream);
+        case EPI_BIAS_GELU_POS_F16: return launch_one<BN, EPI_BIAS_GELU_POS_F16>(ta, tb, p, sm_count, stream);
         case EPI_QKV_SPLIT_BF16: return launch_one<BN, EPI_QKV_SPLIT_BF16>(ta, tb, p, sm_count, stream);
     }
     return cudaErrorInvalidValue;
@@ -374,9 +388,9 @@ cudaError_t set_smem_bn() {
     cudaError_t e;
     if ((e = set_smem<BN, EPI_BIAS_BF16>()) != cudaSuccess) return e;
     if ((e = set_smem<BN, EPI_BIAS_GELU_BF16>()) != cudaSuccess) return e;
-    if ((e = set_smem<BN, EPI_BIAS_RESID_F32>()) != cudaSuccess) return e;
+    if ((e = set_smem<BN, EPI_BIAS_RESID_F16>()) != cudaSuccess) return e;
     if ((e = set_smem<BN, EPI_QKV_SPLIT_BF16>()) != cudaSuccess) return e;
-    return set_smem<BN, EPI_BIAS_GELU_POS_F32>();
+    return set_smem<BN, EPI_BIAS_GELU_POS_F16>();
 }
 }  // namespace
 

@@ -1,7 +1,8 @@
-// K4: LayerNorm over the f32 residual stream, bf16 out (the A operand of the next GEMM, or the encoder output).
-// One warp per row; the row stays in registers between the mean, variance and normalise passes, so HBM sees one
-// f32 read and one bf16 write per element.  (CT2 ops::LayerNorm; eps 1e-5.)
+// K4: LayerNorm over the f16 residual stream, bf16 out (the A operand of the next GEMM, or the encoder output).
+// One warp per row; the row stays in registers (as f32) between the mean, variance and normalise passes, so HBM sees
+// one f16 read and one bf16 write per element; statistics are f32.  (CT2 ops::LayerNorm; eps 1e-5.)
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "layernorm.h"
 
@@ -12,7 +13,7 @@ namespace {
 constexpr int kWarpsPerBlock = 8;
 
 template <int NV>   // NV float4 per lane: d = 128 * NV
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) layernorm_kernel(const float* __restrict__ x,
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) layernorm_kernel(const __half* __restrict__ x,
                                                                         const float* __restrict__ gamma,
                                                                         const float* __restrict__ beta,
                                                                         __nv_bfloat16* __restrict__ y, long long rows,
@@ -21,10 +22,15 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) layernorm_kernel(const fl
     const long long row = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     if (row >= rows) return;
     constexpr int d = NV * 128;
-    const float4* xr = reinterpret_cast<const float4*>(x + row * d);
+    const uint2* xr = reinterpret_cast<const uint2*>(x + row * d);
     float4 v[NV];
 #pragma unroll
-    for (int j = 0; j < NV; ++j) v[j] = __ldcs(xr + lane + 32 * j);
+    for (int j = 0; j < NV; ++j) {
+        const uint2 h4 = __ldcs(xr + lane + 32 * j);
+        const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&h4.x));
+        const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&h4.y));
+        v[j] = make_float4(lo.x, lo.y, hi.x, hi.y);
+    }
     float s = 0.0f;
 #pragma unroll
     for (int j = 0; j < NV; ++j) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
@@ -59,7 +65,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) layernorm_kernel(const fl
 }
 
 template <int NV>
-cudaError_t launch(const float* x, const float* g, const float* b, void* y, long long rows, float eps,
+cudaError_t launch(const __half* x, const float* g, const float* b, void* y, long long rows, float eps,
                    cudaStream_t stream) {
     const long long blocks = (rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
     layernorm_kernel<NV><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, stream>>>(x, g, b,
@@ -70,10 +76,11 @@ cudaError_t launch(const float* x, const float* g, const float* b, void* y, long
 
 }  // namespace
 
-cudaError_t layernorm_launch(const float* x, const float* gamma, const float* beta, void* y, long long rows, int d,
+cudaError_t layernorm_launch(const void* x_f16, const float* gamma, const float* beta, void* y, long long rows, int d,
                              float eps, cudaStream_t stream) {
     if (rows <= 0) return cudaSuccess;
     if (d % 128 != 0) return cudaErrorInvalidValue;
+    const __half* x = reinterpret_cast<const __half*>(x_f16);
     switch (d / 128) {
         case 1: return launch<1>(x, gamma, beta, y, rows, eps, stream);
         case 2: return launch<2>(x, gamma, beta, y, rows, eps, stream);

@@ -4,9 +4,9 @@
 
 namespace aries {
 
-// y[r, :] = (x[r, :] - mean) * rsqrt(var + eps) * gamma + beta;  x f32 [rows, d], y bf16 [rows, d]; d % 128 == 0,
+// y[r, :] = (x[r, :] - mean) * rsqrt(var + eps) * gamma + beta;  x f16 [rows, d] (the residual stream), y bf16 [rows, d]; d % 128 == 0,
 // d <= 2048.  (CT2 ops::LayerNorm, eps 1e-5)
-cudaError_t layernorm_launch(const float* x, const float* gamma, const float* beta, void* y_bf16, long long rows,
+cudaError_t layernorm_launch(const void* x_f16, const float* gamma, const float* beta, void* y_bf16, long long rows,
                              int d, float eps, cudaStream_t stream);
 
 }  // namespace aries
