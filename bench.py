@@ -90,8 +90,10 @@ class ClockSampler:
                 "samples": len(s)}
 
 
-def cpu_reference_step(n_windows: int, model: str, seed0: int = 0):
-    """The reference algorithm on the host cores: oracle log-mel (numpy) + oracle encoder (torch fp32, all threads).
+def cpu_reference_step(n_windows: int, model: str, seed0: int = 0, int8: bool = True):
+    """The reference algorithm on the host cores: oracle log-mel (numpy) + oracle encoder (torch, all threads) with,
+    by default, dynamic-int8 Linear layers -- the nearest stand-in for the reference's faster-whisper
+    ``compute_type="int8"`` CPU configuration (ref: final_optimized_transcriber.py:205) -- or plain fp32.
     This is the ONLY place bench.py executes oracle/ code, and only as the thing timed for the CPU baseline."""
     import numpy as np
     import torch
@@ -101,11 +103,16 @@ def cpu_reference_step(n_windows: int, model: str, seed0: int = 0):
     if w is None:
         w = {k: torch.from_numpy(v) for k, v in osynth.encoder_weights(shape, 1234).items()}
         cpu_reference_step.cache[model] = w
+    q = None
+    if int8:
+        q = cpu_reference_step.cache.get(model + "/int8")
+        if q is None:
+            q = cpu_reference_step.cache[model + "/int8"] = oenc.build_int8_linears(w, shape)
     pcm = osynth.batch_signals(n_windows, seed0)
     t0 = time.perf_counter()
     feats = np.stack([omel.log_mel_window(x, shape.n_mels) for x in pcm])
     t1 = time.perf_counter()
-    out = oenc.encoder_forward(feats, w, shape)
+    out = oenc.encoder_forward(feats, w, shape, int8_linears=q)
     t2 = time.perf_counter()
     return {"mel_s": t1 - t0, "enc_s": t2 - t1, "total_s": t2 - t0, "checksum": float(out.abs().mean())}
 
@@ -143,7 +150,8 @@ def run_reference(args, rank: int, world: int) -> int:
     dt = time.perf_counter() - t0
     value = args.steps * sample_windows * WINDOW_SECONDS / dt
     cores = torch.get_num_threads()
-    sample = (f"{sample_windows} synthetic 30-s windows per step (numpy log-mel + torch fp32 encoder, {args.model} shape, "
+    sample = (f"{sample_windows} synthetic 30-s windows per step (oracle port: numpy log-mel + torch CPU encoder with "
+              f"dynamic-int8 Linear layers as the stand-in for faster-whisper compute_type=int8, {args.model} shape, "
               f"random-init weights); faster-whisper/ctranslate2 importable: {kind == 'reference'}")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -308,10 +316,13 @@ def main() -> int:
         n_sample = 2 if args.model == "large-v3" else 4
         cpu_reference_step(1, args.model)                             # warm the weights / thread pool
         r = cpu_reference_step(n_sample, args.model)
+        r32 = cpu_reference_step(n_sample, args.model, int8=False)
         cpu_baseline = {"value": n_sample * WINDOW_SECONDS / r["total_s"], "unit": UNIT, "cores": _t.get_num_threads(),
                         "kind": "port",
-                        "sample": f"{n_sample} windows of the same workload: numpy log-mel {r['mel_s']:.2f} s + torch fp32 "
-                                  f"encoder {r['enc_s']:.2f} s (oracle port; faster-whisper/ctranslate2 not installable offline)"}
+                        "sample": f"{n_sample} windows of the same workload: numpy log-mel {r['mel_s']:.2f} s + torch CPU "
+                                  f"encoder with dynamic-int8 Linear layers {r['enc_s']:.2f} s (oracle port standing in for "
+                                  f"faster-whisper compute_type=int8; faster-whisper/ctranslate2 not installable offline)",
+                        "fp32_value": n_sample * WINDOW_SECONDS / r32["total_s"]}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

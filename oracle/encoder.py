@@ -33,13 +33,34 @@ def check_features(features: np.ndarray | torch.Tensor, shape: EncoderShape) -> 
             f"but got {tuple(features.shape)}")
 
 
+def build_int8_linears(w: dict, shape: EncoderShape) -> dict:
+    """Dynamic-int8 (per-tensor activation scale, int8 weights, fbgemm / x86 engine) stand-ins for the four Linear
+    layers of every encoder layer -- the closest torch-CPU equivalent of the reference's ``compute_type="int8"``
+    (ref: final_optimized_transcriber.py:205; CT2 quantises the same four GEMMs and keeps everything else f32).
+    Used ONLY by the CPU-baseline legs of bench.py; parity checks always use the f32 path."""
+    import warnings
+    out = {}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for i in range(shape.n_layers):
+            for key in (f"encoder/layer_{i}/self_attention/linear_0", f"encoder/layer_{i}/self_attention/linear_1",
+                        f"encoder/layer_{i}/ffn/linear_0", f"encoder/layer_{i}/ffn/linear_1"):
+                wt, bs = _t(w, key + "/weight"), _t(w, key + "/bias")
+                lin = torch.nn.Linear(wt.shape[1], wt.shape[0])
+                lin.weight.data, lin.bias.data = wt, bs
+                out[key] = torch.ao.quantization.quantize_dynamic(torch.nn.Sequential(lin), {torch.nn.Linear},
+                                                                  dtype=torch.qint8)[0]
+    return out
+
+
 @torch.no_grad()
 def encoder_forward(features, w: dict, shape: EncoderShape, *, return_layers: bool = False,
-                    round_weights_bf16: bool = False):
+                    round_weights_bf16: bool = False, int8_linears: dict | None = None):
     """features f32 [B, n_mels, 3000] -> f32 [B, 1500, d].
 
     ``round_weights_bf16`` rounds weights (not activations) to bf16 first, to separate the error of
     bf16 weight storage from the error of bf16 arithmetic when judging the CUDA path.
+    ``int8_linears`` (from ``build_int8_linears``) swaps the Linear layers for dynamic-int8 ones: CPU baseline only.
     """
     x = features if isinstance(features, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(features))
     x = x.to(torch.float32)
@@ -53,6 +74,11 @@ def encoder_forward(features, w: dict, shape: EncoderShape, *, return_layers: bo
             t = t.to(torch.bfloat16).to(torch.float32)
         return t
 
+    def linear(inp, key):
+        if int8_linears is not None:
+            return int8_linears[key](inp)
+        return F.linear(inp, W(key + "/weight"), W(key + "/bias"))
+
     d, h = shape.d_model, shape.n_heads
     hd = d // h
     x = F.gelu(F.conv1d(x, W("encoder/conv1/weight"), W("encoder/conv1/bias"), stride=1, padding=1))
@@ -65,7 +91,7 @@ def encoder_forward(features, w: dict, shape: EncoderShape, *, return_layers: bo
         p = f"encoder/layer_{i}"
         y = F.layer_norm(x, (d,), W(f"{p}/self_attention/layer_norm/gamma"),
                          W(f"{p}/self_attention/layer_norm/beta"), LN_EPS)
-        qkv = F.linear(y, W(f"{p}/self_attention/linear_0/weight"), W(f"{p}/self_attention/linear_0/bias"))
+        qkv = linear(y, f"{p}/self_attention/linear_0")
         q, k, v = qkv.split(d, dim=-1)
         B = x.shape[0]
         q = q.view(B, T, h, hd).transpose(1, 2) * (hd ** -0.5)
@@ -73,10 +99,10 @@ def encoder_forward(features, w: dict, shape: EncoderShape, *, return_layers: bo
         v = v.view(B, T, h, hd).transpose(1, 2)
         att = torch.softmax(q @ k.transpose(-1, -2), dim=-1)
         ctx = (att @ v).transpose(1, 2).reshape(B, T, d)
-        x = x + F.linear(ctx, W(f"{p}/self_attention/linear_1/weight"), W(f"{p}/self_attention/linear_1/bias"))
+        x = x + linear(ctx, f"{p}/self_attention/linear_1")
         y = F.layer_norm(x, (d,), W(f"{p}/ffn/layer_norm/gamma"), W(f"{p}/ffn/layer_norm/beta"), LN_EPS)
-        y = F.gelu(F.linear(y, W(f"{p}/ffn/linear_0/weight"), W(f"{p}/ffn/linear_0/bias")))
-        x = x + F.linear(y, W(f"{p}/ffn/linear_1/weight"), W(f"{p}/ffn/linear_1/bias"))
+        y = F.gelu(linear(y, f"{p}/ffn/linear_0"))
+        x = x + linear(y, f"{p}/ffn/linear_1")
         if return_layers:
             layers.append(x.clone())
     out = F.layer_norm(x, (d,), W("encoder/layer_norm/gamma"), W("encoder/layer_norm/beta"), LN_EPS)
