@@ -118,3 +118,25 @@ def test_scheduler_with_fake_devices_keeps_order_and_isolates_failures():
     # more devices than windows: trailing shards are empty and succeed
     res = ChunkScheduler([make(i) for i in range(4)]).run(windows[:2], np.zeros((2, 2), np.float32))
     assert [r.n_windows for r in res] == [1, 1, 0, 0] and all(r.success for r in res)
+
+
+def test_reference_chunk_plan_and_zero_copy_windows():
+    """Row f3: the reference's 180 s + 5 s work items (ref: final_optimized_transcriber.py:422-449) as sample ranges,
+    and 30-s windows as views of the caller's buffer."""
+    from whisper_aries_b200 import chunk_windows, plan_reference_chunks
+    sr = 16000
+    n = int(400.5 * sr)                                            # 400.5 s -> ceil(400.5 / 180) = 3 chunks
+    plan = plan_reference_chunks(n)
+    assert plan == [(0, 185 * sr), (180 * sr, 365 * sr), (360 * sr, n)]
+    assert plan_reference_chunks(0) == [] and plan_reference_chunks(10 * sr) == [(0, 10 * sr)]
+    with pytest.raises(ValueError):
+        plan_reference_chunks(n, chunk_length_s=0)
+    pcm = np.arange(n, dtype=np.float32)
+    w = chunk_windows(pcm, 0, 6 * 480000)
+    assert w.shape == (6, 480000) and np.shares_memory(w, pcm) and w[5, -1] == pcm[6 * 480000 - 1]
+    a, b = plan[0]                                                  # 185 s = 6 full windows + 5 s
+    w = chunk_windows(pcm, a, b)
+    assert w.shape == (7, 480000) and w[6, 5 * sr - 1] == pcm[b - 1] and not w[6, 5 * sr:].any()
+    assert np.array_equal(w[:6].reshape(-1), pcm[: 6 * 480000])
+    assert chunk_windows(pcm, 5, 5).shape == (0, 480000)
+    assert chunk_windows(pcm, 0, 100).shape == (1, 480000)

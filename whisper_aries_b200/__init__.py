@@ -5,8 +5,9 @@ Python host code over a C-ABI CUDA library (include/aries_b200.h).  No CPU fallb
 from . import ct2_model
 from .encoder import WhisperEncoder, WhisperModel
 from .feature_extractor import FeatureExtractor
-from .scheduler import ChunkResult, ChunkScheduler, ChunkWork, partition_windows
+from .scheduler import (ChunkResult, ChunkScheduler, ChunkWork, chunk_windows, partition_windows,
+                        plan_reference_chunks)
 from .synthetic import SHAPES, EncoderShape
 
 __all__ = ["FeatureExtractor", "WhisperEncoder", "WhisperModel", "ChunkScheduler", "ChunkWork", "ChunkResult",
-           "partition_windows", "SHAPES", "EncoderShape", "ct2_model"]
+           "partition_windows", "plan_reference_chunks", "chunk_windows", "SHAPES", "EncoderShape", "ct2_model"]

@@ -12,16 +12,6 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "elect.sync _|p, 0xffffffff;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(pred));
-    return pred != 0;
-}
-
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -86,15 +76,6 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
-__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
-                                            int c2, int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
-        "[%2];" ::"r"(smem_u32(smem_dst)),
-        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
-}
-
 // ---------------------------------------------------------------- TMEM alloc
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot) {   // whole warp
@@ -116,9 +97,6 @@ __host__ __device__ constexpr uint64_t umma_smem_desc_hi(uint32_t lbo_bytes, uin
     return (static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16) |
            (static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (2ull << 61);
 }
-__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint64_t hi_bits) {
-    return hi_bits | static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
-}
 // Instruction descriptor, kind::f16, bf16 x bf16 -> f32.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N, bool a_mn_major, bool b_mn_major) {
     return (1u << 4)            // D format f32
@@ -127,77 +105,12 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N, b
            | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
-// D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread.
-__device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                             uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// D[tmem] (+)= A[tmem] * B[smem]: the A operand (M = 128 rows on lanes 0..127, K-major, two bf16 per 32-bit column) is
-// read from tensor memory -- used by attention to feed P straight from the softmax warps' tcgen05.st.
-__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
-                                             uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// Variants taking the shared-memory descriptors as (low word, high word): the high word is a per-kernel constant and
-// the low word advances by (byte offset >> 4), so the issuing thread spends one integer add per operand per MMA.
-__device__ __forceinline__ void umma_bf16_ss_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
-                                                  uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-        "setp.ne.b32 p, %5, 0;\n\t"
-        "mov.b64 da, {%1, %3};\n\t"
-        "mov.b64 db, {%2, %3};\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(tmem_d),
-        "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_bf16_ts_lohi(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t desc_hi,
-                                                  uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
-        "setp.ne.b32 p, %5, 0;\n\t"
-        "mov.b64 db, {%2, %3};\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}" ::"r"(tmem_d),
-        "r"(tmem_a), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// Warp-convergent issue: EVERY lane of the issuing warp executes these (with identical, warp-uniform operands) and the
-// instruction itself is predicated on elect.sync.  Under an ordinary divergent `if (lane == 0)` ptxas wraps each
-// tcgen05 instruction in a loop over the active lanes (~13 instructions per MMA); attention's MMAs are small enough
-// for that to bound the kernel.
-__device__ __forceinline__ void umma_bf16_ss_elect(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
-                                                   uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t"
-        "elect.sync _|e, 0xffffffff;\n\t"
-        "setp.ne.b32 p, %5, 0;\n\t"
-        "mov.b64 da, {%1, %3};\n\t"
-        "mov.b64 db, {%2, %3};\n\t"
-        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(tmem_d),
-        "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_bf16_ts_elect(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t desc_hi,
-                                                   uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p, e;\n\t.reg .b64 db;\n\t"
-        "elect.sync _|e, 0xffffffff;\n\t"
-        "setp.ne.b32 p, %5, 0;\n\t"
-        "mov.b64 db, {%2, %3};\n\t"
-        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}" ::"r"(tmem_d),
-        "r"(tmem_a), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
+// tcgen05.mma / tcgen05.commit are issued by ONE thread.  Every lane of the issuing warp executes the wrappers below
+// (with identical, warp-uniform operands) and the instruction itself is predicated on elect.sync.  Under an ordinary
+// divergent `if (lane == 0)` ptxas wraps each tcgen05 instruction in a loop over the active lanes (~13 instructions,
+// ~80 issue cycles per MMA), which bounded both the attention kernel (small MMAs) and the GEMM.
+//
+// Arrive on an mbarrier once every previously issued tcgen05.mma of the elected thread has completed.
 __device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
     asm volatile(
         "{\n\t.reg .pred e;\n\t"
@@ -205,8 +118,10 @@ __device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
         "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
         : "memory");
 }
-// Four K = 16 steps of one 64-deep contraction in a single statement (one elect.sync for all of them): the operands
-// advance by 32 bytes (descriptor low word += 2) / 8 TMEM columns per step.  Steps 1..3 always accumulate.
+// Four K = 16 steps of one 64-deep contraction in a single statement (one elect.sync for all of them).  The shared-
+// memory descriptors are passed as (low word, high word): the high word is a per-kernel constant and the low word
+// advances by (byte offset >> 4), i.e. by 2 per 32-byte step; a TMEM A operand advances by 8 columns.  Steps 1..3
+// always accumulate.  D[tmem] (+)= A[smem] * B[smem]:
 __device__ __forceinline__ void umma_bf16_ss_x4_elect(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
                                                       uint32_t idesc, uint32_t accumulate_first) {
     asm volatile(
@@ -225,6 +140,8 @@ __device__ __forceinline__ void umma_bf16_ss_x4_elect(uint32_t tmem_d, uint32_t 
         "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate_first)
         : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (M = 128 rows on lanes 0..127, K-major, two bf16 per 32-bit column) is
+// read from tensor memory -- attention feeds P straight from the softmax warps' tcgen05.st.
 __device__ __forceinline__ void umma_bf16_ts_x4_elect(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo,
                                                       uint32_t desc_hi, uint32_t idesc, uint32_t accumulate_first) {
     asm volatile(
@@ -241,11 +158,6 @@ __device__ __forceinline__ void umma_bf16_ts_x4_elect(uint32_t tmem_d, uint32_t 
         "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a], db, %4, 1;\n\t}" ::"r"(tmem_d),
         "r"(tmem_a), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate_first)
         : "memory");
-}
-// Arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed.
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
 }
 
 // ---------------------------------------------------------------- CTA pairs (cta_group::2)
@@ -328,9 +240,6 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
         : "r"(taddr)
         : "memory");
 }
-__device__ __forceinline__ void tmem_ld_wait() {
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 // tcgen05.wait::ld that also names the destination registers of the load it completes, so that the compiler cannot
 // schedule a use of r[] above the wait (the load is asynchronous; the registers are only valid after it).
 __device__ __forceinline__ void tmem_ld_wait_on(uint32_t (&r)[32]) {
@@ -386,27 +295,6 @@ __device__ __forceinline__ void tmem_st_wait() {
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
-}
-
-__device__ __forceinline__ float gelu_erf(float x) {
-    return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
-}
-// Exact-erf GELU with erf from Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, far below bf16 resolution): one
-// branch-free path with one MUFU.RCP and one MUFU.EX2 instead of erff's two-range code (~2.5x fewer instructions).
-__device__ __forceinline__ float gelu_fast(float x) {
-    const float z = fabsf(x) * 0.70710678118654752440f;
-    float t;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
-    float poly = fmaf(t, 1.061405429f, -1.453152027f);
-    poly = fmaf(poly, t, 1.421413741f);
-    poly = fmaf(poly, t, -0.284496736f);
-    poly = fmaf(poly, t, 0.254829592f);
-    poly *= t;
-    float e;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
-    const float erf_abs = fmaf(-poly, e, 1.0f);
-    const float hx = 0.5f * x;
-    return fmaf(fabsf(hx), erf_abs, hx);          // 0.5 x (1 + sign(x) erf|.|) = 0.5 x + |0.5 x| erf|.|
 }
 
 // GELU (exact-erf definition) on two values at once, on the FMA pipe only: x * Phi(x) with Phi(x) = 0.5 + xc Q(xc^2),

@@ -71,6 +71,43 @@ def split_into_windows(pcm: np.ndarray, n_samples: int = N_SAMPLES) -> np.ndarra
     return out
 
 
+def plan_reference_chunks(n_samples: int, chunk_length_s: float = 180.0, overlap_s: float = 5.0,
+                          sample_rate: int = 16000) -> list[tuple[int, int]]:
+    """The reference's work items as sample ranges of ONE PCM buffer.
+
+    The reference cuts a file into ``ceil(duration / chunk_length)`` chunks of ``chunk_length + overlap`` seconds and
+    COPIES each into its ``ChunkWork`` (ref: final_optimized_transcriber.py:422-449; ``get_chunk`` -> ``.astype`` copy at
+    :126-135).  Here a chunk is just ``(start_sample, end_sample)`` into the caller's buffer; ``chunk_windows`` below
+    turns it into 30-s window views without copying."""
+    if n_samples <= 0:
+        return []
+    if chunk_length_s <= 0 or overlap_s < 0:
+        raise ValueError("chunk_length_s must be > 0 and overlap_s >= 0")
+    duration = n_samples / sample_rate
+    total = int(np.ceil(duration / chunk_length_s))
+    out = []
+    for chunk_id in range(total):
+        start_sec = chunk_id * chunk_length_s
+        end_sec = min(start_sec + chunk_length_s + overlap_s, duration)
+        a, b = max(0, int(start_sec * sample_rate)), min(n_samples, int(end_sec * sample_rate))
+        out.append((a, b))
+    return out
+
+
+def chunk_windows(pcm: np.ndarray, start: int, stop: int, n_samples: int = N_SAMPLES) -> np.ndarray:
+    """30-s windows ``[k, n_samples]`` of ``pcm[start:stop]``: a strided VIEW of the caller's buffer for the full
+    windows (no copy, so a pinned buffer stays pinned); only a ragged last window is copied into a zero-padded row."""
+    x = np.asarray(pcm).reshape(-1)[start:stop]
+    full, rest = divmod(x.shape[0], n_samples)
+    if rest == 0:
+        return x.reshape(full, n_samples) if full else np.zeros((0, n_samples), x.dtype)
+    tail = np.zeros((1, n_samples), dtype=x.dtype)
+    tail[0, :rest] = x[full * n_samples:]
+    if full == 0:
+        return tail
+    return np.concatenate([x[: full * n_samples].reshape(full, n_samples), tail])      # (copy: ragged input only)
+
+
 # A worker consumes windows [start, stop) of `windows` and writes rows [start, stop) of `out`.
 Worker = Callable[[np.ndarray, int, int, object], None]
 
