@@ -136,6 +136,62 @@ ARIES_API int aries_encoder_last_launches(const aries_encoder* enc);
 ARIES_API int aries_encoder_set_profiling(aries_encoder* enc, int on);
 ARIES_API int aries_encoder_collect_profile(aries_encoder* enc, float* ms, int* counts, int n);
 
+/* ---------------------------------------------------------------------------------------------- decoder (row f1)
+ * Replaces ctranslate2.models.Whisper.generate(encoder_output, prompts, beam_size=1, max_length=448, suppress_blank=True,
+ * suppress_tokens=[...], max_initial_timestamp_index=50, return_scores=True, return_no_speech_prob=True) as faster-whisper
+ * calls it for the reference's decode knobs beam_size=1 / best_of=1 / temperature=0 (final_optimized_transcriber.py:432-441,
+ * reached from model.transcribe at :326): layers::WhisperDecoder + GreedySearch with the logits processors
+ * SuppressTokensBegin, SuppressTokens and ApplyTimestampRules.  Greedy only (the reference never asks for a beam).
+ * The encoder output stays on the GPU: enc_out_dev is what aries_encoder_run / aries_encode_pcm wrote. */
+typedef struct aries_decoder aries_decoder;
+
+typedef struct aries_decoder_cfg {
+    int32_t vocab;        /* 51866 (large-v3) | 51865 */
+    int32_t d_model;      /* multiple of 64 */
+    int32_t n_heads;      /* d_model / 64 */
+    int32_t n_layers;
+    int32_t d_ffn;        /* multiple of 64 */
+    int32_t n_text_ctx;   /* 448 */
+    int32_t n_audio_ctx;  /* 1500 */
+} aries_decoder_cfg;
+
+/* Token ids come from the converted model's tokenizer (the caller owns the tokenizer, as upstream does). */
+typedef struct aries_generate_opts {
+    int32_t max_length;                    /* total positions, prompt included; <= n_text_ctx */
+    int32_t suppress_blank;                /* forbid " " and EOT at the first sampled position */
+    int32_t blank_id;
+    int32_t eot, sot, no_speech, no_timestamps, timestamp_begin;
+    int32_t max_initial_timestamp_index;   /* 50 = 1.0 s */
+    const int32_t* suppress_tokens;        /* ids that are never sampled (upstream's -1 already expanded) */
+    int32_t n_suppress;
+} aries_generate_opts;
+
+/* Weights: CTranslate2 Whisper variables "decoder/embeddings/weight", "decoder/position_encodings/encodings",
+ * "decoder/layer_N/{self_attention,attention,ffn}/...", "decoder/layer_norm/{gamma,beta}" and optionally
+ * "decoder/projection/weight" (tied to the embedding when absent); host f32, copied (as bf16 / f32) at create.
+ * max_batch (<= 128) sizes the self-attention cache: n_layers * max_batch * n_text_ctx * d_model * 4 bytes. */
+ARIES_API int aries_decoder_create(aries_ctx* ctx, const aries_decoder_cfg* cfg, const aries_weight_desc* weights,
+                         int n_weights, int max_batch, aries_decoder** out);
+ARIES_API int aries_decoder_destroy(aries_decoder* dec);
+
+/* Whisper.generate for `batch` windows.
+ *   enc_out_dev     device bf16 [batch, n_audio_ctx, d_model]
+ *   prompts         host int32 [batch, prompt_len], e.g. <|startoftranscript|> <|en|> <|transcribe|>; the timestamp
+ *                   rules apply to a sequence unless its prompt contains <|notimestamps|>
+ *   tokens_out      host int32 [batch, max_length]: the prompt, the sampled ids, then EOT
+ *   lengths         host int32 [batch]: sampled ids before EOT (upstream's sequences_ids[0] length)   (may be NULL)
+ *   scores          host f32 [batch]: sum of the log-probabilities of the sampled ids                  (may be NULL)
+ *   no_speech_prob  host f32 [batch]: P(<|nospeech|>) at the <|startoftranscript|> position            (may be NULL)
+ * Ordered after the work already queued on `stream`; returns after the results are in host memory. */
+ARIES_API int aries_decoder_generate(aries_decoder* dec, const void* enc_out_dev, int batch, const int32_t* prompts,
+                           int prompt_len, const aries_generate_opts* opts, int32_t* tokens_out, int32_t* lengths,
+                           float* scores, float* no_speech_prob, void* stream);
+
+/* Timing of the last aries_decoder_generate (CUDA events on the decoding stream), n >= 5:
+ * out[0] cross-attention K|V projection ms, out[1] decode loop ms, out[2] steps run, out[3] kernels per step,
+ * out[4] kernels of the K|V projection phase. */
+ARIES_API int aries_decoder_last_stats(const aries_decoder* dec, float* out, int n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -31,6 +31,30 @@ ARIES_API int aries_test_attention(aries_ctx* ctx, const void* qk, const void* v
 /* Timeline of the ARIES_ATTN_TRACE=1 attention variant: [16 CTAs][11 warps][160 clock64 stamps] (0 = unused). */
 ARIES_API int aries_test_attention_trace(aries_ctx* ctx, unsigned long long* host, size_t count);
 
+/* ---- decode-step kernels (row f1) ---- */
+/* out[b, n] = epilogue(sum_k x[b, k] w[n, k]); x bf16 [round_up(B, 16), K] (pad rows zero), w bf16 [N, K];
+ *   epi 0: out bf16 = acc + bias     epi 1: out bf16 = gelu(acc + bias)
+ *   epi 2: out f16 += acc + bias     epi 3: out f32 = acc (N need not be a multiple of 128)
+ * K % 64 == 0, B <= 128; splits = 0 picks the production split, else 1..8 (cluster size). */
+ARIES_API int aries_test_skinny_gemm(aries_ctx* ctx, int epi, int B, int N, int K, const void* x, const void* w,
+                           const float* bias, void* out, int ldo, int splits, void* stream);
+
+/* Single-query attention over a bf16 key/value cache (see csrc/skinny.h DecAttnParams). n_keys_fixed == 0: self-attention
+ * (appends new_k / new_v at position *step_dev, attends to 0 .. *step_dev); otherwise cross-attention over n_keys_fixed
+ * keys with `splits` CTAs per (sequence, head). */
+ARIES_API int aries_test_decode_attention(aries_ctx* ctx, const void* q, int q_ld, void* k, void* v, int64_t kv_rows, int kv_ld,
+                                const void* new_k, const void* new_v, int new_ld, const int* step_dev, int n_keys_fixed,
+                                int batch, int heads, void* out, int out_ld, int splits, void* stream);
+
+/* aries_decoder_generate with teacher forcing: the first n_forced sampled positions take forced[b, i] (host int32
+ * [batch, n_forced]) instead of the argmax; argmax_out (host int32 [batch, max_length], -1 where nothing was sampled)
+ * receives what the argmax was; logits_out (host f32 [max_length - 1, batch, vocab], may be NULL) the raw logits of
+ * every step (disables the CUDA graph). */
+ARIES_API int aries_test_decoder_generate(aries_decoder* dec, const void* enc_out_dev, int batch, const int32_t* prompts,
+                                int prompt_len, const aries_generate_opts* opts, const int32_t* forced, int n_forced,
+                                int32_t* tokens_out, int32_t* argmax_out, float* logits_out, float* scores,
+                                float* no_speech_prob, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -65,7 +65,126 @@ def hf_encoder(shape: synth.EncoderShape, w: dict):
     return enc
 
 
+def hf_decoder(shape: synth.DecoderShape, w: dict):
+    """HF transformers WhisperDecoder carrying the oracle's weights (CT2 variable names -> HF parameter names)."""
+    from transformers import WhisperConfig
+    from transformers.models.whisper.modeling_whisper import WhisperDecoder
+    cfg = WhisperConfig(vocab_size=shape.vocab, d_model=shape.d_model, decoder_layers=shape.n_layers,
+                        decoder_attention_heads=shape.n_heads, decoder_ffn_dim=shape.d_ffn,
+                        max_target_positions=shape.n_text_ctx, pad_token_id=0, bos_token_id=1, eos_token_id=2,
+                        decoder_start_token_id=1)
+    hf = WhisperDecoder(cfg).eval()
+    sd = hf.state_dict()
+    d = shape.d_model
+
+    def T(k):
+        return torch.from_numpy(w[k])
+
+    sd["embed_tokens.weight"] = T("decoder/embeddings/weight")
+    sd["embed_positions.weight"] = T("decoder/position_encodings/encodings")
+    for i in range(shape.n_layers):
+        p, q = f"decoder/layer_{i}", f"layers.{i}"
+        W, b = T(f"{p}/self_attention/linear_0/weight"), T(f"{p}/self_attention/linear_0/bias")
+        sd[f"{q}.self_attn.q_proj.weight"], sd[f"{q}.self_attn.q_proj.bias"] = W[:d], b[:d]
+        sd[f"{q}.self_attn.k_proj.weight"] = W[d:2 * d]
+        sd[f"{q}.self_attn.v_proj.weight"], sd[f"{q}.self_attn.v_proj.bias"] = W[2 * d:], b[2 * d:]
+        sd[f"{q}.self_attn.out_proj.weight"] = T(f"{p}/self_attention/linear_1/weight")
+        sd[f"{q}.self_attn.out_proj.bias"] = T(f"{p}/self_attention/linear_1/bias")
+        sd[f"{q}.self_attn_layer_norm.weight"] = T(f"{p}/self_attention/layer_norm/gamma")
+        sd[f"{q}.self_attn_layer_norm.bias"] = T(f"{p}/self_attention/layer_norm/beta")
+        sd[f"{q}.encoder_attn.q_proj.weight"] = T(f"{p}/attention/linear_0/weight")
+        sd[f"{q}.encoder_attn.q_proj.bias"] = T(f"{p}/attention/linear_0/bias")
+        W, b = T(f"{p}/attention/linear_1/weight"), T(f"{p}/attention/linear_1/bias")
+        sd[f"{q}.encoder_attn.k_proj.weight"] = W[:d]
+        sd[f"{q}.encoder_attn.v_proj.weight"], sd[f"{q}.encoder_attn.v_proj.bias"] = W[d:], b[d:]
+        sd[f"{q}.encoder_attn.out_proj.weight"] = T(f"{p}/attention/linear_2/weight")
+        sd[f"{q}.encoder_attn.out_proj.bias"] = T(f"{p}/attention/linear_2/bias")
+        sd[f"{q}.encoder_attn_layer_norm.weight"] = T(f"{p}/attention/layer_norm/gamma")
+        sd[f"{q}.encoder_attn_layer_norm.bias"] = T(f"{p}/attention/layer_norm/beta")
+        sd[f"{q}.final_layer_norm.weight"] = T(f"{p}/ffn/layer_norm/gamma")
+        sd[f"{q}.final_layer_norm.bias"] = T(f"{p}/ffn/layer_norm/beta")
+        sd[f"{q}.fc1.weight"], sd[f"{q}.fc1.bias"] = T(f"{p}/ffn/linear_0/weight"), T(f"{p}/ffn/linear_0/bias")
+        sd[f"{q}.fc2.weight"], sd[f"{q}.fc2.bias"] = T(f"{p}/ffn/linear_1/weight"), T(f"{p}/ffn/linear_1/bias")
+    sd["layer_norm.weight"], sd["layer_norm.bias"] = T("decoder/layer_norm/gamma"), T("decoder/layer_norm/beta")
+    hf.load_state_dict(sd)
+    return hf
+
+
+def decoder_golden() -> None:
+    """tests/golden/decoder_golden.npz (row f1): (a) logits of the oracle decoder and of HF's WhisperDecoder with the
+    same weights; (b) the logits-rule masks of the oracle and of HF's WhisperTimeStampLogitsProcessor on random logits
+    and token histories; (c) the oracle's greedy ids / decision margins for the seeds the GPU tests use."""
+    from transformers.generation.logits_process import WhisperTimeStampLogitsProcessor
+    from . import whisper_decoder as wd
+    out: dict[str, np.ndarray] = {}
+    shape = synth.DEC_SHAPES["micro"]
+    tok = synth.WhisperTokens.for_vocab(shape.vocab)
+    for tied in (False, True):
+        w = synth.decoder_weights(shape, 4321, tied=tied)
+        g = torch.Generator().manual_seed(5)
+        enc = torch.randn(2, shape.n_audio_ctx, shape.d_model, generator=g)
+        toks = torch.randint(0, shape.vocab, (2, 12), generator=g)
+        lg = wd.Decoder(w, shape).logits(toks, enc)
+        with torch.no_grad():
+            h = hf_decoder(shape, w)(input_ids=toks, encoder_hidden_states=enc).last_hidden_state
+            lg_hf = h @ torch.from_numpy(w.get("decoder/projection/weight", w["decoder/embeddings/weight"])).T
+        err = float((lg - lg_hf).abs().max())
+        print("decoder logits oracle vs HF (tied=%s): max abs %.2e of scale %.2f" % (tied, err, float(lg.abs().max())))
+        assert err < 5e-5
+        key = "tied" if tied else "untied"
+        out[f"logits_{key}_tokens"] = toks.numpy()
+        out[f"logits_{key}_oracle"] = lg[:, :, ::7].numpy()
+        out[f"logits_{key}_hf"] = lg_hf[:, :, ::7].numpy()
+
+    class GC:
+        pass
+    gc = GC()
+    gc.eos_token_id, gc.no_timestamps_token_id, gc.max_initial_timestamp_index = tok.eot, tok.no_timestamps, 50
+    P = 3
+    proc = WhisperTimeStampLogitsProcessor(gc, begin_index=P)
+    rng = np.random.default_rng(0)
+    opts = wd.GenerateOptions(suppress_blank=False)
+    hist, logit_rows, masks = [], [], []
+    for _ in range(80):
+        seq = [tok.sot, tok.first_lang, tok.transcribe]
+        for _ in range(int(rng.integers(0, 8))):
+            seq.append(int(rng.integers(tok.timestamp_begin, shape.vocab)) if rng.random() < 0.4
+                       else int(rng.integers(0, tok.eot)))
+        logits = (rng.standard_normal(shape.vocab) * 3).astype(np.float32)
+        if rng.random() < 0.5:
+            logits[tok.timestamp_begin:] += 2.0
+        logits = logits.astype(np.float16).astype(np.float32)          # stored as f16 to keep the fixture small
+        mine, _ = wd.apply_rules(logits, seq, P, tok, opts, True)
+        theirs = proc(torch.tensor([seq]), torch.tensor(logits[None]).clone())[0].numpy()
+        assert (np.isneginf(mine) == np.isneginf(theirs)).all(), seq
+        hist.append(seq + [-1] * (12 - len(seq)))
+        logit_rows.append(logits)
+        masks.append(np.packbits(np.isneginf(theirs)))
+    out["rules_histories"], out["rules_hf_masks"] = np.array(hist), np.array(masks)
+    out["rules_logits"] = np.array(logit_rows).astype(np.float16)
+
+    for name, batch, timestamps, seed, tied in (("micro", 2, True, 32, False), ("micro", 2, False, 23, False),
+                                                ("mini", 2, True, 20, False), ("micro", 3, False, 4321, True)):
+        shp = synth.DEC_SHAPES[name]
+        tk = synth.WhisperTokens.for_vocab(shp.vocab)
+        dec = wd.Decoder(synth.decoder_weights(shp, seed, tied=tied), shp, round_weights_bf16=True)
+        g = torch.Generator().manual_seed(seed + batch)
+        enc = torch.randn(batch, shp.n_audio_ctx, shp.d_model, generator=g).bfloat16()
+        prompt = [tk.sot, tk.first_lang + 1, tk.transcribe] + ([] if timestamps else [tk.no_timestamps])
+        ref = wd.generate(dec, enc.float(), [prompt] * batch, tk, wd.GenerateOptions(max_length=len(prompt) + 28))
+        key = f"greedy_{name}_{seed}"
+        out[key + "_ids"] = np.array([r["sequences_ids"] + [-1] * (28 - len(r["sequences_ids"])) for r in ref])
+        out[key + "_margins"] = np.array([r["margins"] + [0.0] * (28 - len(r["margins"])) for r in ref], dtype=np.float32)
+        out[key + "_score"] = np.array([r["score"] for r in ref], dtype=np.float32)
+        out[key + "_nsp"] = np.array([r["no_speech_prob"] for r in ref], dtype=np.float32)
+        print(key, [r["sequences_ids"][:6] for r in ref])
+    np.savez_compressed(os.path.join(GOLDEN, "decoder_golden.npz"), **out)
+
+
 def main() -> int:
+    if len(sys.argv) > 1 and sys.argv[1] == "decoder":
+        decoder_golden()
+        return 0
     os.makedirs(GOLDEN, exist_ok=True)
     from transformers import WhisperFeatureExtractor
 
@@ -108,6 +227,7 @@ def main() -> int:
         enc[f"{shape_name}_probe_tokens"] = toks.numpy()
         probe_tokens[shape_name] = margin
     np.savez_compressed(os.path.join(GOLDEN, "encoder_golden.npz"), **enc)
+    decoder_golden()
     for f in os.listdir(GOLDEN):
         print(f, os.path.getsize(os.path.join(GOLDEN, f)))
     return 0

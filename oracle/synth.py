@@ -128,3 +128,110 @@ def encoder_weights(shape: EncoderShape, seed: int = 1234) -> dict[str, np.ndarr
     w["encoder/layer_norm/gamma"] = (1.0 + nrm(d)).astype(np.float32)
     w["encoder/layer_norm/beta"] = nrm(d)
     return w
+
+
+# ---------------------------------------------------------------------------------------------- decoder (row f1)
+@dataclass(frozen=True)
+class DecoderShape:
+    """Text-decoder dims of a Whisper size (OpenAI dims; vocab 51866 for large-v3, 51865 for the other multilingual sizes)."""
+    name: str
+    vocab: int
+    d_model: int
+    n_heads: int
+    n_layers: int
+    d_ffn: int
+    n_text_ctx: int = 448
+    n_audio_ctx: int = 1500
+
+
+@dataclass(frozen=True)
+class WhisperTokens:
+    """Special-token ids the decoding rules need (tokenizer.json of the converted model; large-v3 values by default)."""
+    eot: int = 50257
+    sot: int = 50258
+    transcribe: int = 50360
+    translate: int = 50359
+    sot_lm: int = 50361
+    sot_prev: int = 50362
+    no_speech: int = 50363
+    no_timestamps: int = 50364
+    timestamp_begin: int = 50365
+    blank: int = 220          # " "
+    first_lang: int = 50259
+
+    @classmethod
+    def for_vocab(cls, vocab: int) -> "WhisperTokens":
+        if vocab == 51866:
+            return cls()
+        if vocab == 51865:      # multilingual sizes before large-v3: one language token fewer
+            return cls(50257, 50258, 50359, 50358, 50360, 50361, 50362, 50363, 50364, 220, 50259)
+        # synthetic vocabularies (tests): the last 128 ids are the special block, timestamps take what follows
+        b = vocab - 128
+        return cls(b, b + 1, b + 5, b + 4, b + 6, b + 7, b + 8, b + 9, b + 10, 7, b + 2)
+
+
+DEC_SHAPES = {
+    "tiny": DecoderShape("tiny", 51865, 384, 6, 4, 1536),
+    "medium": DecoderShape("medium", 51865, 1024, 16, 24, 4096),
+    "large-v3": DecoderShape("large-v3", 51866, 1280, 20, 32, 5120),
+    # not Whisper sizes: small shapes every kernel tiling accepts (vocab deliberately not a multiple of 128)
+    "micro": DecoderShape("micro", 1000, 128, 2, 2, 512),
+    "mini": DecoderShape("mini", 3000, 384, 6, 3, 1536),
+}
+
+
+def decoder_weights(shape: DecoderShape, seed: int = 4321, logit_scale: float = 0.15, tied: bool = False,
+                    cross_gain: float = 6.0) -> dict[str, np.ndarray]:
+    """Random-init decoder weights under CTranslate2's Whisper variable names [unverified offline] (f32 numpy).
+
+    Matrices ~ N(0, 0.02^2) except the token embedding (= tied output projection) ~ N(0, logit_scale^2) so that
+    greedy top-1/top-2 margins are well above bf16 noise; biases ~ N(0, 0.02^2) with the key slices zero (Whisper's
+    k_proj has no bias); LayerNorm gamma = 1 + N(0, 0.02^2); learned positions ~ N(0, 0.02^2).
+
+    Real Whisper ties the output projection to the embedding; with RANDOM weights a tied head just repeats the previous
+    token and ignores the audio, which would make "identical token ids" a vacuous test.  So by default an untied
+    ``decoder/projection/weight`` is added and the cross-attention path is amplified (``cross_gain``) so that the
+    decoded ids are diverse and depend on the encoder output; ``tied=True`` gives the Whisper layout."""
+    rng = np.random.default_rng(seed)
+    d, f = shape.d_model, shape.d_ffn
+
+    def nrm(*s, sc=0.02):
+        return (sc * rng.standard_normal(s)).astype(np.float32)
+
+    w: dict[str, np.ndarray] = {}
+    w["decoder/embeddings/weight"] = nrm(shape.vocab, d, sc=logit_scale)
+    w["decoder/position_encodings/encodings"] = nrm(shape.n_text_ctx, d)
+    for i in range(shape.n_layers):
+        p = f"decoder/layer_{i}"
+        for blk in ("self_attention", "attention", "ffn"):
+            w[f"{p}/{blk}/layer_norm/gamma"] = (1.0 + nrm(d)).astype(np.float32)
+            w[f"{p}/{blk}/layer_norm/beta"] = nrm(d)
+        w[f"{p}/self_attention/linear_0/weight"] = nrm(3 * d, d, sc=0.05)
+        b = nrm(3 * d)
+        b[d:2 * d] = 0.0
+        w[f"{p}/self_attention/linear_0/bias"] = b
+        w[f"{p}/self_attention/linear_1/weight"] = nrm(d, d, sc=0.05)
+        w[f"{p}/self_attention/linear_1/bias"] = nrm(d)
+        w[f"{p}/attention/linear_0/weight"] = nrm(d, d, sc=0.05)            # cross-attention query
+        w[f"{p}/attention/linear_0/bias"] = nrm(d)
+        w[f"{p}/attention/linear_1/weight"] = nrm(2 * d, d, sc=0.05)        # cross-attention key | value
+        b = nrm(2 * d)
+        b[:d] = 0.0
+        w[f"{p}/attention/linear_1/bias"] = b
+        w[f"{p}/attention/linear_2/weight"] = nrm(d, d, sc=0.05)
+        w[f"{p}/attention/linear_2/bias"] = nrm(d)
+        w[f"{p}/ffn/linear_0/weight"] = nrm(f, d, sc=0.05)
+        w[f"{p}/ffn/linear_0/bias"] = nrm(f)
+        w[f"{p}/ffn/linear_1/weight"] = nrm(d, f, sc=0.03)
+        w[f"{p}/ffn/linear_1/bias"] = nrm(d)
+    w["decoder/layer_norm/gamma"] = (1.0 + nrm(d)).astype(np.float32)
+    w["decoder/layer_norm/beta"] = nrm(d)
+    if not tied:
+        rng2 = np.random.default_rng(seed + 99)
+        w["decoder/projection/weight"] = (logit_scale * rng2.standard_normal((shape.vocab, d))).astype(np.float32)
+        for i in range(shape.n_layers):
+            p = f"decoder/layer_{i}/attention"
+            w[f"{p}/linear_0/weight"] = w[f"{p}/linear_0/weight"] * 2.0
+            w[f"{p}/linear_1/weight"] = w[f"{p}/linear_1/weight"] * 2.0
+            w[f"{p}/linear_2/weight"] = w[f"{p}/linear_2/weight"] * np.float32(cross_gain)
+    return w

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/ but not exported"
     assert names == set(_lib.PROTOTYPES), "ctypes prototypes and the headers disagree"
-    assert lib.aries_abi_version() == 100
+    assert lib.aries_abi_version() == 101
 
 
 def test_no_cpu_fallback_when_no_gpu():

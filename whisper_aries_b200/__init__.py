@@ -3,11 +3,13 @@
 Python host code over a C-ABI CUDA library (include/aries_b200.h).  No CPU fallback: the CUDA library must be built
 (``__graft_entry__.build()``) and a B200 must be present for anything but construction-time host logic."""
 from . import ct2_model
+from .decoder import WhisperDecoder, WhisperGenerationResult
 from .encoder import WhisperEncoder, WhisperModel
 from .feature_extractor import FeatureExtractor
 from .scheduler import (ChunkResult, ChunkScheduler, ChunkWork, chunk_windows, partition_windows,
                         plan_reference_chunks)
-from .synthetic import SHAPES, EncoderShape
+from .synthetic import DEC_SHAPES, SHAPES, DecoderShape, EncoderShape, WhisperTokens
 
 __all__ = ["FeatureExtractor", "WhisperEncoder", "WhisperModel", "ChunkScheduler", "ChunkWork", "ChunkResult",
-           "partition_windows", "plan_reference_chunks", "chunk_windows", "SHAPES", "EncoderShape", "ct2_model"]
+           "partition_windows", "plan_reference_chunks", "chunk_windows", "SHAPES", "EncoderShape", "ct2_model", "WhisperDecoder", "WhisperGenerationResult", "DEC_SHAPES",
+           "DecoderShape", "WhisperTokens"]

@@ -28,6 +28,20 @@ class WeightDesc(ctypes.Structure):
     _fields_ = [("name", c_char_p), ("data", c_void_p), ("ndim", ctypes.c_int32), ("shape", ctypes.c_int64 * 4)]
 
 
+class DecoderCfg(ctypes.Structure):
+    _fields_ = [("vocab", ctypes.c_int32), ("d_model", ctypes.c_int32), ("n_heads", ctypes.c_int32),
+                ("n_layers", ctypes.c_int32), ("d_ffn", ctypes.c_int32), ("n_text_ctx", ctypes.c_int32),
+                ("n_audio_ctx", ctypes.c_int32)]
+
+
+class GenerateOpts(ctypes.Structure):
+    _fields_ = [("max_length", ctypes.c_int32), ("suppress_blank", ctypes.c_int32), ("blank_id", ctypes.c_int32),
+                ("eot", ctypes.c_int32), ("sot", ctypes.c_int32), ("no_speech", ctypes.c_int32),
+                ("no_timestamps", ctypes.c_int32), ("timestamp_begin", ctypes.c_int32),
+                ("max_initial_timestamp_index", ctypes.c_int32), ("suppress_tokens", ctypes.POINTER(ctypes.c_int32)),
+                ("n_suppress", ctypes.c_int32)]
+
+
 # name -> (restype, argtypes); every symbol include/aries_b200.h and include/aries_b200_test.h declare
 PROTOTYPES = {
     "aries_abi_version": (c_int, []),
@@ -53,6 +67,19 @@ PROTOTYPES = {
     "aries_encoder_last_launches": (c_int, [c_void_p]),
     "aries_encoder_set_profiling": (c_int, [c_void_p, c_int]),
     "aries_encoder_collect_profile": (c_int, [c_void_p, c_float_p, ctypes.POINTER(c_int), c_int]),
+    "aries_decoder_create": (c_int, [c_void_p, ctypes.POINTER(DecoderCfg), ctypes.POINTER(WeightDesc), c_int, c_int,
+                                     ctypes.POINTER(c_void_p)]),
+    "aries_decoder_destroy": (c_int, [c_void_p]),
+    "aries_decoder_generate": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, ctypes.POINTER(GenerateOpts), c_void_p,
+                                       c_void_p, c_void_p, c_void_p, c_void_p]),
+    "aries_decoder_last_stats": (c_int, [c_void_p, c_float_p, c_int]),
+    "aries_test_decoder_generate": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, ctypes.POINTER(GenerateOpts),
+                                            c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "aries_test_skinny_gemm": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                       c_int, c_void_p]),
+    "aries_test_decode_attention": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int, c_void_p,
+                                            c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int,
+                                            c_void_p]),
     "aries_test_gemm": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "aries_test_layernorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),

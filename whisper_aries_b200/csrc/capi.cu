@@ -10,11 +10,13 @@
 #include "../../include/aries_b200.h"
 #include "../../include/aries_b200_test.h"
 #include "attention.h"
+#include "decoder.h"
 #include "encoder.h"
 #include "gemm.h"
 #include "layernorm.h"
 #include "logmel.h"
 #include "profiler.h"
+#include "skinny.h"
 
 namespace {
 
@@ -30,7 +32,7 @@ int fail_cuda(const char* what, cudaError_t e) {
     return e == cudaErrorMemoryAllocation ? ARIES_ENOMEM : (e == cudaErrorInvalidValue ? ARIES_EINVAL : ARIES_ECUDA);
 }
 
-constexpr unsigned kMagicCtx = 0xA51E5001u, kMagicMel = 0xA51E5002u, kMagicEnc = 0xA51E5003u;
+constexpr unsigned kMagicCtx = 0xA51E5001u, kMagicMel = 0xA51E5002u, kMagicEnc = 0xA51E5003u, kMagicDec = 0xA51E5004u;
 
 }  // namespace
 
@@ -67,6 +69,12 @@ struct aries_encoder {
     size_t out_cap;
 };
 
+struct aries_decoder {
+    unsigned magic;
+    aries_ctx* ctx;
+    aries::DecoderPlan* plan;
+};
+
 namespace {
 
 int use(const aries_ctx* ctx) {
@@ -81,6 +89,7 @@ int ensure_kernels(aries_ctx* ctx) {
     cudaError_t e;
     if ((e = aries::gemm_init_device()) != cudaSuccess) return fail_cuda("gemm_init_device", e);
     if ((e = aries::attention_init_device()) != cudaSuccess) return fail_cuda("attention_init_device", e);
+    if ((e = aries::skinny_init_device()) != cudaSuccess) return fail_cuda("skinny_init_device", e);
     ctx->kernels_ready = true;
     return ARIES_OK;
 }
@@ -101,7 +110,7 @@ int grow(T** ptr, size_t* cap, size_t bytes) {
 
 extern "C" {
 
-int aries_abi_version(void) { return 100; }
+int aries_abi_version(void) { return 101; }
 
 const char* aries_last_error(void) { return g_error.c_str(); }
 
@@ -364,7 +373,153 @@ int aries_encoder_collect_profile(aries_encoder* enc, float* ms, int* counts, in
     return ARIES_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------ decoder (row f1)
+int aries_decoder_create(aries_ctx* ctx, const aries_decoder_cfg* cfg, const aries_weight_desc* weights, int n_weights,
+                         int max_batch, aries_decoder** out) {
+    if (!out) return fail(ARIES_EINVAL, "out is NULL");
+    *out = nullptr;
+    int rc = use(ctx);
+    if (rc) return rc;
+    if (!cfg || !weights || n_weights <= 0) return fail(ARIES_EINVAL, "aries_decoder_create: NULL argument");
+    std::vector<aries::WeightView> views(n_weights);
+    for (int i = 0; i < n_weights; ++i) {
+        if (!weights[i].name || !weights[i].data || weights[i].ndim < 1 || weights[i].ndim > 4)
+            return fail(ARIES_EINVAL, "aries_decoder_create: malformed weight descriptor");
+        views[i].name = weights[i].name;
+        views[i].data = weights[i].data;
+        views[i].ndim = weights[i].ndim;
+        for (int k = 0; k < 4; ++k) views[i].shape[k] = weights[i].shape[k];
+    }
+    aries::DecoderShapeC c{cfg->vocab, cfg->d_model, cfg->n_heads, cfg->n_layers, cfg->d_ffn, cfg->n_text_ctx, cfg->n_audio_ctx};
+    aries::DecoderPlan* plan = nullptr;
+    std::string why;
+    cudaError_t e = aries::decoder_plan_create(ctx->device, ctx->sm_count, c, views.data(), n_weights, max_batch, &plan, &why);
+    if (e != cudaSuccess) {
+        g_error = "aries_decoder_create: " + why;
+        cudaGetLastError();
+        return e == cudaErrorInvalidValue ? ARIES_EINVAL : (e == cudaErrorMemoryAllocation ? ARIES_ENOMEM : ARIES_ECUDA);
+    }
+    aries_decoder* d = new (std::nothrow) aries_decoder{kMagicDec, ctx, plan};
+    if (!d) {
+        aries::decoder_plan_destroy(plan);
+        return fail(ARIES_ENOMEM, "out of host memory");
+    }
+    *out = d;
+    return ARIES_OK;
+}
+
+int aries_decoder_destroy(aries_decoder* dec) {
+    if (!dec) return ARIES_OK;
+    if (dec->magic != kMagicDec) return fail(ARIES_ESTATE, "invalid decoder handle");
+    use(dec->ctx);
+    aries::decoder_plan_destroy(dec->plan);
+    dec->magic = 0;
+    delete dec;
+    return ARIES_OK;
+}
+
+namespace {
+int generate_impl(aries_decoder* dec, const void* enc_out_dev, int batch, const int32_t* prompts, int prompt_len,
+                  const aries_generate_opts* opts, const int32_t* forced, int n_forced, int32_t* tokens_out,
+                  int32_t* lengths, int32_t* argmax_out, float* logits_out, float* scores, float* no_speech_prob,
+                  void* stream) {
+    if (!dec || dec->magic != kMagicDec) return fail(ARIES_ESTATE, "invalid decoder handle");
+    int rc = use(dec->ctx);
+    if (rc) return rc;
+    if (!opts) return fail(ARIES_EINVAL, "aries_decoder_generate: opts is NULL");
+    aries::GenerateOptsC o{};
+    o.max_length = opts->max_length; o.suppress_blank = opts->suppress_blank; o.blank_id = opts->blank_id;
+    o.eot = opts->eot; o.sot = opts->sot; o.no_speech = opts->no_speech; o.no_timestamps = opts->no_timestamps;
+    o.timestamp_begin = opts->timestamp_begin; o.max_initial_timestamp_index = opts->max_initial_timestamp_index;
+    o.suppress_tokens = opts->suppress_tokens; o.n_suppress = opts->n_suppress;
+    o.forced = forced; o.n_forced = n_forced; o.argmax_out = argmax_out; o.logits_out = logits_out;
+    cudaError_t e = aries::decoder_generate(dec->plan, enc_out_dev, batch, prompts, prompt_len, o, tokens_out, lengths,
+                                            scores, no_speech_prob, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) {
+        g_error = std::string("aries_decoder_generate: ") + aries::decoder_plan_error(dec->plan);
+        cudaGetLastError();
+        return e == cudaErrorInvalidValue ? ARIES_EINVAL : (e == cudaErrorMemoryAllocation ? ARIES_ENOMEM : ARIES_ECUDA);
+    }
+    return ARIES_OK;
+}
+}  // namespace
+
+int aries_decoder_generate(aries_decoder* dec, const void* enc_out_dev, int batch, const int32_t* prompts, int prompt_len,
+                           const aries_generate_opts* opts, int32_t* tokens_out, int32_t* lengths, float* scores,
+                           float* no_speech_prob, void* stream) {
+    return generate_impl(dec, enc_out_dev, batch, prompts, prompt_len, opts, nullptr, 0, tokens_out, lengths, nullptr,
+                         nullptr, scores, no_speech_prob, stream);
+}
+
+int aries_decoder_last_stats(const aries_decoder* dec, float* out, int n) {
+    if (!dec || dec->magic != kMagicDec) return fail(ARIES_ESTATE, "invalid decoder handle");
+    if (!out || n < 5) return fail(ARIES_EINVAL, "aries_decoder_last_stats: need n >= 5");
+    aries::decoder_plan_last_stats(dec->plan, out);
+    return ARIES_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ test hooks
+int aries_test_decoder_generate(aries_decoder* dec, const void* enc_out_dev, int batch, const int32_t* prompts,
+                                int prompt_len, const aries_generate_opts* opts, const int32_t* forced, int n_forced,
+                                int32_t* tokens_out, int32_t* argmax_out, float* logits_out, float* scores,
+                                float* no_speech_prob, void* stream) {
+    return generate_impl(dec, enc_out_dev, batch, prompts, prompt_len, opts, forced, n_forced, tokens_out, nullptr,
+                         argmax_out, logits_out, scores, no_speech_prob, stream);
+}
+
+int aries_test_skinny_gemm(aries_ctx* ctx, int epi, int B, int N, int K, const void* x, const void* w, const float* bias,
+                           void* out, int ldo, int splits, void* stream) {
+    int rc = use(ctx);
+    if (rc) return rc;
+    if ((rc = ensure_kernels(ctx))) return rc;
+    if (B <= 0 || B > 128 || N <= 0 || K <= 0 || K % 64 || epi < 0 || epi >= aries::SK_COUNT)
+        return fail(ARIES_EINVAL, "aries_test_skinny_gemm: bad shape");
+    const int NB = (B + 15) / 16 * 16;
+    CUtensorMap tw, tx;
+    const unsigned long long dw[2] = {(unsigned long long)K, (unsigned long long)N}, st[2] = {2, (unsigned long long)K * 2};
+    const unsigned long long dx[2] = {(unsigned long long)K, (unsigned long long)NB};
+    const unsigned bw[2] = {64, 128}, bx[2] = {64, (unsigned)NB};
+    cudaError_t e;
+    if ((e = aries::make_tmap_bf16(&tw, w, 2, dw, st, bw)) != cudaSuccess) return fail_cuda("tensor map W", e);
+    if ((e = aries::make_tmap_bf16(&tx, x, 2, dx, st, bx)) != cudaSuccess) return fail_cuda("tensor map X", e);
+    aries::SkinnyParams p{};
+    p.B = B; p.NB = NB; p.N = N; p.K = K;
+    p.splits = splits > 0 ? splits : aries::skinny_pick_splits(N, K, ctx->sm_count);
+    p.bias = bias; p.out = out; p.ldo = ldo; p.pdl = 0;
+    if ((e = aries::skinny_launch(epi, tw, tx, p, static_cast<cudaStream_t>(stream))) != cudaSuccess)
+        return fail_cuda("skinny_launch", e);
+    return ARIES_OK;
+}
+
+int aries_test_decode_attention(aries_ctx* ctx, const void* q, int q_ld, void* k, void* v, int64_t kv_rows, int kv_ld,
+                                const void* new_k, const void* new_v, int new_ld, const int* step_dev, int n_keys_fixed,
+                                int batch, int heads, void* out, int out_ld, int splits, void* stream) {
+    int rc = use(ctx);
+    if (rc) return rc;
+    if (batch <= 0 || heads <= 0 || splits < 1 || splits > 8) return fail(ARIES_EINVAL, "aries_test_decode_attention: bad shape");
+    aries::DecAttnParams p{};
+    p.batch = batch; p.heads = heads; p.q = q; p.q_ld = q_ld; p.k = k; p.v = v; p.kv_rows = kv_rows; p.kv_ld = kv_ld;
+    p.new_k = new_k; p.new_v = new_v; p.new_ld = new_ld; p.step = step_dev; p.n_keys_fixed = n_keys_fixed;
+    p.out = out; p.out_ld = out_ld; p.splits = splits; p.pdl = 0;
+    void* scratch = nullptr;
+    cudaError_t e;
+    const size_t part = (size_t)batch * heads * splits * 66 * 4, tick = (size_t)batch * heads * 4;
+    if (splits > 1) {
+        if ((e = cudaMalloc(&scratch, part + tick)) != cudaSuccess) return fail_cuda("cudaMalloc", e);
+        cudaMemsetAsync(scratch, 0, part + tick, static_cast<cudaStream_t>(stream));
+        p.partial = static_cast<float*>(scratch);
+        p.tickets = reinterpret_cast<unsigned*>(static_cast<char*>(scratch) + part);
+    }
+    e = aries::decode_attention_launch(p, static_cast<cudaStream_t>(stream));
+    if (scratch) {
+        cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+        cudaFree(scratch);
+    }
+    if (e != cudaSuccess) return fail_cuda("decode_attention_launch", e);
+    return ARIES_OK;
+}
+
 int aries_test_gemm(aries_ctx* ctx, int epi, int M, int N, int K, const void* a, const void* b, const float* bias,
                     const void* resid, const float* pos, int pos_rows, void* out, void* out2, int n_split,
                     int t_rows, int t_pad, void* stream) {

@@ -1,0 +1,115 @@
+// Host-side interface of the decode-step kernels (row f1): the weight-streaming "skinny" GEMM (skinny_gemm_sm100.cu),
+// single-query attention over a key/value cache (decode_attention.cu) and the token embedding / sampling kernels
+// (decode_misc.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+namespace aries {
+
+// ------------------------------------------------------------------------------------------------ skinny GEMM
+//   out[b, n] = epilogue( sum_k X[b, k] * W[n, k] ),  b < B <= 128 sequences, W [N, K] bf16 K-major (a Linear weight).
+// One decode step multiplies a handful of rows by every weight matrix of the decoder: the op is bound by streaming W
+// from HBM once, so W is the 128-row M operand of tcgen05.mma, the sequences are the N operand (padded to NB = a
+// multiple of 16), K is split over CTAs so that >= 1 CTA per SM pulls bytes, and the last CTA of an n-tile to finish
+// reduces the partial sums in a fixed order (bit-reproducible) and applies the epilogue.
+enum SkinnyEpilogue {
+    SK_BIAS_BF16 = 0,        // out bf16 [B, ldo] = acc + bias
+    SK_BIAS_GELU_BF16 = 1,   // out bf16 = gelu_erf(acc + bias)
+    SK_BIAS_RESID_F16 = 2,   // out f16 = acc + bias + out (in place on the f16 residual stream)
+    SK_LOGITS_F32 = 3,       // out f32 [B, ldo] = acc (no bias; N need not be a multiple of 128)
+    SK_COUNT = 4,
+};
+
+struct SkinnyParams {
+    int B;              // sequences (rows of X that are real)
+    int NB;             // rows of the X tensor map's box = UMMA N: multiple of 16 in [16, 128], >= B
+    int N, K;           // weight rows (output features), depth (K % 64 == 0)
+    int splits;         // K splits (>= 1; every split owns at least one 64-deep block)
+    const float* bias;  // [N] (unused by SK_LOGITS_F32)
+    void* out;
+    int ldo;            // elements between consecutive sequences in out
+    float* partial;     // f32 [splits][NB][n_tiles * 128] (only touched when splits > 1)
+    unsigned* tickets;  // [n_tiles], zero before the first launch; the kernel leaves them zero
+    int pdl;            // launched with programmatic stream serialisation (griddepcontrol in the kernel)
+};
+
+int skinny_pick_splits(int N, int K, int sm_count);
+size_t skinny_partial_bytes(int NB, int N, int splits);
+cudaError_t skinny_init_device();
+// tmap_w: [N, K] bf16, box 64 x 128; tmap_x: [>= NB rows, K] bf16, box 64 x NB.
+cudaError_t skinny_launch(int epi, const CUtensorMap& tmap_w, const CUtensorMap& tmap_x, const SkinnyParams& p,
+                          cudaStream_t stream);
+
+// ------------------------------------------------------------------------------------------------ decode attention
+// One query per (sequence, head), head_dim 64, keys / values bf16 rows of 64 contiguous elements:
+//   out[b, h*64 .. +64] = softmax(q . K^T / 8) V
+// Self-attention (n_keys_fixed == 0): first appends this step's key / value (new_k / new_v rows of the QKV buffer) to
+// the cache at position *step, then attends to positions 0 .. *step.  Cross-attention: n_keys_fixed keys, optionally
+// split over `splits` CTAs whose partial (max, sum, weighted values) are merged by the last one to finish.
+struct DecAttnParams {
+    int batch, heads;
+    const void* q;          // bf16, q of (b, h) at q + b * q_ld + h * 64
+    int q_ld;
+    void* k;                // bf16, key j of (b, h) at k + (b * kv_rows + j) * kv_ld + h * 64
+    void* v;
+    long long kv_rows;
+    int kv_ld;
+    const void* new_k;      // self-attention: this step's key / value of (b, h) at new_k + b * new_ld + h * 64
+    const void* new_v;
+    int new_ld;
+    const int* step;        // device scalar (self-attention)
+    int n_keys_fixed;       // cross-attention: 1500
+    void* out;              // bf16, out + b * out_ld + h * 64
+    int out_ld;
+    int splits;
+    float* partial;         // f32 [batch * heads][splits][66]
+    unsigned* tickets;      // [batch * heads]
+    int pdl;
+};
+cudaError_t decode_attention_launch(const DecAttnParams& p, cudaStream_t stream);
+
+// ------------------------------------------------------------------------------------------------ embedding / sampling
+// x f16 [B, d] = emb[tokens[b, *step]] (bf16 table, tied with the output projection) + pos[*step] (f32 table)
+cudaError_t decode_embed_launch(const int* tokens, int tokens_ld, const int* step, const void* emb_bf16, const float* pos,
+                                void* x_f16, int batch, int d, int pdl, cudaStream_t stream);
+
+// y bf16 [rows, d] = LayerNorm(x f16 [rows, d]) * gamma + beta (eps 1e-5), griddepcontrol-aware (rows = sequences).
+cudaError_t decode_layernorm_launch(const void* x_f16, const float* gamma, const float* beta, void* y_bf16, int rows, int d,
+                                    int pdl, cudaStream_t stream);
+
+// Device-side mirror of the greedy step of ctranslate2 Whisper.generate (SuppressTokensBegin, SuppressTokens,
+// ApplyTimestampRules, argmax, cumulative log-prob); see oracle/whisper_decoder.py apply_rules for the rules.
+struct SampleParams {
+    int batch, vocab;
+    const float* logits;        // [batch, logits_ld]
+    int logits_ld;
+    int* tokens;                // [batch, tokens_ld]; positions < prompt_len hold the prompt
+    int tokens_ld;
+    int prompt_len;
+    int max_length;             // total positions
+    int* step;                  // device scalar: index of the token the decoder just consumed; incremented here
+    const unsigned* suppress_bits;   // bitmask over the vocabulary (1 = never sampled)
+    int suppress_blank, blank_id;
+    int eot, no_speech, no_timestamps, timestamp_begin;
+    int max_initial_timestamp_index;
+    const int* sot_index;       // [batch] position of <|startoftranscript|> in the prompt
+    const int* use_timestamps;  // [batch] 1 = apply the timestamp rules (prompt has no <|notimestamps|>)
+    int* done;                  // [batch]
+    int* last_timestamp;        // [batch] most recent timestamp token sampled (-1 none)
+    float* score;               // [batch] sum of log-probs of the sampled tokens
+    float* no_speech_prob;      // [batch]
+    int* n_done;                // device scalar: finished sequences
+    unsigned* ticket;           // device scalar, zero before the first launch
+    const int* forced;          // tests: [batch, forced_ld] continuation to force (NULL in production)
+    int forced_ld, n_forced;
+    int* argmax_out;            // tests: [batch, tokens_ld] what the argmax was at each sampled position (or NULL)
+    int pdl;
+};
+cudaError_t decode_sample_launch(const SampleParams& p, cudaStream_t stream);
+
+// griddepcontrol-aware launch helper shared by the decode kernels
+cudaError_t launch_maybe_pdl(const void* func, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, void** args,
+                             bool pdl);
+
+}  // namespace aries

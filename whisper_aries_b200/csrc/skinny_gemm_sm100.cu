@@ -1,0 +1,282 @@
+// Weight-streaming GEMM of the decode step (row f1) for sm_100a: out[b, n] = epilogue(sum_k X[b, k] W[n, k]).
+//
+// A decode step multiplies B <= 128 token rows by every Linear weight of the Whisper decoder (CT2 layers::Dense inside
+// layers::WhisperDecoder, reached from ctranslate2.models.Whisper.generate).  The op is bound by
+// reading W from HBM exactly once, so the roles of the tcgen05 operands are swapped with respect to the encoder GEMM:
+//   * W is the M operand: one CTA owns 128 weight rows (one TMA box of 64 x 128 per 64-deep block, SWIZZLE_128B),
+//   * the token rows are the N operand (NB = batch padded to a multiple of 16, one TMA box of 64 x NB),
+//   * the accumulator is 128 TMEM lanes (output features) x NB columns (sequences).
+// K is split over a thread-block CLUSTER (grid.y = cluster size = splits <= 8) so that 70..300 CTAs stream weights at
+// once; the CTAs of a cluster park their f32 partial tile in their own shared memory and every CTA then reduces and
+// finishes 1/splits of the sequences by reading its peers' tiles through distributed shared memory -- fixed summation
+// order (bit-reproducible), no HBM round trip, no atomics.
+// Programmatic dependent launch: the producer prefetches its first WEIGHT blocks before griddepcontrol.wait (weights
+// are never written during decoding), so weight streaming overlaps the tail of the previous kernel of the step.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "ptx.cuh"
+#include "skinny.h"
+
+namespace aries {
+
+namespace {
+
+constexpr int BMW = 128;            // weight rows per CTA
+constexpr int BK = 64;
+constexpr int kStages = 4;
+constexpr int kWBytes = BMW * BK * 2;
+constexpr int kThreads = 192;       // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+constexpr uint32_t kTmemCols = 128;
+constexpr int kMaxSplits = 8;
+
+__host__ __device__ inline int stage_bytes(int NB) { return kWBytes + NB * BK * 2; }
+inline int smem_bytes(int NB) {
+    const int pipe = kStages * stage_bytes(NB);
+    const int part = NB * BMW * 4;
+    return (pipe > part ? pipe : part) + 256 + 1024;
+}
+
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ float ld_dsmem_f32(uint32_t local_addr, uint32_t rank) {
+    uint32_t remote;
+    float v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(rank));
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
+    return v;
+}
+
+template <int EPI>
+__device__ __forceinline__ void store_one(const SkinnyParams& p, int b, int n, float v) {
+    const size_t at = (size_t)b * p.ldo + n;
+    if (EPI == SK_LOGITS_F32) {
+        reinterpret_cast<float*>(p.out)[at] = v;
+        return;
+    }
+    v += __ldg(p.bias + n);
+    if (EPI == SK_BIAS_GELU_BF16) v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+    if (EPI == SK_BIAS_RESID_F16) {
+        __half* o = reinterpret_cast<__half*>(p.out);
+        v += __half2float(o[at]);
+        o[at] = __float2half_rn(fminf(fmaxf(v, -65504.0f), 65504.0f));
+    } else {
+        reinterpret_cast<__nv_bfloat16*>(p.out)[at] = __float2bfloat16_rn(v);
+    }
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(kThreads)
+skinny_gemm_tcgen05(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
+                    const SkinnyParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+    const int sbytes = stage_bytes(p.NB);
+    const int pipe = kStages * sbytes, part = p.NB * BMW * 4;
+    uint8_t* tail = smem + (pipe > part ? pipe : part);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
+    uint64_t* empty_bar = full_bar + kStages;
+    uint64_t* tfull_bar = empty_bar + kStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * BMW;
+    const int split = blockIdx.y;               // == rank in the cluster (cluster = 1 x splits x 1)
+    const int num_kb = p.K / BK;
+    const int kps = (num_kb + p.splits - 1) / p.splits;
+    const int kb0 = split * kps;
+    const int kb1 = (kb0 + kps < num_kb) ? kb0 + kps : num_kb;
+    const int my_kb = kb1 - kb0;                // >= 1 by construction of `splits`
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmap_w);
+        tma_prefetch_desc(&tmap_x);
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(tfull_bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---------------------------------------------------------------- TMA producer
+            // weights first (independent of the previous kernel), then wait for it, then the activations
+            const int pre = my_kb < kStages ? my_kb : kStages;
+            for (int i = 0; i < pre; ++i) {
+                mbar_expect_tx(&full_bar[i], sbytes);
+                tma_load_2d(smem + i * sbytes, &tmap_w, &full_bar[i], (kb0 + i) * BK, n0);
+            }
+            pdl_wait();
+            pdl_trigger();
+            for (int i = 0; i < pre; ++i)
+                tma_load_2d(smem + i * sbytes + kWBytes, &tmap_x, &full_bar[i], (kb0 + i) * BK, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            if (pre == kStages) phase = 1;          // the ring wrapped once
+            stage = pre % kStages;
+            for (int i = pre; i < my_kb; ++i) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* s = smem + stage * sbytes;
+                mbar_expect_tx(&full_bar[stage], sbytes);
+                tma_load_2d(s, &tmap_w, &full_bar[stage], (kb0 + i) * BK, n0);
+                tma_load_2d(s + kWBytes, &tmap_x, &full_bar[stage], (kb0 + i) * BK, 0);
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+        } else {
+            pdl_wait();
+            pdl_trigger();
+        }
+    } else if (warp == 1) {
+        // -------------------------------------------------------------------- MMA issuer (convergent, elect-predicated)
+        pdl_wait();
+        pdl_trigger();
+        const uint32_t idesc = umma_idesc_bf16(BMW, (uint32_t)p.NB, false, false);
+        constexpr uint64_t desc_hi64 = umma_smem_desc_hi(16, 1024);
+        constexpr uint32_t desc_hi = (uint32_t)(desc_hi64 >> 32);
+        const uint32_t desc_lo0 = (uint32_t)(desc_hi64 & 0xFFFFFFFFu) | ((base >> 4) & 0x3FFF);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int i = 0; i < my_kb; ++i) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t a_lo = desc_lo0 + ((uint32_t)(stage * sbytes) >> 4);
+            umma_bf16_ss_x4_elect(tmem_base, a_lo, a_lo + (kWBytes >> 4), desc_hi, idesc, i != 0);
+            umma_commit_elect(&empty_bar[stage]);
+            if (i == my_kb - 1) umma_commit_elect(tfull_bar);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+    } else {
+        // -------------------------------------------------------------------- epilogue warps: one output feature per thread
+        pdl_wait();
+        pdl_trigger();
+        const int quarter = warp & 3;
+        const int nl = quarter * 32 + lane;
+        const int n = n0 + nl;
+        float* my_part = reinterpret_cast<float*>(smem);
+        mbar_wait(tfull_bar, 0);
+        tc_fence_after();
+        for (int c = 0; c < p.NB / 16; ++c) {
+            uint32_t acc[16];
+            tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(quarter * 32) << 16) + c * 16, acc);
+            tmem_ld_wait_on(acc);
+            if (p.splits == 1) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int b = c * 16 + j;
+                    if (b < p.B && n < p.N) store_one<EPI>(p, b, n, __uint_as_float(acc[j]));
+                }
+            } else {
+                // the pipeline stages are free: every MMA of this CTA has retired (tfull)
+#pragma unroll
+                for (int j = 0; j < 16; ++j) my_part[(c * 16 + j) * BMW + nl] = __uint_as_float(acc[j]);
+            }
+        }
+        tc_fence_before();
+    }
+
+    __syncwarp();
+    if (p.splits > 1) {
+        cluster_sync_all();                         // every CTA's partial tile is in its shared memory
+        if (warp >= 2) {
+            const int quarter = warp & 3;
+            const int nl = quarter * 32 + lane;
+            const int n = n0 + nl;
+            const uint32_t part0 = base;
+            for (int b = split; b < p.B; b += p.splits) {
+                float sum = 0.0f;
+                const uint32_t at = part0 + (uint32_t)(b * BMW + nl) * 4u;
+                for (int s = 0; s < p.splits; ++s) sum += ld_dsmem_f32(at, (uint32_t)s);
+                if (n < p.N) store_one<EPI>(p, b, n, sum);
+            }
+        }
+        cluster_sync_all();                         // peers are done reading this CTA's shared memory
+    } else {
+        __syncthreads();
+    }
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<kTmemCols>(tmem_base);
+    }
+}
+
+template <int EPI>
+cudaError_t launch_epi(const CUtensorMap& tw, const CUtensorMap& tx, const SkinnyParams& p, cudaStream_t stream) {
+    const int n_tiles = (p.N + BMW - 1) / BMW;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(n_tiles, p.splits);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem_bytes(p.NB);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (p.splits > 1) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 1;
+        attr[na].val.clusterDim.y = p.splits;
+        attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (p.pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    return cudaLaunchKernelEx(&cfg, skinny_gemm_tcgen05<EPI>, tw, tx, p);
+}
+
+template <int EPI>
+cudaError_t set_smem() {
+    return cudaFuncSetAttribute(skinny_gemm_tcgen05<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(128));
+}
+
+}  // namespace
+
+int skinny_pick_splits(int N, int K, int sm_count) {
+    const int n_tiles = (N + BMW - 1) / BMW;
+    const int num_kb = K / BK;
+    int want = (2 * sm_count + n_tiles - 1) / n_tiles;           // ~2 CTAs per SM in flight
+    if (want > kMaxSplits) want = kMaxSplits;
+    if (want > num_kb) want = num_kb;
+    if (want < 1) want = 1;
+    const int kps = (num_kb + want - 1) / want;
+    return (num_kb + kps - 1) / kps;                             // every split owns >= 1 block
+}
+
+size_t skinny_partial_bytes(int, int, int) { return 0; }         // partial sums live in distributed shared memory
+
+cudaError_t skinny_init_device() {
+    cudaError_t e;
+    if ((e = set_smem<SK_BIAS_BF16>()) != cudaSuccess) return e;
+    if ((e = set_smem<SK_BIAS_GELU_BF16>()) != cudaSuccess) return e;
+    if ((e = set_smem<SK_BIAS_RESID_F16>()) != cudaSuccess) return e;
+    return set_smem<SK_LOGITS_F32>();
+}
+
+cudaError_t skinny_launch(int epi, const CUtensorMap& tw, const CUtensorMap& tx, const SkinnyParams& p,
+                          cudaStream_t stream) {
+    if (p.K % BK != 0 || p.K <= 0 || p.N <= 0 || p.B <= 0 || p.B > p.NB || p.NB % 16 != 0 || p.NB < 16 || p.NB > 128 ||
+        p.splits < 1 || p.splits > kMaxSplits)
+        return cudaErrorInvalidValue;
+    const int num_kb = p.K / BK, kps = (num_kb + p.splits - 1) / p.splits;
+    if ((p.splits - 1) * kps >= num_kb) return cudaErrorInvalidValue;      // an empty split would hang its cluster
+    switch (epi) {
+        case SK_BIAS_BF16: return launch_epi<SK_BIAS_BF16>(tw, tx, p, stream);
+        case SK_BIAS_GELU_BF16: return launch_epi<SK_BIAS_GELU_BF16>(tw, tx, p, stream);
+        case SK_BIAS_RESID_F16: return launch_epi<SK_BIAS_RESID_F16>(tw, tx, p, stream);
+        case SK_LOGITS_F32: return launch_epi<SK_LOGITS_F32>(tw, tx, p, stream);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace aries

@@ -133,11 +133,12 @@ class WhisperModel:
 
     ``WhisperModel("large-v3", weights=..., device="cuda", device_index=0)`` mirrors the reference's construction
     (ref: final_optimized_transcriber.py:179-182).  ``compute_type`` is accepted for signature compatibility; the
-    B200 path always computes in bf16 with f32 accumulation.  Decoding (``transcribe`` / ``generate``) is out of
-    scope for this library."""
+    B200 path always computes in bf16 with f32 accumulation.  When ``weights`` also holds the ``decoder/...`` variables
+    and ``decoder_shape`` is given, ``generate`` (greedy ``ctranslate2.models.Whisper.generate``, row f1) is available
+    too; tokenisation / segment assembly (``transcribe``) stay outside this library."""
 
     def __init__(self, model_size_or_shape, weights: dict | None = None, device: str = "cuda", device_index: int = 0,
-                 compute_type: str = "bfloat16", **_ignored):
+                 compute_type: str = "bfloat16", decoder_shape=None, max_batch: int = 64, suppress_ids=(), **_ignored):
         if device not in ("cuda", "auto"):
             raise ValueError("whisper_aries_b200 has no CPU path: device must be 'cuda'")
         dev = f"cuda:{device_index}"
@@ -156,6 +157,17 @@ class WhisperModel:
         self.compute_type = compute_type
         self.feature_extractor = FeatureExtractor(feature_size=shape.n_mels, device=dev)
         self.encoder = WhisperEncoder(shape, weights, device=dev)
+        self.decoder = None
+        if decoder_shape is not None:
+            from .decoder import WhisperDecoder
+            self.decoder = WhisperDecoder(decoder_shape, weights, device=dev, max_batch=max_batch,
+                                          suppress_ids=suppress_ids)
+
+    def generate(self, encoder_output, prompts, **kw):
+        """``ctranslate2.models.Whisper.generate`` (greedy) on the encoder output of ``encode`` / ``encode_audio``."""
+        if self.decoder is None:
+            raise RuntimeError("this WhisperModel was built without decoder weights (pass decoder_shape=...)")
+        return self.decoder.generate(encoder_output, prompts, **kw)
 
     def encode(self, features):
         return self.encoder.encode(features)
