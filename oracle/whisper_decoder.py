@@ -84,23 +84,31 @@ class Decoder:
         return out
 
     @torch.no_grad()
-    def logits(self, tokens: torch.Tensor, enc: torch.Tensor, cross=None) -> torch.Tensor:
-        """tokens int64 [B, T], enc f32 [B, 1500, d] -> f32 [B, T, vocab]."""
+    def logits(self, tokens: torch.Tensor, enc: torch.Tensor, cross=None, emulate_bf16: bool = False) -> torch.Tensor:
+        """tokens int64 [B, T], enc f32 [B, 1500, d] -> f32 [B, T, vocab].
+
+        ``emulate_bf16`` rounds every tensor the CUDA path stores (LayerNorm outputs, projections, attention outputs and
+        the cached keys / values to bf16; the residual stream to f16) while keeping the arithmetic in f32: the error of
+        THAT pipeline against the plain f32 one is the noise floor of the number format, against which the GPU tests
+        judge the kernels' own error."""
         W, d = self.w, self.shape.d_model
+        bf = (lambda t: t.to(torch.bfloat16).to(torch.float32)) if emulate_bf16 else (lambda t: t)
+        hf = (lambda t: t.to(torch.float16).to(torch.float32)) if emulate_bf16 else (lambda t: t)
         cross = cross if cross is not None else self.cross_kv(enc)
-        x = W["decoder/embeddings/weight"][tokens] + W["decoder/position_encodings/encodings"][: tokens.shape[1]]
+        cross = [(bf(k), bf(v)) for k, v in cross]
+        x = hf(W["decoder/embeddings/weight"][tokens] + W["decoder/position_encodings/encodings"][: tokens.shape[1]])
         for i in range(self.shape.n_layers):
             p = f"decoder/layer_{i}"
-            y = F.layer_norm(x, (d,), W[f"{p}/self_attention/layer_norm/gamma"], W[f"{p}/self_attention/layer_norm/beta"], LN_EPS)
-            q, k, v = F.linear(y, W[f"{p}/self_attention/linear_0/weight"], W[f"{p}/self_attention/linear_0/bias"]).split(d, -1)
-            x = x + F.linear(self._mha(q, k, v, True), W[f"{p}/self_attention/linear_1/weight"], W[f"{p}/self_attention/linear_1/bias"])
-            y = F.layer_norm(x, (d,), W[f"{p}/attention/layer_norm/gamma"], W[f"{p}/attention/layer_norm/beta"], LN_EPS)
-            q = F.linear(y, W[f"{p}/attention/linear_0/weight"], W[f"{p}/attention/linear_0/bias"])
-            x = x + F.linear(self._mha(q, cross[i][0], cross[i][1], False), W[f"{p}/attention/linear_2/weight"], W[f"{p}/attention/linear_2/bias"])
-            y = F.layer_norm(x, (d,), W[f"{p}/ffn/layer_norm/gamma"], W[f"{p}/ffn/layer_norm/beta"], LN_EPS)
-            x = x + F.linear(F.gelu(F.linear(y, W[f"{p}/ffn/linear_0/weight"], W[f"{p}/ffn/linear_0/bias"])),
-                             W[f"{p}/ffn/linear_1/weight"], W[f"{p}/ffn/linear_1/bias"])
-        x = F.layer_norm(x, (d,), W["decoder/layer_norm/gamma"], W["decoder/layer_norm/beta"], LN_EPS)
+            y = bf(F.layer_norm(x, (d,), W[f"{p}/self_attention/layer_norm/gamma"], W[f"{p}/self_attention/layer_norm/beta"], LN_EPS))
+            q, k, v = bf(F.linear(y, W[f"{p}/self_attention/linear_0/weight"], W[f"{p}/self_attention/linear_0/bias"])).split(d, -1)
+            x = hf(x + F.linear(bf(self._mha(q, k, v, True)), W[f"{p}/self_attention/linear_1/weight"], W[f"{p}/self_attention/linear_1/bias"]))
+            y = bf(F.layer_norm(x, (d,), W[f"{p}/attention/layer_norm/gamma"], W[f"{p}/attention/layer_norm/beta"], LN_EPS))
+            q = bf(F.linear(y, W[f"{p}/attention/linear_0/weight"], W[f"{p}/attention/linear_0/bias"]))
+            x = hf(x + F.linear(bf(self._mha(q, cross[i][0], cross[i][1], False)), W[f"{p}/attention/linear_2/weight"], W[f"{p}/attention/linear_2/bias"]))
+            y = bf(F.layer_norm(x, (d,), W[f"{p}/ffn/layer_norm/gamma"], W[f"{p}/ffn/layer_norm/beta"], LN_EPS))
+            h = bf(F.gelu(F.linear(y, W[f"{p}/ffn/linear_0/weight"], W[f"{p}/ffn/linear_0/bias"])))
+            x = hf(x + F.linear(h, W[f"{p}/ffn/linear_1/weight"], W[f"{p}/ffn/linear_1/bias"]))
+        x = bf(F.layer_norm(x, (d,), W["decoder/layer_norm/gamma"], W["decoder/layer_norm/beta"], LN_EPS))
         proj = W.get("decoder/projection/weight", W["decoder/embeddings/weight"])
         return x @ proj.T
 

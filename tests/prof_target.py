@@ -1,4 +1,5 @@
-"""Small profiling targets for ncu (run under gpurun):  python tests/prof_target.py mel|attn|ln|gemm-o|gemm-fc1|gemm-fc2|gemm-qkv"""
+"""Small profiling targets for ncu (run under gpurun):
+    python tests/prof_target.py mel|attn|ln|gemm-o|gemm-fc1|gemm-fc2|gemm-qkv|dec-xattn|dec-skinny|dec-logits"""
 import ctypes
 import sys
 
@@ -42,6 +43,27 @@ elif what == "ln":
     y = torch.empty((rows, d), device=dev, dtype=torch.bfloat16)
     for _ in range(3):
         lib.aries_test_layernorm(ctx.handle, ptr(x), ptr(gm), ptr(bt), ptr(y), rows, d, None)
+    torch.cuda.synchronize()
+elif what == "dec-xattn":
+    # cross-attention of one decode step at the bench shape: 64 windows x 20 heads x 1500 keys (491.5 MB of keys / values)
+    B_, H, n = 64, 20, 1500
+    d = 64 * H
+    q = torch.randn(B_, d, device=dev).bfloat16()
+    kv = torch.randn(B_ * n, 2 * d, device=dev).bfloat16()
+    out = torch.empty((B_, d), device=dev, dtype=torch.bfloat16)
+    for _ in range(3):
+        lib.aries_test_decode_attention(ctx.handle, ptr(q), d, ptr(kv), ctypes.c_void_p(kv.data_ptr() + d * 2), n, 2 * d,
+                                        None, None, 0, None, n, B_, H, ptr(out), d, 1, None)
+    torch.cuda.synchronize()
+elif what in ("dec-skinny", "dec-logits"):
+    # the fc1 projection (13.1 MB of weights) / the logits projection (132.8 MB) of one decode step, 64 sequences
+    B_, N, K, epi = (64, 5120, 1280, 1) if what == "dec-skinny" else (64, 51866, 1280, 3)
+    x = torch.randn(B_, K, device=dev).bfloat16()
+    w = (torch.randn(N, K, device=dev) * 0.05).bfloat16()
+    bias = torch.randn(N, device=dev)
+    out = torch.empty((B_, N), device=dev, dtype=torch.float32 if epi == 3 else torch.bfloat16)
+    for _ in range(3):
+        lib.aries_test_skinny_gemm(ctx.handle, epi, B_, N, K, ptr(x), ptr(w), ptr(bias), ptr(out), N, 0, None)
     torch.cuda.synchronize()
 else:
     M = 96000

@@ -7,8 +7,10 @@
 //   grid = (heads, batch, splits), 128 threads.  Eight lanes share one 128-byte key / value row (16 bytes each, full
 //   sectors), a warp covers 4 rows per load instruction and four loads are kept in flight per lane.
 //   pass 1: scores (log2 domain) -> shared memory + running max; pass 2: p = exp2(s - max), o += p V.
-//   splits > 1 (cross-attention at small batch): partial (max, sum, o) per split go to a small f32 buffer and the
-//   last CTA of a (b, h) to finish merges them (ticket counter, self-resetting).
+//   splits > 1 (cross-attention at small batch): the CTAs of a (b, h) form a thread-block cluster (grid.z = cluster
+//   size <= 8); each parks its partial (max, sum, o) in its own shared memory and rank 0 merges them through
+//   distributed shared memory -- no HBM round trip, no atomics.  A share of <= 192 keys also fetches its value rows
+//   together with the keys (one HBM round trip instead of two).
 // Self-attention also appends the step's new key / value row to the cache before attending (same CTA, so no race).
 #include <cuda_bf16.h>
 
@@ -24,6 +26,17 @@ constexpr int kMaxKeys = 1536;            // shared score buffer (cross-attentio
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float ld_peer_f32(const float* local, uint32_t rank) {
+    uint32_t remote;
+    float v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"((uint32_t)__cvta_generic_to_shared(local)), "r"(rank));
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote));
+    return v;
+}
+
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
@@ -34,18 +47,17 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
     }
 }
 
+template <bool kPrefetchV>
 __global__ void __launch_bounds__(kThreads) decode_attention_kernel(const DecAttnParams p) {
     __shared__ float s_score[kMaxKeys];
     __shared__ float s_red[4][66];
     __shared__ float s_max[4];
-    __shared__ unsigned s_ticket;
 
     const int h = blockIdx.x, b = blockIdx.y, split = blockIdx.z;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int grp = lane >> 3, sub = lane & 7;       // 8 lanes per key row; lane `sub` owns dims 8 sub .. 8 sub + 7
 
     pdl_wait();
-    pdl_trigger();
 
     int n_keys = p.n_keys_fixed;
     const __nv_bfloat16* kbase = reinterpret_cast<const __nv_bfloat16*>(p.k) + (size_t)b * p.kv_rows * p.kv_ld + h * 64;
@@ -78,14 +90,32 @@ __global__ void __launch_bounds__(kThreads) decode_attention_kernel(const DecAtt
     }
 
     // ---------------------------------------------------------------- pass 1: scores
+    // A share of <= 64 keys (cross-attention split finely at small batch, early self-attention steps) is ONE iteration:
+    // its value rows are fetched together with the keys, so the CTA pays one HBM round trip instead of two.
+    constexpr int kPre = kPrefetchV ? 3 : 1;                 // iterations whose value rows are fetched with the keys
+    const bool pre = kPrefetchV && (j1 - j0) <= 64 * kPre;   // (a template flag: the prefetch costs registers)
+    uint4 vpre[kPre][4];
     float m = -INFINITY;
-    for (int jw = j0 + warp * 4; jw < j1; jw += 64) {          // warp-uniform trip count (shuffles inside)
+    int it = 0;
+    for (int jw = j0 + warp * 4; jw < j1; jw += 64, ++it) {  // warp-uniform trip count (shuffles inside)
         const int jb = jw + grp;
         uint4 kk[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int j = jb + 16 * u;
             kk[u] = (j < j1) ? *reinterpret_cast<const uint4*>(kbase + (size_t)j * p.kv_ld + sub * 8) : make_uint4(0, 0, 0, 0);
+        }
+        if (pre) {
+#pragma unroll
+            for (int i = 0; i < kPre; ++i)
+                if (i == it) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int j = jb + 16 * u;
+                        vpre[i][u] = (j < j1) ? *reinterpret_cast<const uint4*>(vbase + (size_t)j * p.kv_ld + sub * 8)
+                                              : make_uint4(0, 0, 0, 0);
+                    }
+                }
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -113,13 +143,23 @@ __global__ void __launch_bounds__(kThreads) decode_attention_kernel(const DecAtt
     // ---------------------------------------------------------------- pass 2: weights and weighted values
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     float l = 0.0f;
-    for (int jw = j0 + warp * 4; jw < j1; jw += 64) {
+    it = 0;
+    for (int jw = j0 + warp * 4; jw < j1; jw += 64, ++it) {
         const int jb = jw + grp;
         uint4 vv[4];
+        if (pre) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int j = jb + 16 * u;
-            vv[u] = (j < j1) ? *reinterpret_cast<const uint4*>(vbase + (size_t)j * p.kv_ld + sub * 8) : make_uint4(0, 0, 0, 0);
+            for (int i = 0; i < kPre; ++i)
+                if (i == it) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) vv[u] = vpre[i][u];
+                }
+        } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = jb + 16 * u;
+                vv[u] = (j < j1) ? *reinterpret_cast<const uint4*>(vbase + (size_t)j * p.kv_ld + sub * 8) : make_uint4(0, 0, 0, 0);
+            }
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -134,6 +174,7 @@ __global__ void __launch_bounds__(kThreads) decode_attention_kernel(const DecAtt
             }
         }
     }
+    pdl_trigger();       // after the streaming part: dependents launched earlier would only occupy SM slots
     // the 4 row groups of a warp, then the 4 warps
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -158,33 +199,35 @@ __global__ void __launch_bounds__(kThreads) decode_attention_kernel(const DecAtt
         }
         return;
     }
-    // ---------------------------------------------------------------- split merge
-    float* part = p.partial + ((size_t)(b * p.heads + h) * p.splits) * 66;
-    if (tid < 66) {
-        float v;
-        if (tid < 65) v = s_red[0][tid] + s_red[1][tid] + s_red[2][tid] + s_red[3][tid];
-        else v = m;
-        part[split * 66 + tid] = v;
-    }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) s_ticket = atomicAdd(&p.tickets[b * p.heads + h], 1u);
-    __syncthreads();
-    if (s_ticket != (unsigned)(p.splits - 1)) return;
-    __threadfence();
-    if (tid < 64) {
-        float M = -INFINITY;
-        for (int s = 0; s < p.splits; ++s) M = fmaxf(M, __ldcg(part + s * 66 + 65));
-        float o = 0.0f, ls = 0.0f;
-        for (int s = 0; s < p.splits; ++s) {
-            const float ms = __ldcg(part + s * 66 + 65);
-            const float w = (ms == -INFINITY) ? 0.0f : exp2f(ms - M);
-            o = fmaf(w, __ldcg(part + s * 66 + tid), o);
-            ls = fmaf(w, __ldcg(part + s * 66 + 64), ls);
+    // ---------------------------------------------------------------- split merge (cluster, distributed shared memory)
+    __shared__ float s_part[66];
+    if (tid < 65) s_part[tid] = s_red[0][tid] + s_red[1][tid] + s_red[2][tid] + s_red[3][tid];
+    if (tid == 65) s_part[65] = m;
+    cluster_sync_all();                                   // every CTA's partial is in its shared memory
+    if (split == 0 && tid < 64) {
+        float ms[8], ls[8], os[8];
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            const uint32_t r = (uint32_t)(s < p.splits ? s : 0);
+            ms[s] = ld_peer_f32(&s_part[65], r);
+            ls[s] = ld_peer_f32(&s_part[64], r);
+            os[s] = ld_peer_f32(&s_part[tid], r);
         }
-        out[tid] = __float2bfloat16_rn(o / ls);
+        float M = -INFINITY;
+#pragma unroll
+        for (int s = 0; s < 8; ++s)
+            if (s < p.splits) M = fmaxf(M, ms[s]);
+        float o = 0.0f, lsum = 0.0f;
+#pragma unroll
+        for (int s = 0; s < 8; ++s)
+            if (s < p.splits && ms[s] != -INFINITY) {
+                const float w = exp2f(ms[s] - M);
+                o = fmaf(w, os[s], o);
+                lsum = fmaf(w, ls[s], lsum);
+            }
+        out[tid] = __float2bfloat16_rn(o / lsum);
     }
-    if (tid == 0) p.tickets[b * p.heads + h] = 0u;
+    cluster_sync_all();                                   // rank 0 is done reading its peers
 }
 
 }  // namespace
@@ -205,14 +248,33 @@ cudaError_t launch_maybe_pdl(const void* func, dim3 grid, dim3 block, size_t sme
 }
 
 cudaError_t decode_attention_launch(const DecAttnParams& p, cudaStream_t stream) {
-    if (p.batch <= 0 || p.heads <= 0 || p.splits < 1) return cudaErrorInvalidValue;
+    if (p.batch <= 0 || p.heads <= 0 || p.splits < 1 || p.splits > 8) return cudaErrorInvalidValue;
     const int n_max = p.n_keys_fixed ? p.n_keys_fixed : (int)p.kv_rows;
     if ((n_max + p.splits - 1) / p.splits > kMaxKeys) return cudaErrorInvalidValue;
     if (p.n_keys_fixed == 0 && p.splits != 1) return cudaErrorInvalidValue;
-    DecAttnParams q = p;
-    void* args[] = {&q};
-    return launch_maybe_pdl(reinterpret_cast<const void*>(decode_attention_kernel), dim3(p.heads, p.batch, p.splits),
-                            dim3(kThreads), 0, stream, args, p.pdl != 0);
+    const bool prefetch = p.n_keys_fixed > 0 && (p.n_keys_fixed + p.splits - 1) / p.splits <= 192;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(p.heads, p.batch, p.splits);
+    cfg.blockDim = dim3(kThreads);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (p.splits > 1) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 1;
+        attr[na].val.clusterDim.y = 1;
+        attr[na].val.clusterDim.z = p.splits;
+        ++na;
+    }
+    if (p.pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    return prefetch ? cudaLaunchKernelEx(&cfg, decode_attention_kernel<true>, p)
+                    : cudaLaunchKernelEx(&cfg, decode_attention_kernel<false>, p);
 }
 
 }  // namespace aries

@@ -10,6 +10,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include "layernorm.h"
 #include "skinny.h"
 
 namespace aries {
@@ -72,7 +73,7 @@ __global__ void __launch_bounds__(128) decode_layernorm_kernel(const __half* __r
     }
 }
 
-constexpr int kSampleThreads = 256;
+constexpr int kSampleThreads = 1024;     // one CTA per sequence; 16-byte loads, ~13 per thread and pass at 51866 ids
 
 struct Best {
     float v;
@@ -117,17 +118,38 @@ __global__ void __launch_bounds__(kSampleThreads) decode_sample_kernel(const Sam
     int* toks = p.tokens + (size_t)b * p.tokens_ld;
     const int V = p.vocab, tb = p.timestamp_begin;
 
+    // rows are 16-byte aligned (logits_ld is a multiple of 128) and padded past the vocabulary, so every pass reads
+    // float4 and masks n >= V
+    const float4* lg4 = reinterpret_cast<const float4*>(lg);
+    const int n4 = (V + 3) / 4;
+
     // ---- no-speech probability: softmax of the raw logits at the <|startoftranscript|> position
     if (t == p.sot_index[b]) {
         float m = -INFINITY;
-        for (int n = tid; n < V; n += kSampleThreads) m = fmaxf(m, lg[n]);
+#pragma unroll 4
+        for (int i = tid; i < n4; i += kSampleThreads) {
+            const float4 v = lg4[i];
+            const int n = 4 * i;
+            m = fmaxf(m, v.x);
+            if (n + 1 < V) m = fmaxf(m, v.y);
+            if (n + 2 < V) m = fmaxf(m, v.z);
+            if (n + 3 < V) m = fmaxf(m, v.w);
+        }
         m = warp_max(m);
         if (lane == 0) s_f[0][warp] = m;
         __syncthreads();
         m = s_f[0][0];
         for (int w = 1; w < kWarps; ++w) m = fmaxf(m, s_f[0][w]);
         float s = 0.0f;
-        for (int n = tid; n < V; n += kSampleThreads) s += __expf(lg[n] - m);
+#pragma unroll 4
+        for (int i = tid; i < n4; i += kSampleThreads) {
+            const float4 v = lg4[i];
+            const int n = 4 * i;
+            s += __expf(v.x - m);
+            if (n + 1 < V) s += __expf(v.y - m);
+            if (n + 2 < V) s += __expf(v.z - m);
+            if (n + 3 < V) s += __expf(v.w - m);
+        }
         s = warp_sum(s);
         if (lane == 0) s_f[1][warp] = s;
         __syncthreads();
@@ -168,12 +190,19 @@ __global__ void __launch_bounds__(kSampleThreads) decode_sample_kernel(const Sam
             // ---- pass A: maxima
             Best all{-INFINITY, 0x7fffffff}, ts{-INFINITY, 0x7fffffff};
             float text_max = -INFINITY;
-            for (int n = tid; n < V; n += kSampleThreads) {
-                if (!allowed(n)) continue;
-                const float v = lg[n];
-                all = better(all, Best{v, n});
-                if (n >= tb) ts = better(ts, Best{v, n});
-                else text_max = fmaxf(text_max, v);
+#pragma unroll 2
+            for (int i = tid; i < n4; i += kSampleThreads) {
+                const float4 q = lg4[i];
+                const float vv[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int n = 4 * i + u;
+                    if (n >= V || !allowed(n)) continue;
+                    const float v = vv[u];
+                    all = better(all, Best{v, n});
+                    if (n >= tb) ts = better(ts, Best{v, n});
+                    else text_max = fmaxf(text_max, v);
+                }
             }
             all = warp_best(all);
             ts = warp_best(ts);
@@ -194,11 +223,18 @@ __global__ void __launch_bounds__(kSampleThreads) decode_sample_kernel(const Sam
             }
             // ---- pass B: log-sum-exp of everything allowed and of the timestamps
             float sum_all = 0.0f, sum_ts = 0.0f;
-            for (int n = tid; n < V; n += kSampleThreads) {
-                if (!allowed(n)) continue;
-                const float v = lg[n];
-                sum_all += __expf(v - all.v);
-                if (n >= tb) sum_ts += __expf(v - ts.v);
+#pragma unroll 2
+            for (int i = tid; i < n4; i += kSampleThreads) {
+                const float4 q = lg4[i];
+                const float vv[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int n = 4 * i + u;
+                    if (n >= V || !allowed(n)) continue;
+                    const float v = vv[u];
+                    sum_all += __expf(v - all.v);
+                    if (n >= tb) sum_ts += __expf(v - ts.v);
+                }
             }
             sum_all = warp_sum(sum_all);
             sum_ts = warp_sum(sum_ts);
@@ -261,6 +297,9 @@ cudaError_t decode_embed_launch(const int* tokens, int tokens_ld, const int* ste
 cudaError_t decode_layernorm_launch(const void* x_f16, const float* gamma, const float* beta, void* y_bf16, int rows, int d,
                                     int pdl, cudaStream_t stream) {
     if (rows <= 0 || d % 2 != 0) return cudaErrorInvalidValue;
+    // Whisper widths (multiples of 128 the encoder kernel is instantiated for): the row stays in registers, one pass
+    if (layernorm_launch_pdl(x_f16, gamma, beta, y_bf16, rows, d, 1e-5f, stream, pdl != 0) == cudaSuccess) return cudaSuccess;
+    cudaGetLastError();
     const __half* x = reinterpret_cast<const __half*>(x_f16);
     __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(y_bf16);
     void* args[] = {&x, &gamma, &beta, &y, &rows, &d};

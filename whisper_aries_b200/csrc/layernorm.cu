@@ -18,6 +18,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) layernorm_kernel(const __
                                                                         const float* __restrict__ beta,
                                                                         __nv_bfloat16* __restrict__ y, long long rows,
                                                                         float eps) {
+    // no-ops unless launched with programmatic stream serialisation (the decode step, skinny.h)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int lane = threadIdx.x & 31;
     const long long row = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -66,32 +69,43 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) layernorm_kernel(const __
 
 template <int NV>
 cudaError_t launch(const __half* x, const float* g, const float* b, void* y, long long rows, float eps,
-                   cudaStream_t stream) {
+                   cudaStream_t stream, bool pdl = false) {
     const long long blocks = (rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    layernorm_kernel<NV><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, stream>>>(x, g, b,
-                                                                              reinterpret_cast<__nv_bfloat16*>(y), rows,
-                                                                              eps);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)blocks);
+    cfg.blockDim = dim3(kWarpsPerBlock * 32);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, layernorm_kernel<NV>, x, g, b, reinterpret_cast<__nv_bfloat16*>(y), rows, eps);
 }
 
 }  // namespace
 
 cudaError_t layernorm_launch(const void* x_f16, const float* gamma, const float* beta, void* y, long long rows, int d,
                              float eps, cudaStream_t stream) {
+    return layernorm_launch_pdl(x_f16, gamma, beta, y, rows, d, eps, stream, false);
+}
+
+cudaError_t layernorm_launch_pdl(const void* x_f16, const float* gamma, const float* beta, void* y, long long rows, int d,
+                                 float eps, cudaStream_t stream, bool pdl) {
     if (rows <= 0) return cudaSuccess;
     if (d % 128 != 0) return cudaErrorInvalidValue;
     const __half* x = reinterpret_cast<const __half*>(x_f16);
     switch (d / 128) {
-        case 1: return launch<1>(x, gamma, beta, y, rows, eps, stream);
-        case 2: return launch<2>(x, gamma, beta, y, rows, eps, stream);
-        case 3: return launch<3>(x, gamma, beta, y, rows, eps, stream);
-        case 4: return launch<4>(x, gamma, beta, y, rows, eps, stream);
-        case 5: return launch<5>(x, gamma, beta, y, rows, eps, stream);
-        case 6: return launch<6>(x, gamma, beta, y, rows, eps, stream);
-        case 8: return launch<8>(x, gamma, beta, y, rows, eps, stream);
-        case 10: return launch<10>(x, gamma, beta, y, rows, eps, stream);
-        case 12: return launch<12>(x, gamma, beta, y, rows, eps, stream);
-        case 16: return launch<16>(x, gamma, beta, y, rows, eps, stream);
+        case 1: return launch<1>(x, gamma, beta, y, rows, eps, stream, pdl);
+        case 2: return launch<2>(x, gamma, beta, y, rows, eps, stream, pdl);
+        case 3: return launch<3>(x, gamma, beta, y, rows, eps, stream, pdl);
+        case 4: return launch<4>(x, gamma, beta, y, rows, eps, stream, pdl);
+        case 5: return launch<5>(x, gamma, beta, y, rows, eps, stream, pdl);
+        case 6: return launch<6>(x, gamma, beta, y, rows, eps, stream, pdl);
+        case 8: return launch<8>(x, gamma, beta, y, rows, eps, stream, pdl);
+        case 10: return launch<10>(x, gamma, beta, y, rows, eps, stream, pdl);
+        case 12: return launch<12>(x, gamma, beta, y, rows, eps, stream, pdl);
+        case 16: return launch<16>(x, gamma, beta, y, rows, eps, stream, pdl);
     }
     return cudaErrorInvalidValue;
 }

@@ -9,4 +9,8 @@ namespace aries {
 cudaError_t layernorm_launch(const void* x_f16, const float* gamma, const float* beta, void* y_bf16, long long rows,
                              int d, float eps, cudaStream_t stream);
 
+// Same kernel launched with programmatic stream serialisation (the decode step's dependent-launch chain).
+cudaError_t layernorm_launch_pdl(const void* x_f16, const float* gamma, const float* beta, void* y_bf16, long long rows,
+                                 int d, float eps, cudaStream_t stream, bool pdl);
+
 }  // namespace aries

@@ -39,16 +39,28 @@ inline int smem_bytes(int NB) {
 
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ float ld_dsmem_f32(uint32_t local_addr, uint32_t rank) {
+__device__ __forceinline__ uint32_t dsmem_addr(uint32_t local_addr, uint32_t rank) {
     uint32_t remote;
-    float v;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(rank));
-    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
+    return remote;
+}
+__device__ __forceinline__ float ld_dsmem_f32(uint32_t remote) {
+    float v;
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote));
     return v;
 }
 
+// The residual value is passed in: the callers fetch the residuals of ALL the elements they own before the first store
+// (a load inside the store loop may alias the previous store, so the compiler keeps them in order and every element pays
+// a full memory round trip: 10 us for 16 sequences).
 template <int EPI>
-__device__ __forceinline__ void store_one(const SkinnyParams& p, int b, int n, float v) {
+__device__ __forceinline__ float load_resid(const SkinnyParams& p, int b, int n) {
+    if (EPI != SK_BIAS_RESID_F16) return 0.0f;
+    return __half2float(reinterpret_cast<const __half*>(p.out)[(size_t)b * p.ldo + n]);
+}
+
+template <int EPI>
+__device__ __forceinline__ void store_one(const SkinnyParams& p, int b, int n, float v, float resid) {
     const size_t at = (size_t)b * p.ldo + n;
     if (EPI == SK_LOGITS_F32) {
         reinterpret_cast<float*>(p.out)[at] = v;
@@ -58,7 +70,7 @@ __device__ __forceinline__ void store_one(const SkinnyParams& p, int b, int n, f
     if (EPI == SK_BIAS_GELU_BF16) v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
     if (EPI == SK_BIAS_RESID_F16) {
         __half* o = reinterpret_cast<__half*>(p.out);
-        v += __half2float(o[at]);
+        v += resid;
         o[at] = __float2half_rn(fminf(fmaxf(v, -65504.0f), 65504.0f));
     } else {
         reinterpret_cast<__nv_bfloat16*>(p.out)[at] = __float2bfloat16_rn(v);
@@ -90,6 +102,7 @@ skinny_gemm_tcgen05(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
     const int kb1 = (kb0 + kps < num_kb) ? kb0 + kps : num_kb;
     const int my_kb = kb1 - kb0;                // >= 1 by construction of `splits`
 
+    const int pre = my_kb < kStages ? my_kb : kStages;
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmap_w);
         tma_prefetch_desc(&tmap_x);
@@ -99,6 +112,13 @@ skinny_gemm_tcgen05(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
         }
         mbar_init(tfull_bar, 1);
         fence_mbar_init();
+        // The producer starts streaming WEIGHTS at once: before the TMEM allocation, the CTA-wide sync and
+        // griddepcontrol.wait (weights are never written during decoding, so they do not depend on the previous
+        // kernel) -- the first HBM round trip overlaps the whole prologue and the tail of the previous kernel.
+        for (int i = 0; i < pre; ++i) {
+            mbar_expect_tx(&full_bar[i], sbytes);
+            tma_load_2d(smem + i * sbytes, &tmap_w, &full_bar[i], (kb0 + i) * BK, n0);
+        }
     }
     if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
     tc_fence_before();
@@ -108,21 +128,13 @@ skinny_gemm_tcgen05(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
 
     if (warp == 0) {
         if (lane == 0) {
-            // ---------------------------------------------------------------- TMA producer
-            // weights first (independent of the previous kernel), then wait for it, then the activations
-            const int pre = my_kb < kStages ? my_kb : kStages;
-            for (int i = 0; i < pre; ++i) {
-                mbar_expect_tx(&full_bar[i], sbytes);
-                tma_load_2d(smem + i * sbytes, &tmap_w, &full_bar[i], (kb0 + i) * BK, n0);
-            }
+            // ---------------------------------------------------------------- TMA producer (continued)
             pdl_wait();
             pdl_trigger();
             for (int i = 0; i < pre; ++i)
                 tma_load_2d(smem + i * sbytes + kWBytes, &tmap_x, &full_bar[i], (kb0 + i) * BK, 0);
-            int stage = 0;
-            uint32_t phase = 0;
-            if (pre == kStages) phase = 1;          // the ring wrapped once
-            stage = pre % kStages;
+            int stage = pre % kStages;
+            uint32_t phase = (pre == kStages) ? 1 : 0;          // the ring wrapped once
             for (int i = pre; i < my_kb; ++i) {
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 uint8_t* s = smem + stage * sbytes;
@@ -169,10 +181,16 @@ skinny_gemm_tcgen05(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
             tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(quarter * 32) << 16) + c * 16, acc);
             tmem_ld_wait_on(acc);
             if (p.splits == 1) {
+                float res[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const int b = c * 16 + j;
-                    if (b < p.B && n < p.N) store_one<EPI>(p, b, n, __uint_as_float(acc[j]));
+                    res[j] = (b < p.B && n < p.N) ? load_resid<EPI>(p, b, n) : 0.0f;
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int b = c * 16 + j;
+                    if (b < p.B && n < p.N) store_one<EPI>(p, b, n, __uint_as_float(acc[j]), res[j]);
                 }
             } else {
                 // the pipeline stages are free: every MMA of this CTA has retired (tfull)
@@ -190,12 +208,32 @@ skinny_gemm_tcgen05(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
             const int quarter = warp & 3;
             const int nl = quarter * 32 + lane;
             const int n = n0 + nl;
-            const uint32_t part0 = base;
-            for (int b = split; b < p.B; b += p.splits) {
-                float sum = 0.0f;
-                const uint32_t at = part0 + (uint32_t)(b * BMW + nl) * 4u;
-                for (int s = 0; s < p.splits; ++s) sum += ld_dsmem_f32(at, (uint32_t)s);
-                if (n < p.N) store_one<EPI>(p, b, n, sum);
+            // peers' tiles through distributed shared memory: all loads of a sequence are issued before the first add
+            // (a chain of dependent remote loads costs ~0.2 us each: 13 us for 64 sequences)
+            uint32_t peer[kMaxSplits];
+#pragma unroll
+            for (int s = 0; s < kMaxSplits; ++s) peer[s] = dsmem_addr(base + (uint32_t)nl * 4u, (uint32_t)(s < p.splits ? s : 0));
+            for (int b = split; b < p.B; b += 2 * p.splits) {      // two sequences per round: 16 remote loads in flight
+                const int b2 = b + p.splits;
+                const bool has2 = b2 < p.B;
+                const float r1 = (n < p.N) ? load_resid<EPI>(p, b, n) : 0.0f;
+                const float r2 = (n < p.N && has2) ? load_resid<EPI>(p, b2, n) : 0.0f;
+                float v[kMaxSplits], w[kMaxSplits];
+#pragma unroll
+                for (int s = 0; s < kMaxSplits; ++s) {
+                    v[s] = (s < p.splits) ? ld_dsmem_f32(peer[s] + (uint32_t)(b * BMW) * 4u) : 0.0f;
+                    w[s] = (s < p.splits && has2) ? ld_dsmem_f32(peer[s] + (uint32_t)(b2 * BMW) * 4u) : 0.0f;
+                }
+                float sum = 0.0f, sum2 = 0.0f;
+#pragma unroll
+                for (int s = 0; s < kMaxSplits; ++s) {                 // fixed order: bit-reproducible
+                    sum += v[s];
+                    sum2 += w[s];
+                }
+                if (n < p.N) {
+                    store_one<EPI>(p, b, n, sum, r1);
+                    if (has2) store_one<EPI>(p, b2, n, sum2, r2);
+                }
             }
         }
         cluster_sync_all();                         // peers are done reading this CTA's shared memory

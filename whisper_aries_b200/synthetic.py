@@ -226,3 +226,30 @@ def decoder_weights(shape: DecoderShape, seed: int = 4321, logit_scale: float = 
             w[f"{p}/linear_1/weight"] = w[f"{p}/linear_1/weight"] * 2.0
             w[f"{p}/linear_2/weight"] = w[f"{p}/linear_2/weight"] * np.float32(cross_gain)
     return w
+
+
+def decoder_weights_fast(shape: DecoderShape, seed: int = 0) -> dict[str, np.ndarray]:
+    """Whisper-layout (tied) random decoder weights drawn with torch's multi-threaded generator: 0.8 G parameters for
+    large-v3 in a few seconds.  Benchmarks only -- parity tests use ``decoder_weights`` (numpy, shared with the oracle)."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    d, f = shape.d_model, shape.d_ffn
+
+    def nrm(*s, sc=0.02):
+        return (torch.randn(*s, generator=g) * sc).numpy()
+
+    w = {"decoder/embeddings/weight": nrm(shape.vocab, d, sc=0.05),
+         "decoder/position_encodings/encodings": nrm(shape.n_text_ctx, d)}
+    for i in range(shape.n_layers):
+        p = f"decoder/layer_{i}"
+        for blk in ("self_attention", "attention", "ffn"):
+            w[f"{p}/{blk}/layer_norm/gamma"] = 1.0 + nrm(d)
+            w[f"{p}/{blk}/layer_norm/beta"] = nrm(d)
+        for name, n_out, n_in in (("self_attention/linear_0", 3 * d, d), ("self_attention/linear_1", d, d),
+                                  ("attention/linear_0", d, d), ("attention/linear_1", 2 * d, d),
+                                  ("attention/linear_2", d, d), ("ffn/linear_0", f, d), ("ffn/linear_1", d, f)):
+            w[f"{p}/{name}/weight"] = nrm(n_out, n_in)
+            w[f"{p}/{name}/bias"] = nrm(n_out)
+    w["decoder/layer_norm/gamma"] = 1.0 + nrm(d)
+    w["decoder/layer_norm/beta"] = nrm(d)
+    return w
