@@ -47,7 +47,10 @@ traffic = {}
 names = {"mel": "logmel_tiles_kernel", "attn": "attention_fwd_kernel", "ln": "layernorm_kernel",
          "gemm-fc1": "gemm_bf16_tcgen05 (fc1: M=96000 N=5120 K=1280, bias+GELU epilogue)",
          "gemm-qkv": "gemm_bf16_tcgen05 (QKV: M=96000 N=3840 K=1280, bias epilogue)",
-         "gemm-o": "gemm_bf16_tcgen05 (out-proj: M=96000 N=1280 K=1280, bias + f16 residual epilogue)"}
+         "gemm-o": "gemm_bf16_tcgen05 (out-proj: M=96000 N=1280 K=1280, bias + f16 residual epilogue)",
+         "dec-xattn": "decode_attention_kernel (row f1: cross-attention of one decode step, 64 windows x 20 heads x 1500 keys)",
+         "dec-skinny": "skinny_gemm_tcgen05 (row f1: fc1 of one decode step, 64 sequences, N=5120 K=1280, cluster split-K 7)",
+         "dec-logits": "skinny_gemm_tcgen05 (row f1: logits of one decode step, 64 sequences, N=51866 K=1280)"}
 for tag, name in names.items():
     rep = os.path.join(G, f"final_{tag}.ncu-rep")
     if not os.path.exists(rep):
@@ -99,9 +102,21 @@ if os.path.exists(lc):
     import shutil
     shutil.copy(lc, os.path.join(out_dir, "launches_bench_w16.csv"))
 
+# row f1: launch lists of a few decode steps (tests/gpu_diag_decode.py prof B)
+for B in (1, 64):
+    lc = os.path.join(G, f"dec_launches_b{B}.csv")
+    if os.path.exists(lc):
+        title = (f"ncu launch list -- `python tests/gpu_diag_decode.py prof {B}`: 6 greedy decode steps, {B} window(s), large-v3 "
+                 "layer shape with 4 layers, direct stream launches (no graph, no programmatic launch)")
+        md = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "summarize_launches.py"), lc, title],
+                            capture_output=True, text=True).stdout
+        with open(os.path.join(out_dir, f"launches_decode_b{B}_summary.md"), "w") as f:
+            f.write(md)
+
 # bench.py reads the fc1 GEMM as the representative launch of the dominant kernel class
 tj = {"source": f"profiles/{rnd}/ncu_full_*.txt (ncu --set full, one launch each, tests/prof_target.py shapes)",
       "gemm_bf16_tcgen05": traffic.get("gemm-fc1", {}).get("dram_bytes"),
-      "logmel_tiles_kernel": traffic.get("mel", {}).get("dram_bytes"), "detail": traffic}
+      "logmel_tiles_kernel": traffic.get("mel", {}).get("dram_bytes"),
+      "decode_attention_kernel": traffic.get("dec-xattn", {}).get("dram_bytes"), "detail": traffic}
 json.dump(tj, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
 print(json.dumps({k: round(v["dram_bytes"] / 1e6, 1) for k, v in traffic.items()}))

@@ -96,3 +96,32 @@ def test_model_from_directory_matches_model_from_dict(tmp_path):
     assert torch.equal(from_dir.encode_audio(pcm), from_dict.encode_audio(pcm))
     with pytest.raises(ValueError, match="CTranslate2 model directory"):
         WhisperModel("large-v3", device="cuda")
+
+
+def test_decoder_variables_round_trip(tmp_path):
+    """Row f1: the decoder/ variables of the same container, with the output projection stored as an alias of the
+    embedding (as Whisper checkpoints do) and the suppress list taken from config.json."""
+    shape = osynth.DEC_SHAPES["micro"]
+    w = osynth.decoder_weights(shape, 3, tied=True)
+    variables = dict(osynth.encoder_weights(osynth.SHAPES["micro"], 7))
+    variables.update(w)
+    d = tmp_path / "model"
+    d.mkdir()
+    ct2_model.write_model_bin(str(d / "model.bin"), variables, dtypes={"decoder/embeddings/weight": "float16"},
+                              aliases={"decoder/projection/weight": "decoder/embeddings/weight"})
+    (d / "config.json").write_text(json.dumps({"suppress_ids": [1, 2, 7], "suppress_ids_begin": [220, 50257]}))
+    got_shape, got, info = ct2_model.load_decoder_weights(str(d))
+    assert dataclasses.astuple(got_shape) == dataclasses.astuple(shape)
+    assert info["suppress_ids"] == [1, 2, 7] and info["suppress_ids_begin"] == [220, 50257]
+    assert not any(k.startswith("encoder/") for k in got)
+    for k, v in w.items():
+        if k == "decoder/embeddings/weight":
+            assert np.abs(got[k] - v).max() <= 2 ** -11 * np.abs(v).max()
+        else:
+            assert np.array_equal(got[k], v), k
+    assert np.array_equal(got["decoder/projection/weight"], got["decoder/embeddings/weight"])     # the alias
+    with pytest.raises((KeyError, ValueError)):
+        enc_only = tmp_path / "enc"
+        enc_only.mkdir()
+        ct2_model.write_model_bin(str(enc_only / "model.bin"), dict(osynth.encoder_weights(osynth.SHAPES["micro"], 7)))
+        ct2_model.load_decoder_weights(str(enc_only))

@@ -206,3 +206,49 @@ def load_encoder_weights(model_dir: str) -> tuple[EncoderShape, dict, dict]:
     if feat is not None and int(feat) != shape.n_mels:
         raise ValueError(f"preprocessor_config.json feature_size {feat} != conv1 input channels {shape.n_mels}")
     return shape, weights, info
+
+
+def decoder_shape_of(weights: dict, name: str = "ct2"):
+    """Infers the text-decoder dims (vocab, d_model, layers, ffn, positions) from the ``decoder/`` variables (row f1)."""
+    from .synthetic import DEC_SHAPES, DecoderShape
+    emb = weights["decoder/embeddings/weight"]
+    vocab, d = int(emb.shape[0]), int(emb.shape[1])
+    layers = 0
+    while f"decoder/layer_{layers}/ffn/linear_0/weight" in weights:
+        layers += 1
+    if layers == 0:
+        raise ValueError("no decoder layers found (decoder/layer_0/...)")
+    ffn = int(weights["decoder/layer_0/ffn/linear_0/weight"].shape[0])
+    n_ctx = int(weights["decoder/position_encodings/encodings"].shape[0])
+    for known in DEC_SHAPES.values():
+        if (known.vocab, known.d_model, known.n_layers, known.d_ffn, known.n_text_ctx) == (vocab, d, layers, ffn, n_ctx):
+            return known
+    if d % 64:
+        raise ValueError(f"d_model {d} is not a multiple of the head size 64")
+    return DecoderShape(name, vocab, d, d // 64, layers, ffn, n_ctx)
+
+
+def load_decoder_weights(model_dir: str):
+    """``(shape, {CT2 variable name: float32 ndarray}, info)`` for the ``decoder/`` variables of a converted model
+    directory (embeddings, learned positions, per-layer self-attention / cross-attention / ffn, final LayerNorm and
+    the output projection -- an alias of the embedding in Whisper checkpoints).  ``info["suppress_ids"]`` /
+    ``info["suppress_ids_begin"]`` come from ``config.json`` (what upstream's ``suppress_tokens=[-1]`` expands to)."""
+    path = os.path.join(model_dir, "model.bin")
+    if not os.path.exists(path):
+        raise FileNotFoundError(f"{path}: not a CTranslate2 model directory")
+    variables, meta = read_model_bin(path, prefix="decoder/")
+    for alias, target in meta["aliases"].items():
+        if alias.startswith("decoder/") and target in variables:
+            variables[alias] = variables[target]
+    weights = {n: _dequantise(n, variables, meta) for n in variables
+               if not n.endswith("_scale") and variables[n].ndim >= 1}
+    shape = decoder_shape_of(weights, os.path.basename(os.path.normpath(model_dir)) or "ct2")
+    info = {"meta": {k: v for k, v in meta.items() if k != "bf16"}, "suppress_ids": [], "suppress_ids_begin": []}
+    p = os.path.join(model_dir, "config.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            cfg = json.load(f)
+        info["config.json"] = cfg
+        info["suppress_ids"] = [int(t) for t in cfg.get("suppress_ids", [])]
+        info["suppress_ids_begin"] = [int(t) for t in cfg.get("suppress_ids_begin", [])]
+    return shape, weights, info

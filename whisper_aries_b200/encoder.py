@@ -151,7 +151,19 @@ class WhisperModel:
             if not (isinstance(model_size_or_shape, str) and os.path.isdir(model_size_or_shape)):
                 raise ValueError("weights=None needs the path of a CTranslate2 model directory (model.bin); "
                                  f"got {model_size_or_shape!r}")
-            model_size_or_shape, weights, self.model_info = load_encoder_weights(model_size_or_shape)
+            model_dir = model_size_or_shape
+            model_size_or_shape, weights, self.model_info = load_encoder_weights(model_dir)
+            if decoder_shape is None:
+                # the same model.bin carries the decoder: build it too, as upstream's WhisperModel(path) does
+                from .ct2_model import load_decoder_weights
+                try:
+                    decoder_shape, dec_w, dec_info = load_decoder_weights(model_dir)
+                except (KeyError, ValueError):
+                    decoder_shape = None                       # an encoder-only directory
+                else:
+                    weights = dict(weights)
+                    weights.update(dec_w)
+                    suppress_ids = suppress_ids or dec_info["suppress_ids"]
         shape = SHAPES[model_size_or_shape] if isinstance(model_size_or_shape, str) else model_size_or_shape
         self.shape = shape
         self.compute_type = compute_type
