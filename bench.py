@@ -257,7 +257,7 @@ def run_decode(args, rank: int, local_rank: int, world: int) -> int:
     cpu = None
     if not args.no_cpu_baseline:
         torch.set_num_threads(max(1, os.cpu_count() or 1))
-        n = 6
+        n = 40
         tps, dt = cpu_decode_sample(args.model, n)
         cpu = {"value": tps, "unit": "tokens/s", "cores": torch.get_num_threads(), "kind": "port",
                "sample": f"1 window x {n} tokens in {dt:.1f} s: oracle fp32 decoder (torch CPU, prefix recomputed per token), "

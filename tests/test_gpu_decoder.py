@@ -290,3 +290,39 @@ def test_encode_then_generate_end_to_end():
             assert got[i] == w_
             n_ok += 1
         assert n_ok >= MIN_COMPARED, (n_ok, margins)
+
+
+def test_large_v3_shape_logits_match_oracle():
+    """The BASELINE shape (d 1280, 20 heads, 32 layers, ffn 5120, vocab 51866 -- not a multiple of 128): teacher-forced
+    logits of 2 windows x 6 tokens against the fp32 oracle with the same (bf16-rounded) random weights.  Covers every
+    production tiling: cluster split-K of 7 / 3 / 4 / 8, the 406-tile logits projection, 8-way split cross-attention."""
+    from oracle import synth as osynth, whisper_decoder as wd
+    from whisper_aries_b200 import WhisperDecoder, synthetic
+    shape = synthetic.DEC_SHAPES["large-v3"]
+    tok = synthetic.WhisperTokens.for_vocab(shape.vocab)
+    w = synthetic.decoder_weights_fast(shape, 5)
+    dec = WhisperDecoder(shape, w, tokens=tok, device="cuda:0", max_batch=2)
+    oracle = wd.Decoder(w, osynth.DEC_SHAPES["large-v3"], round_weights_bf16=True)
+    del w
+    g = torch.Generator().manual_seed(9)
+    enc = torch.randn(2, shape.n_audio_ctx, shape.d_model, generator=g).bfloat16()
+    prompt = [tok.sot, tok.first_lang, tok.transcribe]
+    forced = [[50400, 1001, 2002, 3003, 50420, 50420], [50365, 17, 29999, 51000, 51000, 44]]
+    L = len(prompt) + 6
+    res, extras = dec.generate(enc.cuda(), [prompt, prompt], max_length=L, suppress_tokens=[], _forced=forced,
+                               _want_logits=True, return_no_speech_prob=True)
+    seqs = torch.tensor([prompt + f for f in forced])[:, :L - 1]
+    ref = oracle.logits(seqs, enc.float())
+    emu = oracle.logits(seqs, enc.float(), emulate_bf16=True)
+    logits = torch.from_numpy(extras[0]["logits"]).transpose(0, 1)               # [B, T, V]
+    for b in range(2):
+        for t in range(L - 1):
+            cos = torch.nn.functional.cosine_similarity(logits[b, t], ref[b, t], dim=0).item()
+            assert cos >= 0.999, f"window {b} step {t}: logits cosine {cos}"
+    rms_cuda = (logits - ref).pow(2).mean().sqrt().item()
+    rms_emu = (emu - ref).pow(2).mean().sqrt().item()
+    assert rms_cuda <= 2.0 * rms_emu + 1e-3, (rms_cuda, rms_emu)
+    assert [r.sequences_ids[0] for r in res] == forced
+    # the sampled-position argmax obeys the rules: first position is a timestamp within the first second
+    a0 = extras[0]["argmax"][:, len(prompt)]
+    assert ((a0 >= tok.timestamp_begin) & (a0 <= tok.timestamp_begin + 50)).all()

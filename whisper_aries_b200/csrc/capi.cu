@@ -252,7 +252,6 @@ int aries_encoder_create(aries_ctx* ctx, const aries_encoder_cfg* cfg, const ari
         cudaGetLastError();
         return e == cudaErrorInvalidValue ? ARIES_EINVAL : (e == cudaErrorMemoryAllocation ? ARIES_ENOMEM : ARIES_ECUDA);
     }
-    ctx->kernels_ready = true;
     aries_encoder* h = new (std::nothrow) aries_encoder{kMagicEnc, ctx, plan, nullptr, 0, nullptr, 0, nullptr, 0};
     if (!h) {
         aries::encoder_plan_destroy(plan);
