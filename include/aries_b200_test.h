@@ -39,6 +39,12 @@ ARIES_API int aries_test_attention_trace(aries_ctx* ctx, unsigned long long* hos
 ARIES_API int aries_test_skinny_gemm(aries_ctx* ctx, int epi, int B, int N, int K, const void* x, const void* w,
                            const float* bias, void* out, int ldo, int splits, void* stream);
 
+/* Same GEMM with the LayerNorm of the decode step fused into the operand load (B <= 8, K <= 1280, epi 0 | 1 | 3):
+ * out[b, n] = epilogue(sum_k LN(x_f16[b, :])[k] * gamma[k] + beta[k]) w[n, k]); x_f16 f16 [B, K]. */
+ARIES_API int aries_test_skinny_gemm_ln(aries_ctx* ctx, int epi, int B, int N, int K, const void* x_f16, const float* gamma,
+                              const float* beta, const void* w, const float* bias, void* out, int ldo, int splits,
+                              void* stream);
+
 /* Single-query attention over a bf16 key/value cache (see csrc/skinny.h DecAttnParams). n_keys_fixed == 0: self-attention
  * (appends new_k / new_v at position *step_dev, attends to 0 .. *step_dev); otherwise cross-attention over n_keys_fixed
  * keys with `splits` CTAs per (sequence, head). */

@@ -491,6 +491,30 @@ int aries_test_skinny_gemm(aries_ctx* ctx, int epi, int B, int N, int K, const v
     return ARIES_OK;
 }
 
+int aries_test_skinny_gemm_ln(aries_ctx* ctx, int epi, int B, int N, int K, const void* x_f16, const float* gamma,
+                              const float* beta, const void* w, const float* bias, void* out, int ldo, int splits,
+                              void* stream) {
+    int rc = use(ctx);
+    if (rc) return rc;
+    if ((rc = ensure_kernels(ctx))) return rc;
+    if (B <= 0 || B > 8 || N <= 0 || K <= 0 || K % 64 || epi < 0 || epi >= aries::SK_COUNT || !x_f16 || !gamma || !beta)
+        return fail(ARIES_EINVAL, "aries_test_skinny_gemm_ln: bad shape");
+    CUtensorMap tw;
+    const unsigned long long dw[2] = {(unsigned long long)K, (unsigned long long)N}, st[2] = {2, (unsigned long long)K * 2};
+    const unsigned bw[2] = {64, 128};
+    cudaError_t e;
+    if ((e = aries::make_tmap_bf16(&tw, w, 2, dw, st, bw)) != cudaSuccess) return fail_cuda("tensor map W", e);
+    aries::SkinnyParams p{};
+    p.B = B; p.NB = 16; p.N = N; p.K = K;
+    p.splits = splits > 0 ? splits : aries::skinny_pick_splits_ln(N, K, ctx->sm_count);
+    p.bias = bias; p.out = out; p.ldo = ldo; p.pdl = 0;
+    p.ln_x = x_f16; p.ln_gamma = gamma; p.ln_beta = beta;
+    if (p.splits < 1) return fail(ARIES_EINVAL, "aries_test_skinny_gemm_ln: K too deep for the fused variant");
+    if ((e = aries::skinny_launch(epi, tw, tw, p, static_cast<cudaStream_t>(stream))) != cudaSuccess)
+        return fail_cuda("skinny_launch (fused LayerNorm)", e);
+    return ARIES_OK;
+}
+
 int aries_test_decode_attention(aries_ctx* ctx, const void* q, int q_ld, void* k, void* v, int64_t kv_rows, int kv_ld,
                                 const void* new_k, const void* new_v, int new_ld, const int* step_dev, int n_keys_fixed,
                                 int batch, int heads, void* out, int out_ld, int splits, void* stream) {

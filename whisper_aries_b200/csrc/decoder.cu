@@ -51,7 +51,7 @@ struct DecLayerW {
 
 struct GraphKey {
     int batch, prompt_len, max_length, suppress_blank, blank_id, eot, no_speech, no_timestamps, timestamp_begin,
-        max_initial, n_forced, want_argmax, pdl;
+        max_initial, n_forced, want_argmax, pdl, fuse_ln;
     bool operator==(const GraphKey& o) const { return std::memcmp(this, &o, sizeof(GraphKey)) == 0; }
 };
 
@@ -309,11 +309,22 @@ cudaError_t decoder_plan_create(int device, int sm_count, const DecoderShapeC& c
 namespace {
 
 // One decode step: consumes tokens[:, *step], writes tokens[:, *step + 1], increments *step.
-cudaError_t run_step(DecoderPlan* pl, int batch, const SampleParams& sp, int xsplits, bool pdl, cudaStream_t stream,
-                     int* launches) {
+cudaError_t run_step(DecoderPlan* pl, int batch, const SampleParams& sp, int xsplits, bool pdl, bool fuse_ln,
+                     cudaStream_t stream, int* launches) {
     const auto& c = pl->cfg;
     const int d = c.d_model, f = c.d_ffn, C = c.n_text_ctx, A = c.n_audio_ctx;
     int n = 0;
+    // LayerNorm folded into the consuming GEMM's operand load (<= 8 sequences): 3 launches fewer per layer
+    auto ln_skinny = [&](int epi, const CUtensorMap& w, int N, const float* g, const float* b, const float* bias, void* out,
+                         int ldo) {
+        SkinnyParams q{};
+        q.B = batch; q.NB = 16; q.N = N; q.K = d;
+        q.splits = skinny_pick_splits_ln(N, d, pl->sm_count);
+        q.bias = bias; q.out = out; q.ldo = ldo; q.pdl = pdl;
+        q.ln_x = pl->x; q.ln_gamma = g; q.ln_beta = b;
+        ++n;
+        return skinny_launch(epi, w, w, q, stream);
+    };
     auto skinny = [&](int epi, const CUtensorMap& w, const CUtensorMap& xin, int N, int K, const float* bias, void* out,
                       int ldo) {
         SkinnyParams q{};
@@ -328,8 +339,13 @@ cudaError_t run_step(DecoderPlan* pl, int batch, const SampleParams& sp, int xsp
     const __nv_bfloat16* qkv = reinterpret_cast<const __nv_bfloat16*>(pl->qkv);
     for (int l = 0; l < c.n_layers; ++l) {
         const DecLayerW& lw = pl->layers[l];
-        ARIES_TRY(decode_layernorm_launch(pl->x, lw.ln1_g, lw.ln1_b, pl->y, batch, d, pdl, stream), "layer norm 1");
-        ARIES_TRY(skinny(SK_BIAS_BF16, lw.m_qkv, pl->a_y, 3 * d, d, lw.bqkv, pl->qkv, 3 * d), "qkv projection");
+        if (fuse_ln) {
+            ARIES_TRY(ln_skinny(SK_BIAS_BF16, lw.m_qkv, 3 * d, lw.ln1_g, lw.ln1_b, lw.bqkv, pl->qkv, 3 * d), "LN + qkv projection");
+        } else {
+            ARIES_TRY(decode_layernorm_launch(pl->x, lw.ln1_g, lw.ln1_b, pl->y, batch, d, pdl, stream), "layer norm 1");
+            ARIES_TRY(skinny(SK_BIAS_BF16, lw.m_qkv, pl->a_y, 3 * d, d, lw.bqkv, pl->qkv, 3 * d), "qkv projection");
+            ++n;
+        }
         DecAttnParams a{};
         a.batch = batch; a.heads = c.n_heads;
         a.q = qkv; a.q_ld = 3 * d;
@@ -341,8 +357,13 @@ cudaError_t run_step(DecoderPlan* pl, int batch, const SampleParams& sp, int xsp
         a.out = pl->ctx; a.out_ld = d; a.splits = 1; a.pdl = pdl;
         ARIES_TRY(decode_attention_launch(a, stream), "self-attention");
         ARIES_TRY(skinny(SK_BIAS_RESID_F16, lw.m_o, pl->a_ctx, d, d, lw.bo, pl->x, d), "self-attention output");
-        ARIES_TRY(decode_layernorm_launch(pl->x, lw.ln2_g, lw.ln2_b, pl->y, batch, d, pdl, stream), "layer norm 2");
-        ARIES_TRY(skinny(SK_BIAS_BF16, lw.m_q2, pl->a_y, d, d, lw.bq2, pl->q2, d), "cross-attention query");
+        if (fuse_ln) {
+            ARIES_TRY(ln_skinny(SK_BIAS_BF16, lw.m_q2, d, lw.ln2_g, lw.ln2_b, lw.bq2, pl->q2, d), "LN + cross-attention query");
+        } else {
+            ARIES_TRY(decode_layernorm_launch(pl->x, lw.ln2_g, lw.ln2_b, pl->y, batch, d, pdl, stream), "layer norm 2");
+            ARIES_TRY(skinny(SK_BIAS_BF16, lw.m_q2, pl->a_y, d, d, lw.bq2, pl->q2, d), "cross-attention query");
+            ++n;
+        }
         DecAttnParams x{};
         x.batch = batch; x.heads = c.n_heads;
         x.q = pl->q2; x.q_ld = d;
@@ -353,15 +374,20 @@ cudaError_t run_step(DecoderPlan* pl, int batch, const SampleParams& sp, int xsp
         x.pdl = pdl;
         ARIES_TRY(decode_attention_launch(x, stream), "cross-attention");
         ARIES_TRY(skinny(SK_BIAS_RESID_F16, lw.m_o2, pl->a_ctx, d, d, lw.bo2, pl->x, d), "cross-attention output");
-        ARIES_TRY(decode_layernorm_launch(pl->x, lw.ln3_g, lw.ln3_b, pl->y, batch, d, pdl, stream), "layer norm 3");
-        ARIES_TRY(skinny(SK_BIAS_GELU_BF16, lw.m_fc1, pl->a_y, f, d, lw.b1, pl->h, f), "fc1");
+        if (fuse_ln) {
+            ARIES_TRY(ln_skinny(SK_BIAS_GELU_BF16, lw.m_fc1, f, lw.ln3_g, lw.ln3_b, lw.b1, pl->h, f), "LN + fc1");
+        } else {
+            ARIES_TRY(decode_layernorm_launch(pl->x, lw.ln3_g, lw.ln3_b, pl->y, batch, d, pdl, stream), "layer norm 3");
+            ARIES_TRY(skinny(SK_BIAS_GELU_BF16, lw.m_fc1, pl->a_y, f, d, lw.b1, pl->h, f), "fc1");
+            ++n;
+        }
         ARIES_TRY(skinny(SK_BIAS_RESID_F16, lw.m_fc2, pl->a_h, d, f, lw.b2, pl->x, d), "fc2");
-        n += 5;
+        n += 2;
     }
     ARIES_TRY(decode_layernorm_launch(pl->x, pl->lnf_g, pl->lnf_b, pl->y, batch, d, pdl, stream), "final layer norm");
     ARIES_TRY(skinny(SK_LOGITS_F32, pl->m_proj, pl->a_y, c.vocab, d, nullptr, pl->logits, pl->v_pad), "logits");
     ARIES_TRY(decode_sample_launch(sp, stream), "sampling");
-    n += 2;
+    n += 2;                       // (final LayerNorm + sampling; the skinny lambdas count themselves)
     *launches = n;
     return cudaSuccess;
 }
@@ -473,6 +499,10 @@ cudaError_t decoder_generate(DecoderPlan* pl, const void* enc_out, int batch, co
     // cross-attention: ~4 CTAs per SM in flight; the splits of a (sequence, head) form a cluster of <= 8 CTAs
     int want = (4 * pl->sm_count + batch * c.n_heads - 1) / (batch * c.n_heads);
     const int xsplits = want < 1 ? 1 : (want > 8 ? 8 : want);
+    // fused LayerNorm: small batch only (two rows per warp), and only where every fused GEMM fits (d <= 1280)
+    const bool fuse_ln = env_on("ARIES_DECODE_FUSED_LN", true) && batch <= 8 && d <= 1280 &&
+                         skinny_pick_splits_ln(3 * d, d, pl->sm_count) > 0 && skinny_pick_splits_ln(d, d, pl->sm_count) > 0 &&
+                         skinny_pick_splits_ln(c.d_ffn, d, pl->sm_count) > 0;
     const bool use_graph = env_on("ARIES_DECODE_GRAPH", true) && !o.logits_out;
     // programmatic dependent launch pays while the step is latency-bound (measured: -10 % per step up to 32 sequences,
     // +12 % at 64, where every kernel fills the machine and early-launched dependents only take SM slots)
@@ -482,7 +512,8 @@ cudaError_t decoder_generate(DecoderPlan* pl, const void* enc_out, int batch, co
 
     if (use_graph) {
         GraphKey key{batch, prompt_len, o.max_length, o.suppress_blank, o.blank_id, o.eot, o.no_speech, o.no_timestamps,
-                     o.timestamp_begin, o.max_initial_timestamp_index, o.n_forced, o.argmax_out ? 1 : 0, pdl ? 1 : 0};
+                     o.timestamp_begin, o.max_initial_timestamp_index, o.n_forced, o.argmax_out ? 1 : 0, pdl ? 1 : 0,
+                     fuse_ln ? 1 : 0};
         if (!pl->graph || !(key == pl->graph_key)) {
             if (pl->graph) {
                 cudaGraphExecDestroy(pl->graph);
@@ -492,7 +523,7 @@ cudaError_t decoder_generate(DecoderPlan* pl, const void* enc_out, int batch, co
                 sp.pdl = pdl;
                 cudaGraph_t g = nullptr;
                 ARIES_TRY(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal), "begin capture");
-                cudaError_t e1 = run_step(pl, batch, sp, xsplits, pdl, stream, &per_step);
+                cudaError_t e1 = run_step(pl, batch, sp, xsplits, pdl, fuse_ln, stream, &per_step);
                 cudaError_t e2 = cudaStreamEndCapture(stream, &g);
                 cudaError_t e3 = (e1 == cudaSuccess && e2 == cudaSuccess) ? cudaGraphInstantiate(&pl->graph, g, 0) : cudaErrorUnknown;
                 if (g) cudaGraphDestroy(g);
@@ -521,7 +552,7 @@ cudaError_t decoder_generate(DecoderPlan* pl, const void* enc_out, int batch, co
         if (use_graph) {
             ARIES_TRY(cudaGraphLaunch(pl->graph, stream), "graph launch");
         } else {
-            cudaError_t e = run_step(pl, batch, sp, xsplits, pdl, stream, &per_step);
+            cudaError_t e = run_step(pl, batch, sp, xsplits, pdl, fuse_ln, stream, &per_step);
             if (e != cudaSuccess) return e;
             if (o.logits_out)
                 ARIES_TRY(cudaMemcpy2DAsync(o.logits_out + (size_t)t * batch * V, (size_t)V * 4, pl->logits,

@@ -32,9 +32,18 @@ struct SkinnyParams {
     float* partial;     // f32 [splits][NB][n_tiles * 128] (only touched when splits > 1)
     unsigned* tickets;  // [n_tiles], zero before the first launch; the kernel leaves them zero
     int pdl;            // launched with programmatic stream serialisation (griddepcontrol in the kernel)
+    // Fused LayerNorm (small batch): when ln_x != NULL the token-row operand is not loaded by TMA but computed in the
+    // kernel as LayerNorm(ln_x[b, :]) * gamma + beta (f16 residual stream in, bf16 operand written straight into the
+    // swizzled shared-memory tile) -- saves the separate LayerNorm launch of the latency-bound decode step.
+    // Needs B <= 8, NB == 16, K <= 1280, K % 64 == 0 and at most 8 K-blocks per split.
+    const void* ln_x;       // f16 [B, K]
+    const float* ln_gamma;  // [K]
+    const float* ln_beta;   // [K]
 };
 
 int skinny_pick_splits(int N, int K, int sm_count);
+// same, for the fused-LayerNorm variant (every split must hold all of its K-blocks at once: <= 8); 0 if impossible
+int skinny_pick_splits_ln(int N, int K, int sm_count);
 size_t skinny_partial_bytes(int NB, int N, int splits);
 cudaError_t skinny_init_device();
 // tmap_w: [N, K] bf16, box 64 x 128; tmap_x: [>= NB rows, K] bf16, box 64 x NB.

@@ -25,14 +25,17 @@ namespace {
 constexpr int BMW = 128;            // weight rows per CTA
 constexpr int BK = 64;
 constexpr int kStages = 4;
+constexpr int kStagesLn = 8;        // fused-LayerNorm variant: all K-blocks of a split are resident (no ring reuse)
+constexpr int kLnMaxB = 8;          // sequences the fused variant handles (two rows per epilogue warp)
+constexpr int kLnMaxJ = 5;          // 16-byte chunks of a row per lane: K <= 5 * 256
 constexpr int kWBytes = BMW * BK * 2;
 constexpr int kThreads = 192;       // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
 constexpr uint32_t kTmemCols = 128;
 constexpr int kMaxSplits = 8;
 
 __host__ __device__ inline int stage_bytes(int NB) { return kWBytes + NB * BK * 2; }
-inline int smem_bytes(int NB) {
-    const int pipe = kStages * stage_bytes(NB);
+inline int smem_bytes(int NB, bool ln = false) {
+    const int pipe = (ln ? kStagesLn : kStages) * stage_bytes(NB);
     const int part = NB * BMW * 4;
     return (pipe > part ? pipe : part) + 256 + 1024;
 }
@@ -77,11 +80,13 @@ __device__ __forceinline__ void store_one(const SkinnyParams& p, int b, int n, f
     }
 }
 
-template <int EPI>
+template <int EPI, bool LN>
 __global__ void __launch_bounds__(kThreads)
 skinny_gemm_tcgen05(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
                     const SkinnyParams p) {
+    constexpr int kStages = LN ? aries::kStagesLn : aries::kStages;      // shadows the namespace constant
     extern __shared__ uint8_t smem_raw[];
+    __shared__ float s_gamma[LN ? kStagesLn * BK : 1], s_beta[LN ? kStagesLn * BK : 1];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
     const int sbytes = stage_bytes(p.NB);
@@ -107,7 +112,7 @@ skinny_gemm_tcgen05(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
         tma_prefetch_desc(&tmap_w);
         tma_prefetch_desc(&tmap_x);
         for (int s = 0; s < kStages; ++s) {
-            mbar_init(&full_bar[s], 1);
+            mbar_init(&full_bar[s], LN ? 2 : 1);      // LN: the weight TMA and the epilogue warps' operand tile
             mbar_init(&empty_bar[s], 1);
         }
         mbar_init(tfull_bar, 1);
@@ -116,7 +121,7 @@ skinny_gemm_tcgen05(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
         // griddepcontrol.wait (weights are never written during decoding, so they do not depend on the previous
         // kernel) -- the first HBM round trip overlaps the whole prologue and the tail of the previous kernel.
         for (int i = 0; i < pre; ++i) {
-            mbar_expect_tx(&full_bar[i], sbytes);
+            mbar_expect_tx(&full_bar[i], LN ? kWBytes : sbytes);
             tma_load_2d(smem + i * sbytes, &tmap_w, &full_bar[i], (kb0 + i) * BK, n0);
         }
     }
@@ -131,8 +136,10 @@ skinny_gemm_tcgen05(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
             // ---------------------------------------------------------------- TMA producer (continued)
             pdl_wait();
             pdl_trigger();
-            for (int i = 0; i < pre; ++i)
-                tma_load_2d(smem + i * sbytes + kWBytes, &tmap_x, &full_bar[i], (kb0 + i) * BK, 0);
+            if (!LN) {
+                for (int i = 0; i < pre; ++i)
+                    tma_load_2d(smem + i * sbytes + kWBytes, &tmap_x, &full_bar[i], (kb0 + i) * BK, 0);
+            }
             int stage = pre % kStages;
             uint32_t phase = (pre == kStages) ? 1 : 0;          // the ring wrapped once
             for (int i = pre; i < my_kb; ++i) {
@@ -168,8 +175,95 @@ skinny_gemm_tcgen05(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
         }
     } else {
         // -------------------------------------------------------------------- epilogue warps: one output feature per thread
-        pdl_wait();
-        pdl_trigger();
+        if (LN) {
+            // ---- fused LayerNorm: these 4 warps BUILD the token-row operand (they are idle until the MMAs retire).
+            // Before griddepcontrol.wait (nothing here depends on the previous kernel): gamma / beta of this split's
+            // K range to shared memory, and zeros into the pad rows of every operand tile.
+            const int et = threadIdx.x - 64;                       // 0 .. 127
+            const int k_lo = kb0 * BK, k_n = my_kb * BK;
+            for (int i = et; i < k_n; i += 128) {
+                s_gamma[i] = __ldg(p.ln_gamma + k_lo + i);
+                s_beta[i] = __ldg(p.ln_beta + k_lo + i);
+            }
+            for (int i = et; i < (p.NB - p.B) * 8 * my_kb; i += 128) {
+                const int st = i / ((p.NB - p.B) * 8), rem = i - st * (p.NB - p.B) * 8;
+                const int r = p.B + rem / 8, cc = rem & 7;
+                *reinterpret_cast<uint4*>(smem + st * sbytes + kWBytes + r * 128 + ((cc ^ (r & 7)) << 4)) = make_uint4(0, 0, 0, 0);
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");         // gamma / beta visible to the four warps
+            pdl_wait();
+            pdl_trigger();
+            // One warp per row (rows ew and ew + 4): the row lives in registers as 16-byte chunks (lane + 32 j), the
+            // statistics are two-pass f32 like layernorm_kernel, and every chunk that falls into this split's K range is
+            // normalised, rounded to bf16 and stored at its SWIZZLE_128B position (chunk ^ (row & 7)) of the K-major tile.
+            const int ew = warp - 2;
+            const int n_chunks = p.K / 8;
+            const __half* xs = reinterpret_cast<const __half*>(p.ln_x);
+            float v[2][kLnMaxJ][8];
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                const int r = ew + 4 * rr;
+#pragma unroll
+                for (int j = 0; j < kLnMaxJ; ++j) {
+                    const int c = lane + 32 * j;
+                    uint4 u = make_uint4(0, 0, 0, 0);
+                    if (r < p.B && c < n_chunks) u = *reinterpret_cast<const uint4*>(xs + (size_t)r * p.K + 8 * c);
+                    const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 f = __half22float2(h2[e]);
+                        v[rr][j][2 * e] = f.x;
+                        v[rr][j][2 * e + 1] = f.y;
+                    }
+                }
+            }
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                const int r = ew + 4 * rr;
+                if (r >= p.B) continue;                            // warp-uniform
+                float sum = 0.0f;
+#pragma unroll
+                for (int j = 0; j < kLnMaxJ; ++j)
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) sum += v[rr][j][e];        // chunks past the row are zero
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                const float mean = sum / (float)p.K;
+                float sq = 0.0f;
+#pragma unroll
+                for (int j = 0; j < kLnMaxJ; ++j) {
+                    if (lane + 32 * j < n_chunks) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) sq += (v[rr][j][e] - mean) * (v[rr][j][e] - mean);
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+                const float rstd = rsqrtf(sq / (float)p.K + 1e-5f);
+#pragma unroll
+                for (int j = 0; j < kLnMaxJ; ++j) {
+                    const int c = lane + 32 * j;
+                    const int kb = c >> 3;
+                    if (c < n_chunks && kb >= kb0 && kb < kb1) {
+                        const int kk = (kb - kb0) * BK + (c & 7) * 8;          // offset inside this split's K range
+                        uint4 o4;
+                        uint32_t* o = reinterpret_cast<uint32_t*>(&o4);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            o[e] = pack_bf16x2((v[rr][j][2 * e] - mean) * rstd * s_gamma[kk + 2 * e] + s_beta[kk + 2 * e],
+                                               (v[rr][j][2 * e + 1] - mean) * rstd * s_gamma[kk + 2 * e + 1] + s_beta[kk + 2 * e + 1]);
+                        *reinterpret_cast<uint4*>(smem + (kb - kb0) * sbytes + kWBytes + r * 128 + (((c & 7) ^ (r & 7)) << 4)) = o4;
+                    }
+                }
+            }
+            fence_proxy_async_smem();                              // generic-proxy stores -> visible to tcgen05.mma
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (et == 0)
+                for (int i = 0; i < my_kb; ++i) mbar_arrive(&full_bar[i]);
+        } else {
+            pdl_wait();
+            pdl_trigger();
+        }
         const int quarter = warp & 3;
         const int nl = quarter * 32 + lane;
         const int n = n0 + nl;
@@ -249,10 +343,11 @@ skinny_gemm_tcgen05(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
 template <int EPI>
 cudaError_t launch_epi(const CUtensorMap& tw, const CUtensorMap& tx, const SkinnyParams& p, cudaStream_t stream) {
     const int n_tiles = (p.N + BMW - 1) / BMW;
+    const bool ln = p.ln_x != nullptr;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(n_tiles, p.splits);
     cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = smem_bytes(p.NB);
+    cfg.dynamicSmemBytes = smem_bytes(p.NB, ln);
     cfg.stream = stream;
     cudaLaunchAttribute attr[2];
     int na = 0;
@@ -270,12 +365,17 @@ cudaError_t launch_epi(const CUtensorMap& tw, const CUtensorMap& tx, const Skinn
     }
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    return cudaLaunchKernelEx(&cfg, skinny_gemm_tcgen05<EPI>, tw, tx, p);
+    if (ln) return cudaLaunchKernelEx(&cfg, skinny_gemm_tcgen05<EPI, true>, tw, tx, p);
+    return cudaLaunchKernelEx(&cfg, skinny_gemm_tcgen05<EPI, false>, tw, tx, p);
 }
 
 template <int EPI>
 cudaError_t set_smem() {
-    return cudaFuncSetAttribute(skinny_gemm_tcgen05<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(128));
+    cudaError_t e = cudaFuncSetAttribute(skinny_gemm_tcgen05<EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         smem_bytes(128));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(skinny_gemm_tcgen05<EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                smem_bytes(16, true));
 }
 
 }  // namespace
@@ -292,6 +392,15 @@ int skinny_pick_splits(int N, int K, int sm_count) {
     if (want < 1) want = 1;
     const int kps = (num_kb + want - 1) / want;
     return (num_kb + kps - 1) / kps;                             // every split owns >= 1 block
+}
+
+int skinny_pick_splits_ln(int N, int K, int sm_count) {
+    const int num_kb = K / BK;
+    int splits = skinny_pick_splits(N, K, sm_count);
+    while (splits <= kMaxSplits && (num_kb + splits - 1) / splits > kStagesLn) ++splits;
+    if (splits > kMaxSplits || splits > num_kb) return 0;
+    const int kps = (num_kb + splits - 1) / splits;
+    return (num_kb + kps - 1) / kps;
 }
 
 size_t skinny_partial_bytes(int, int, int) { return 0; }         // partial sums live in distributed shared memory
@@ -311,6 +420,9 @@ cudaError_t skinny_launch(int epi, const CUtensorMap& tw, const CUtensorMap& tx,
         return cudaErrorInvalidValue;
     const int num_kb = p.K / BK, kps = (num_kb + p.splits - 1) / p.splits;
     if ((p.splits - 1) * kps >= num_kb) return cudaErrorInvalidValue;      // an empty split would hang its cluster
+    if (p.ln_x && (p.B > kLnMaxB || p.NB != 16 || p.K > kLnMaxJ * 256 || kps > kStagesLn || !p.ln_gamma || !p.ln_beta ||
+                   epi == SK_BIAS_RESID_F16))
+        return cudaErrorInvalidValue;
     switch (epi) {
         case SK_BIAS_BF16: return launch_epi<SK_BIAS_BF16>(tw, tx, p, stream);
         case SK_BIAS_GELU_BF16: return launch_epi<SK_BIAS_GELU_BF16>(tw, tx, p, stream);
