@@ -391,3 +391,32 @@ def test_fused_and_unfused_layernorm_paths_agree(monkeypatch):
     a, b = torch.from_numpy(outs["1"][1]), torch.from_numpy(outs["0"][1])
     assert (a - b).abs().max().item() <= 0.02 * b.abs().max().item()
     assert [r.sequences_ids[0][:10] for r in outs["1"][0]] == [r.sequences_ids[0][:10] for r in outs["0"][0]]
+
+
+def test_scheduler_transcribe_worker_returns_token_rows():
+    """ChunkScheduler + gpu_transcribe_worker: PCM windows in, token rows out (prompt, sampled ids, EOT padding, count
+    in column 0), in window order, equal to encode_audio + generate called directly; ragged last micro-batch."""
+    from oracle import synth as osynth
+    from whisper_aries_b200 import ChunkScheduler, WhisperModel, gpu_transcribe_worker, synthetic
+    eshape, dshape = synthetic.SHAPES["micro"], synthetic.DEC_SHAPES["micro"]
+    w = dict(synthetic.encoder_weights(eshape, 1234))
+    w.update(synthetic.decoder_weights(dshape, 4330))
+    model = WhisperModel(eshape, w, device="cuda", device_index=0, decoder_shape=dshape, max_batch=4)
+    tok = model.decoder.tokens
+    prompt = [tok.sot, tok.first_lang, tok.transcribe]
+    L = 20
+    pcm = osynth.batch_signals(5, 3)
+    out = np.zeros((5, L + 1), dtype=np.int32)
+    res = ChunkScheduler([gpu_transcribe_worker(model, prompt, max_length=L, micro_batch=2, suppress_tokens=[])]).run(pcm, out)
+    assert all(r.success for r in res), [r.error for r in res]
+    direct = []                    # the same micro-batches, so that every kernel sees the same shapes: bit-identical
+    for a in range(0, 5, 2):
+        x = torch.from_numpy(pcm[a:a + 2]).cuda()
+        direct += model.generate(model.encode_audio(x), [prompt] * x.shape[0], max_length=L, suppress_tokens=[])
+    for i, r in enumerate(direct):
+        ids = r.sequences_ids[0]
+        assert out[i, 0] == len(ids) and out[i, 1:4].tolist() == prompt
+        assert out[i, 4:4 + len(ids)].tolist() == ids and (out[i, 4 + len(ids):] == tok.eot).all()
+    bad = np.zeros((5, 7), dtype=np.int32)
+    res = ChunkScheduler([gpu_transcribe_worker(model, prompt, max_length=L, micro_batch=2)]).run(pcm, bad)
+    assert not res[0].success and "int32" in res[0].error       # reported per shard, as the reference does (ref: :355-365)

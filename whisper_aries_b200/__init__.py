@@ -6,10 +6,10 @@ from . import ct2_model
 from .decoder import WhisperDecoder, WhisperGenerationResult
 from .encoder import WhisperEncoder, WhisperModel
 from .feature_extractor import FeatureExtractor
-from .scheduler import (ChunkResult, ChunkScheduler, ChunkWork, chunk_windows, partition_windows,
-                        plan_reference_chunks)
+from .scheduler import (ChunkResult, ChunkScheduler, ChunkWork, chunk_windows, gpu_transcribe_worker, gpu_worker,
+                        partition_windows, plan_reference_chunks)
 from .synthetic import DEC_SHAPES, SHAPES, DecoderShape, EncoderShape, WhisperTokens
 
 __all__ = ["FeatureExtractor", "WhisperEncoder", "WhisperModel", "ChunkScheduler", "ChunkWork", "ChunkResult",
-           "partition_windows", "plan_reference_chunks", "chunk_windows", "SHAPES", "EncoderShape", "ct2_model", "WhisperDecoder", "WhisperGenerationResult", "DEC_SHAPES",
+           "partition_windows", "plan_reference_chunks", "chunk_windows", "gpu_worker", "gpu_transcribe_worker", "SHAPES", "EncoderShape", "ct2_model", "WhisperDecoder", "WhisperGenerationResult", "DEC_SHAPES",
            "DecoderShape", "WhisperTokens"]

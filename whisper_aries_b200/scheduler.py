@@ -195,3 +195,48 @@ def gpu_worker(model, micro_batch: int = 16) -> Worker:
         comp.synchronize()
 
     return run
+
+
+def gpu_transcribe_worker(model, prompt: Sequence[int], max_length: int = 448, micro_batch: int = 16, **generate_kw) -> Worker:
+    """Worker for one GPU that goes all the way to token ids: PCM -> log-mel -> encoder -> greedy
+    ``generate`` with the encoder states staying in HBM -- the 3.84 MB per window that ``gpu_worker`` gathers to the host
+    (the first scaling risk SURVEY.md 8e names) becomes ``max_length`` int32 per window.
+
+    ``out`` is an int32 array / tensor ``[n_windows, max_length + 1]``: column 0 = number of sampled ids (before EOT),
+    columns 1.. = the prompt followed by the sampled ids and EOT padding (what ``aries_decoder_generate`` returns)."""
+    import torch
+
+    if model.decoder is None:
+        raise ValueError("gpu_transcribe_worker needs a WhisperModel built with decoder weights (decoder_shape=...)")
+    dev = model.encoder.device
+    prompt = [int(t) for t in prompt]
+    P = len(prompt)
+    eot = model.decoder.tokens.eot
+    state = {}
+
+    def run(windows, start: int, stop: int, out) -> None:
+        torch.cuda.set_device(dev)
+        n_s = int(windows.shape[1])
+        if state.get("n_s") != n_s:
+            state["n_s"] = n_s
+            state["buf"] = torch.empty((micro_batch, n_s), dtype=torch.float32, device=dev)
+        wt = windows if isinstance(windows, torch.Tensor) else torch.from_numpy(windows)
+        ot = out if isinstance(out, torch.Tensor) else torch.from_numpy(out)
+        L = min(int(max_length), model.decoder.shape.n_text_ctx)
+        if ot.shape[1] != L + 1 or ot.dtype != torch.int32:
+            raise ValueError(f"out must be int32 [n_windows, {L + 1}]")
+        for s in range(start, stop, micro_batch):
+            e = min(s + micro_batch, stop)
+            buf = state["buf"][: e - s]
+            buf.copy_(wt[s:e], non_blocking=True)
+            enc = model.encode_audio(buf)
+            res = model.decoder.generate(enc, [prompt] * (e - s), max_length=L, **generate_kw)
+            for i, r in enumerate(res):
+                ids = r.sequences_ids[0]
+                row = ot[s + i]
+                row[0] = len(ids)
+                row[1:1 + P] = torch.tensor(prompt, dtype=torch.int32)
+                row[1 + P:1 + P + len(ids)] = torch.tensor(ids, dtype=torch.int32) if ids else torch.empty(0, dtype=torch.int32)
+                row[1 + P + len(ids):] = eot
+
+    return run
