@@ -123,6 +123,11 @@ ARIES_API int aries_encoder_run_host(aries_encoder* enc, const float* mel_host, 
 ARIES_API int aries_encode_pcm(aries_encoder* enc, aries_mel* mel, const float* pcm_dev, int batch, int64_t n_samples,
                      int64_t pcm_stride, void* out_dev, void* workspace, size_t workspace_bytes, void* stream);
 
+/* PCM staging (row f3, additive): int16 samples (what ffmpeg's pcm_s16le decode yields, ref: utils.py:116) -> float32 / 32768,
+ * the conversion faster-whisper's decode_audio does on the host, here on the device so that the host->device copy of the hot
+ * path carries 2 bytes per sample.  pcm_s16_dev / out_dev: device pointers, n samples; stream-ordered. */
+ARIES_API int aries_pcm_s16_to_f32(aries_ctx* ctx, const int16_t* pcm_s16_dev, float* out_dev, int64_t n, void* stream);
+
 /* Number of kernels the last aries_logmel_run / aries_encoder_run / aries_encode_pcm on this handle launched. */
 ARIES_API int aries_logmel_last_launches(const aries_mel* mel);
 ARIES_API int aries_encoder_last_launches(const aries_encoder* enc);

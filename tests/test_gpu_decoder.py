@@ -420,3 +420,27 @@ def test_scheduler_transcribe_worker_returns_token_rows():
     bad = np.zeros((5, 7), dtype=np.int32)
     res = ChunkScheduler([gpu_transcribe_worker(model, prompt, max_length=L, micro_batch=2)]).run(pcm, bad)
     assert not res[0].success and "int32" in res[0].error       # reported per shard, as the reference does (ref: :355-365)
+
+
+def test_decode_to_the_last_position():
+    """max_length = n_text_ctx = 448: the self-attention cache is filled to its last row.  Free-run to get a sequence,
+    then teacher-force it and compare the logits deep into the sequence with the oracle's single full-prefix pass."""
+    shape, tok, otok, enc, dec, oracle, wd = _setup("micro", 2, 23)
+    prompt = [tok.sot, tok.first_lang, tok.transcribe, tok.no_timestamps]
+    L = shape.n_text_ctx
+    res = dec.generate(enc.cuda(), [prompt] * 2, max_length=L, suppress_tokens=[tok.eot])
+    assert all(len(r.sequences_ids[0]) == L - len(prompt) for r in res)
+    assert dec.last_stats()["steps"] == L - 1
+    forced = [r.sequences_ids[0] for r in res]
+    res2, extras = dec.generate(enc.cuda(), [prompt] * 2, max_length=L, suppress_tokens=[tok.eot], _forced=forced,
+                                _want_logits=True)
+    assert [r.sequences_ids[0] for r in res2] == forced
+    seqs = torch.tensor([prompt + f for f in forced])[:, :L - 1]
+    ref = oracle.logits(seqs, enc.float())
+    logits = torch.from_numpy(extras[0]["logits"]).transpose(0, 1)
+    for t in (3, 64, 65, 200, 446):
+        for b in range(2):
+            cos = torch.nn.functional.cosine_similarity(logits[b, t], ref[b, t], dim=0).item()
+            assert cos >= 0.9995, f"window {b} step {t}: logits cosine {cos}"
+    # the raw argmax of the graph run and of the stream run (logits download) agree everywhere: same kernels, same bits
+    assert np.array_equal(extras[0]["argmax"][:, len(prompt):], np.array(forced))

@@ -109,3 +109,35 @@ def test_attention(ctx, cfg):
     qf, kf, vf = (t.bfloat16().float().permute(0, 2, 1, 3) for t in (q, k, v))
     ref = (torch.softmax(qf @ kf.transpose(-1, -2) / 8.0, dim=-1) @ vf).permute(0, 2, 1, 3).reshape(B * T, d)
     assert (out.float() - ref).abs().max().item() <= 0.03          # P and the output are rounded to bf16
+
+
+@pytest.mark.parametrize("n", [1, 7, 8, 4096 + 3, 480000, 64 * 480000])
+def test_pcm_s16_to_f32_is_exact(n):
+    """Row f3: the device-side int16 -> float32 / 32768 conversion equals numpy's, bit for bit (also ragged lengths and an
+    unaligned view), at the bench size (64 windows)."""
+    import numpy as np
+    from whisper_aries_b200 import pcm_s16_to_f32
+    rng = np.random.default_rng(n)
+    x = rng.integers(-32768, 32768, size=n + 1, dtype=np.int16)
+    x[:2] = [-32768, 32767]
+    xd = torch.from_numpy(x).cuda()
+    got = pcm_s16_to_f32(xd[:n])
+    assert np.array_equal(got.cpu().numpy(), x[:n].astype(np.float32) / 32768.0)
+    got = pcm_s16_to_f32(xd[1:])                 # 2-byte aligned only: scalar kernel
+    assert np.array_equal(got.cpu().numpy(), x[1:].astype(np.float32) / 32768.0)
+
+
+def test_scheduler_accepts_int16_windows():
+    """gpu_worker with int16 PCM gives the same encoder states as with the float32 conversion done on the host."""
+    import numpy as np
+    from oracle import synth as osynth
+    from whisper_aries_b200 import ChunkScheduler, WhisperModel, gpu_worker, synthetic
+    shape = synthetic.SHAPES["micro"]
+    model = WhisperModel(shape, synthetic.encoder_weights(shape, 1234), device="cuda", device_index=0)
+    pcm16 = np.clip(np.round(osynth.batch_signals(5, 0) * 32768.0), -32768, 32767).astype(np.int16)
+    out16 = torch.empty((5, shape.n_ctx, shape.d_model), dtype=torch.bfloat16).pin_memory()
+    out32 = torch.empty_like(out16).pin_memory()
+    sched = ChunkScheduler([gpu_worker(model, micro_batch=2)])
+    assert all(r.success for r in sched.run(torch.from_numpy(pcm16).pin_memory(), out16))
+    assert all(r.success for r in sched.run(torch.from_numpy(pcm16.astype(np.float32) / 32768.0).pin_memory(), out32))
+    assert torch.equal(out16, out32)

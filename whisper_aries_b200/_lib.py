@@ -65,6 +65,7 @@ PROTOTYPES = {
     "aries_encode_pcm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_size_t,
                                  c_void_p]),
     "aries_encoder_last_launches": (c_int, [c_void_p]),
+    "aries_pcm_s16_to_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "aries_encoder_set_profiling": (c_int, [c_void_p, c_int]),
     "aries_encoder_collect_profile": (c_int, [c_void_p, c_float_p, ctypes.POINTER(c_int), c_int]),
     "aries_decoder_create": (c_int, [c_void_p, ctypes.POINTER(DecoderCfg), ctypes.POINTER(WeightDesc), c_int, c_int,

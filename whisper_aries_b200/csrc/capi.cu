@@ -352,6 +352,16 @@ int aries_encode_pcm(aries_encoder* enc, aries_mel* mel, const float* pcm_dev, i
     return aries_encoder_run(enc, mel_buf, batch, 3000, out_dev, workspace, workspace_bytes, stream);
 }
 
+int aries_pcm_s16_to_f32(aries_ctx* ctx, const int16_t* pcm_s16_dev, float* out_dev, int64_t n, void* stream) {
+    int rc = use(ctx);
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!pcm_s16_dev || !out_dev))) return fail(ARIES_EINVAL, "aries_pcm_s16_to_f32: NULL buffer or negative length");
+    cudaError_t e = aries::pcm_s16_to_f32(reinterpret_cast<const short*>(pcm_s16_dev), out_dev, n, ctx->sm_count,
+                                          static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail_cuda("aries_pcm_s16_to_f32", e);
+    return ARIES_OK;
+}
+
 int aries_encoder_last_launches(const aries_encoder* enc) {
     return (enc && enc->magic == kMagicEnc) ? aries::encoder_plan_last_launches(enc->plan) : -1;
 }

@@ -28,4 +28,7 @@ cudaError_t mel_to_time_major(const float* mel, int batch, int n_mels, int frame
 
 void logmel_host_tables(mel::Tables* tb);
 
+// pcm.cu: s16 PCM -> f32 / 32768 on the device (row f3)
+cudaError_t pcm_s16_to_f32(const short* in, float* out, long long n, int sm_count, cudaStream_t stream);
+
 }  // namespace aries

@@ -47,9 +47,9 @@ __device__ __forceinline__ uint32_t dsmem_addr(uint32_t local_addr, uint32_t ran
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(rank));
     return remote;
 }
-__device__ __forceinline__ float ld_dsmem_f32(uint32_t remote) {
-    float v;
-    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote));
+__device__ __forceinline__ float4 ld_dsmem_f32x4(uint32_t remote) {
+    float4 v;
+    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(remote));
     return v;
 }
 
@@ -78,6 +78,59 @@ __device__ __forceinline__ void store_one(const SkinnyParams& p, int b, int n, f
     } else {
         reinterpret_cast<__nv_bfloat16*>(p.out)[at] = __float2bfloat16_rn(v);
     }
+}
+
+// Four consecutive output features of one sequence (n % 4 == 0): vector loads / stores when the row pitch allows it.
+template <int EPI>
+__device__ __forceinline__ float4 load_resid4(const SkinnyParams& p, int b, int n) {
+    if (EPI != SK_BIAS_RESID_F16) return make_float4(0, 0, 0, 0);
+    if (n + 3 < p.N && (p.ldo & 3) == 0) {
+        const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(p.out) + (size_t)b * p.ldo + n);
+        const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+        const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+        return make_float4(lo.x, lo.y, hi.x, hi.y);
+    }
+    float r[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) r[e] = (n + e < p.N) ? load_resid<EPI>(p, b, n + e) : 0.0f;
+    return make_float4(r[0], r[1], r[2], r[3]);
+}
+
+template <int EPI>
+__device__ __forceinline__ void store_four(const SkinnyParams& p, int b, int n, float4 v, float4 resid) {
+    if (n + 3 < p.N && (p.ldo & 3) == 0) {
+        const size_t at = (size_t)b * p.ldo + n;
+        if (EPI == SK_LOGITS_F32) {
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + at) = v;
+            return;
+        }
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+        v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+        if (EPI == SK_BIAS_GELU_BF16) {
+            v.x = 0.5f * v.x * (1.0f + erff(v.x * 0.70710678118654752f));
+            v.y = 0.5f * v.y * (1.0f + erff(v.y * 0.70710678118654752f));
+            v.z = 0.5f * v.z * (1.0f + erff(v.z * 0.70710678118654752f));
+            v.w = 0.5f * v.w * (1.0f + erff(v.w * 0.70710678118654752f));
+        }
+        uint2 q;
+        if (EPI == SK_BIAS_RESID_F16) {
+            const float kMax = 65504.0f;
+            const __half2 lo = __floats2half2_rn(fminf(fmaxf(v.x + resid.x, -kMax), kMax), fminf(fmaxf(v.y + resid.y, -kMax), kMax));
+            const __half2 hi = __floats2half2_rn(fminf(fmaxf(v.z + resid.z, -kMax), kMax), fminf(fmaxf(v.w + resid.w, -kMax), kMax));
+            q.x = *reinterpret_cast<const unsigned*>(&lo);
+            q.y = *reinterpret_cast<const unsigned*>(&hi);
+            *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.out) + at) = q;
+        } else {
+            q.x = pack_bf16x2(v.x, v.y);
+            q.y = pack_bf16x2(v.z, v.w);
+            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + at) = q;
+        }
+        return;
+    }
+    const float vv[4] = {v.x, v.y, v.z, v.w}, rr[4] = {resid.x, resid.y, resid.z, resid.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+        if (n + e < p.N) store_one<EPI>(p, b, n + e, vv[e], rr[e]);
 }
 
 template <int EPI, bool LN>
@@ -299,34 +352,40 @@ skinny_gemm_tcgen05(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
     if (p.splits > 1) {
         cluster_sync_all();                         // every CTA's partial tile is in its shared memory
         if (warp >= 2) {
-            const int quarter = warp & 3;
-            const int nl = quarter * 32 + lane;
-            const int n = n0 + nl;
-            // peers' tiles through distributed shared memory: all loads of a sequence are issued before the first add
-            // (a chain of dependent remote loads costs ~0.2 us each: 13 us for 64 sequences)
+            // Peers' tiles through distributed shared memory, 16 bytes per load: thread (n4, bsel) owns four consecutive
+            // output features of every fourth sequence of this CTA's share (b = split + splits * i), and issues all the
+            // loads of two sequences -- up to 16 -- before the first add (a chain of dependent scalar remote loads cost
+            // 13 us for 64 sequences).  Summation order over the splits is fixed: bit-reproducible.
+            const int et = threadIdx.x - 64;
+            const int n4 = et & 31, bsel = et >> 5;
+            const int n = n0 + 4 * n4;
             uint32_t peer[kMaxSplits];
 #pragma unroll
-            for (int s = 0; s < kMaxSplits; ++s) peer[s] = dsmem_addr(base + (uint32_t)nl * 4u, (uint32_t)(s < p.splits ? s : 0));
-            for (int b = split; b < p.B; b += 2 * p.splits) {      // two sequences per round: 16 remote loads in flight
-                const int b2 = b + p.splits;
+            for (int s = 0; s < kMaxSplits; ++s) peer[s] = dsmem_addr(base + (uint32_t)n4 * 16u, (uint32_t)(s < p.splits ? s : 0));
+            for (int i = bsel; split + p.splits * i < p.B; i += 8) {
+                const int b = split + p.splits * i;
+                const int b2 = split + p.splits * (i + 4);
                 const bool has2 = b2 < p.B;
-                const float r1 = (n < p.N) ? load_resid<EPI>(p, b, n) : 0.0f;
-                const float r2 = (n < p.N && has2) ? load_resid<EPI>(p, b2, n) : 0.0f;
-                float v[kMaxSplits], w[kMaxSplits];
+                float4 r1 = make_float4(0, 0, 0, 0), r2 = r1;
+                if (n < p.N) {
+                    r1 = load_resid4<EPI>(p, b, n);
+                    if (has2) r2 = load_resid4<EPI>(p, b2, n);
+                }
+                float4 v[kMaxSplits], w[kMaxSplits];
 #pragma unroll
                 for (int s = 0; s < kMaxSplits; ++s) {
-                    v[s] = (s < p.splits) ? ld_dsmem_f32(peer[s] + (uint32_t)(b * BMW) * 4u) : 0.0f;
-                    w[s] = (s < p.splits && has2) ? ld_dsmem_f32(peer[s] + (uint32_t)(b2 * BMW) * 4u) : 0.0f;
+                    v[s] = (s < p.splits) ? ld_dsmem_f32x4(peer[s] + (uint32_t)(b * BMW) * 4u) : make_float4(0, 0, 0, 0);
+                    w[s] = (s < p.splits && has2) ? ld_dsmem_f32x4(peer[s] + (uint32_t)(b2 * BMW) * 4u) : make_float4(0, 0, 0, 0);
                 }
-                float sum = 0.0f, sum2 = 0.0f;
+                float4 sum = make_float4(0, 0, 0, 0), sum2 = sum;
 #pragma unroll
-                for (int s = 0; s < kMaxSplits; ++s) {                 // fixed order: bit-reproducible
-                    sum += v[s];
-                    sum2 += w[s];
+                for (int s = 0; s < kMaxSplits; ++s) {
+                    sum.x += v[s].x; sum.y += v[s].y; sum.z += v[s].z; sum.w += v[s].w;
+                    sum2.x += w[s].x; sum2.y += w[s].y; sum2.z += w[s].z; sum2.w += w[s].w;
                 }
                 if (n < p.N) {
-                    store_one<EPI>(p, b, n, sum, r1);
-                    if (has2) store_one<EPI>(p, b2, n, sum2, r2);
+                    store_four<EPI>(p, b, n, sum, r1);
+                    if (has2) store_four<EPI>(p, b2, n, sum2, r2);
                 }
             }
         }

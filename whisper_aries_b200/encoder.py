@@ -184,6 +184,26 @@ class WhisperModel:
     def encode(self, features):
         return self.encoder.encode(features)
 
-    def encode_audio(self, pcm):
-        """PCM windows (CUDA f32 ``[B, <=480000]``) -> encoder states, fused on the device."""
-        return self.encoder.encode_pcm(self.feature_extractor, pcm)
+    def encode_audio(self, pcm, out=None):
+        """PCM windows (CUDA f32, or int16 as decoded by ffmpeg, ``[B, <=480000]``) -> encoder states, fused on the
+        device.  int16 input is converted on the GPU (``/ 32768`` as faster-whisper's ``decode_audio`` does on the host)."""
+        import torch
+        if isinstance(pcm, torch.Tensor) and pcm.dtype == torch.int16:
+            pcm = pcm_s16_to_f32(pcm)
+        return self.encoder.encode_pcm(self.feature_extractor, pcm, out=out)
+
+
+def pcm_s16_to_f32(pcm_s16, out=None):
+    """CUDA int16 tensor -> CUDA float32 tensor of the same shape, ``x / 32768`` (``aries_pcm_s16_to_f32``)."""
+    import torch
+    if not (isinstance(pcm_s16, torch.Tensor) and pcm_s16.is_cuda and pcm_s16.dtype == torch.int16):
+        raise ValueError("pcm_s16_to_f32 expects a CUDA int16 tensor")
+    x = pcm_s16.contiguous()
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+    elif out.shape != x.shape or out.dtype != torch.float32 or not out.is_contiguous() or out.device != x.device:
+        raise ValueError("out must be a contiguous CUDA float32 tensor of the input's shape")
+    ctx = _lib.Context.get(x.device.index or 0)
+    stream = torch.cuda.current_stream(x.device).cuda_stream
+    _lib.check(ctx.lib.aries_pcm_s16_to_f32(ctx.handle, x.data_ptr(), out.data_ptr(), x.numel(), stream))
+    return out

@@ -148,7 +148,9 @@ class ChunkScheduler:
 
 def gpu_worker(model, micro_batch: int = 16) -> Worker:
     """Worker for one GPU: pinned staging, H2D on a side stream double-buffered against compute, fused
-    PCM -> mel -> encoder on the device, D2H of the bf16 states into the caller's (pinned) output rows."""
+    PCM -> mel -> encoder on the device, D2H of the bf16 states into the caller's (pinned) output rows.
+    ``windows`` may be float32 or int16 (ffmpeg's pcm_s16le, ref: utils.py:116): int16 halves the H2D bytes and is
+    converted on the GPU."""
     import torch
 
     dev = model.encoder.device
@@ -158,9 +160,12 @@ def gpu_worker(model, micro_batch: int = 16) -> Worker:
     def run(windows, start: int, stop: int, out) -> None:
         torch.cuda.set_device(dev)
         n_s = int(windows.shape[1])
-        if "bufs" not in state or state["n_s"] != n_s:
-            state["n_s"] = n_s
-            state["bufs"] = [torch.empty((micro_batch, n_s), dtype=torch.float32, device=dev) for _ in range(2)]
+        wt = windows if isinstance(windows, torch.Tensor) else torch.from_numpy(windows)
+        if wt.dtype not in (torch.float32, torch.int16):
+            raise ValueError("windows must be float32 or int16 PCM")
+        if "bufs" not in state or state["n_s"] != n_s or state["dtype"] != wt.dtype:
+            state["n_s"], state["dtype"] = n_s, wt.dtype
+            state["bufs"] = [torch.empty((micro_batch, n_s), dtype=wt.dtype, device=dev) for _ in range(2)]
             state["outs"] = [torch.empty((micro_batch, t, d), dtype=torch.bfloat16, device=dev) for _ in range(2)]
             state["copy"] = torch.cuda.Stream(dev)
             state["comp"] = torch.cuda.Stream(dev)
@@ -168,7 +173,6 @@ def gpu_worker(model, micro_batch: int = 16) -> Worker:
             state["comp_done"] = [torch.cuda.Event() for _ in range(2)]
             state["d2h_done"] = [torch.cuda.Event() for _ in range(2)]
         copy, comp = state["copy"], state["comp"]
-        wt = windows if isinstance(windows, torch.Tensor) else torch.from_numpy(windows)
         ot = out if isinstance(out, torch.Tensor) else torch.from_numpy(out)
         if ot.dtype != torch.bfloat16:
             ot = ot.view(torch.bfloat16)
@@ -185,7 +189,7 @@ def gpu_worker(model, micro_batch: int = 16) -> Worker:
                 comp.wait_event(state["h2d_done"][i])
                 if k >= 2:
                     comp.wait_event(state["d2h_done"][i])       # out buffer i drained by step k-2's D2H
-                model.encoder.encode_pcm(model.feature_extractor, state["bufs"][i][: e - s], out=state["outs"][i][: e - s])
+                model.encode_audio(state["bufs"][i][: e - s], out=state["outs"][i][: e - s])
                 state["comp_done"][i].record(comp)
             with torch.cuda.stream(copy):
                 copy.wait_event(state["comp_done"][i])
