@@ -134,9 +134,43 @@ def reference_backend():
         sys.path.pop(0)
 
 
+def run_reference_decode(args, world: int) -> int:
+    """--impl reference --mode decode: the oracle decoder (fp32 torch, all host threads) greedy-decoding one window."""
+    import torch
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    n = 24
+    for _ in range(max(1, args.warmup)):
+        cpu_decode_sample(args.model, 4)
+    t0 = time.perf_counter()
+    toks = 0
+    for _ in range(args.steps):
+        tps, dt = cpu_decode_sample(args.model, n)
+        toks += n
+    dt = time.perf_counter() - t0
+    value = toks / dt
+    sample = (f"1 window x {n} sampled tokens per step: oracle fp32 decoder (torch CPU, whole prefix recomputed per token), "
+              f"{args.model} shape, random-init weights; ctranslate2 importable: "
+              f"{reference_backend() == 'reference'}")
+    line = {"impl": "reference", "metric": f"decoded tokens/sec (greedy generate, {args.model} decoder)", "value": value,
+            "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.model} decoder, greedy generate (reference arm: bounded sample of 1 window x {n} "
+                                   "tokens per step on the host CPU)", "windows_per_gpu": args.windows,
+                       "tokens_per_window": args.tokens},
+            "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
 def run_reference(args, rank: int, world: int) -> int:
     if rank != 0:
         return 0
+    if args.mode == "decode":
+        return run_reference_decode(args, world)
     import torch
     kind = reference_backend()
     # torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm is rank 0 alone and owns the host
@@ -175,13 +209,18 @@ def cpu_decode_sample(model: str, n_tokens: int):
     from whisper_aries_b200 import synthetic
     shape = osynth.DEC_SHAPES[model]
     tok = osynth.WhisperTokens.for_vocab(shape.vocab)
-    dec = wd.Decoder(synthetic.decoder_weights_fast(synthetic.DEC_SHAPES[model], 0), shape)
+    dec = cpu_decode_sample.cache.get(model)
+    if dec is None:                                             # weights are drawn once, outside every timed region
+        dec = cpu_decode_sample.cache[model] = wd.Decoder(synthetic.decoder_weights_fast(synthetic.DEC_SHAPES[model], 0), shape)
     enc = torch.randn(1, shape.n_audio_ctx, shape.d_model)
     prompt = [tok.sot, tok.first_lang, tok.transcribe]
     t0 = time.perf_counter()
     res = wd.generate(dec, enc, [prompt], tok, wd.GenerateOptions(max_length=len(prompt) + n_tokens, suppress_tokens=[tok.eot]))
     dt = time.perf_counter() - t0
     return len(res[0]["sequences_ids"]) / dt, dt
+
+
+cpu_decode_sample.cache = {}
 
 
 def run_decode(args, rank: int, local_rank: int, world: int) -> int:

@@ -98,6 +98,24 @@ if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "err"
     if what == "err":
         err()
+    elif what == "pdlmask":
+        # which kernel classes should take a programmatic edge at a given batch (ARIES_DECODE_PDL_MASK)
+        from whisper_aries_b200 import WhisperDecoder, synthetic
+        shape = synthetic.DEC_SHAPES["large-v3"]
+        tok = synthetic.WhisperTokens.for_vocab(shape.vocab)
+        batches = [int(a) for a in sys.argv[2:]] or [64]
+        dec = WhisperDecoder(shape, fast_decoder_weights(shape), tokens=tok, max_batch=max(batches))
+        prompt = [tok.sot, tok.first_lang, tok.transcribe]
+        os.environ["ARIES_DECODE_GRAPH"] = "1"
+        os.environ["ARIES_DECODE_PDL"] = "1"
+        for B in batches:
+            enc = torch.randn(B, shape.n_audio_ctx, shape.d_model, device="cuda").bfloat16()
+            for mask in range(8):
+                os.environ["ARIES_DECODE_PDL_MASK"] = str(mask)
+                for _ in range(2):
+                    dec.generate(enc, [prompt] * B, max_length=64 + len(prompt), suppress_tokens=[tok.eot])
+                    st = dec.last_stats()
+                print(f"B={B} pdl mask {mask} (1 gemm, 2 attention, 4 rest): {st['decode_ms'] / st['steps']:.3f} ms/step", flush=True)
     elif what == "prof":
         prof(int(sys.argv[2]) if len(sys.argv) > 2 else 64)
     else:

@@ -51,7 +51,7 @@ struct DecLayerW {
 
 struct GraphKey {
     int batch, prompt_len, max_length, suppress_blank, blank_id, eot, no_speech, no_timestamps, timestamp_begin,
-        max_initial, n_forced, want_argmax, pdl, fuse_ln;
+        max_initial, n_forced, want_argmax, pdl, fuse_ln, pdl_mask;
     bool operator==(const GraphKey& o) const { return std::memcmp(this, &o, sizeof(GraphKey)) == 0; }
 };
 
@@ -314,13 +314,20 @@ cudaError_t run_step(DecoderPlan* pl, int batch, const SampleParams& sp, int xsp
     const auto& c = pl->cfg;
     const int d = c.d_model, f = c.d_ffn, C = c.n_text_ctx, A = c.n_audio_ctx;
     int n = 0;
+    // Which kernel classes take a programmatic edge: 1 = skinny GEMMs, 2 = attention, 4 = the rest.  Measured per step
+    // (tests/gpu_diag_decode.py pdlmask): 64 windows 4.74 ms with none, 4.50 with 5, 5.72 with 7 -- an attention grid
+    // (1280 CTAs) launched early only holds SM slots while it waits; 16 windows 2.99 / 2.75 / 2.77.
+    // With 1-2 windows every grid is tiny and 7 wins by 3 % (1.55 vs 1.59 ms).  Default: 7 for <= 2 windows, else 5.
+    const char* mask_env = getenv("ARIES_DECODE_PDL_MASK");
+    const int mask = mask_env ? atoi(mask_env) : (batch <= 2 ? 7 : 5);
+    const bool pdl_g = pdl && (mask & 1), pdl_a = pdl && (mask & 2), pdl_o = pdl && (mask & 4);
     // LayerNorm folded into the consuming GEMM's operand load (<= 8 sequences): 3 launches fewer per layer
     auto ln_skinny = [&](int epi, const CUtensorMap& w, int N, const float* g, const float* b, const float* bias, void* out,
                          int ldo) {
         SkinnyParams q{};
         q.B = batch; q.NB = 16; q.N = N; q.K = d;
         q.splits = skinny_pick_splits_ln(N, d, pl->sm_count);
-        q.bias = bias; q.out = out; q.ldo = ldo; q.pdl = pdl;
+        q.bias = bias; q.out = out; q.ldo = ldo; q.pdl = pdl_g;
         q.ln_x = pl->x; q.ln_gamma = g; q.ln_beta = b;
         ++n;
         return skinny_launch(epi, w, w, q, stream);
@@ -330,11 +337,11 @@ cudaError_t run_step(DecoderPlan* pl, int batch, const SampleParams& sp, int xsp
         SkinnyParams q{};
         q.B = batch; q.NB = pl->NB; q.N = N; q.K = K;
         q.splits = skinny_pick_splits(N, K, pl->sm_count);
-        q.bias = bias; q.out = out; q.ldo = ldo; q.pdl = pdl;
+        q.bias = bias; q.out = out; q.ldo = ldo; q.pdl = pdl_g;
         ++n;
         return skinny_launch(epi, w, xin, q, stream);
     };
-    ARIES_TRY(decode_embed_launch(pl->tokens, C, pl->step, pl->emb, pl->pos, pl->x, batch, d, pdl, stream), "embed");
+    ARIES_TRY(decode_embed_launch(pl->tokens, C, pl->step, pl->emb, pl->pos, pl->x, batch, d, pdl_o, stream), "embed");
     ++n;
     const __nv_bfloat16* qkv = reinterpret_cast<const __nv_bfloat16*>(pl->qkv);
     for (int l = 0; l < c.n_layers; ++l) {
@@ -342,7 +349,7 @@ cudaError_t run_step(DecoderPlan* pl, int batch, const SampleParams& sp, int xsp
         if (fuse_ln) {
             ARIES_TRY(ln_skinny(SK_BIAS_BF16, lw.m_qkv, 3 * d, lw.ln1_g, lw.ln1_b, lw.bqkv, pl->qkv, 3 * d), "LN + qkv projection");
         } else {
-            ARIES_TRY(decode_layernorm_launch(pl->x, lw.ln1_g, lw.ln1_b, pl->y, batch, d, pdl, stream), "layer norm 1");
+            ARIES_TRY(decode_layernorm_launch(pl->x, lw.ln1_g, lw.ln1_b, pl->y, batch, d, pdl_o, stream), "layer norm 1");
             ARIES_TRY(skinny(SK_BIAS_BF16, lw.m_qkv, pl->a_y, 3 * d, d, lw.bqkv, pl->qkv, 3 * d), "qkv projection");
             ++n;
         }
@@ -354,13 +361,13 @@ cudaError_t run_step(DecoderPlan* pl, int batch, const SampleParams& sp, int xsp
         a.kv_rows = C; a.kv_ld = d;
         a.new_k = qkv + d; a.new_v = qkv + 2 * d; a.new_ld = 3 * d;
         a.step = pl->step; a.n_keys_fixed = 0;
-        a.out = pl->ctx; a.out_ld = d; a.splits = 1; a.pdl = pdl;
+        a.out = pl->ctx; a.out_ld = d; a.splits = 1; a.pdl = pdl_a;
         ARIES_TRY(decode_attention_launch(a, stream), "self-attention");
         ARIES_TRY(skinny(SK_BIAS_RESID_F16, lw.m_o, pl->a_ctx, d, d, lw.bo, pl->x, d), "self-attention output");
         if (fuse_ln) {
             ARIES_TRY(ln_skinny(SK_BIAS_BF16, lw.m_q2, d, lw.ln2_g, lw.ln2_b, lw.bq2, pl->q2, d), "LN + cross-attention query");
         } else {
-            ARIES_TRY(decode_layernorm_launch(pl->x, lw.ln2_g, lw.ln2_b, pl->y, batch, d, pdl, stream), "layer norm 2");
+            ARIES_TRY(decode_layernorm_launch(pl->x, lw.ln2_g, lw.ln2_b, pl->y, batch, d, pdl_o, stream), "layer norm 2");
             ARIES_TRY(skinny(SK_BIAS_BF16, lw.m_q2, pl->a_y, d, d, lw.bq2, pl->q2, d), "cross-attention query");
             ++n;
         }
@@ -371,22 +378,24 @@ cudaError_t run_step(DecoderPlan* pl, int batch, const SampleParams& sp, int xsp
         x.k = kv; x.v = kv + d; x.kv_rows = A; x.kv_ld = 2 * d;
         x.n_keys_fixed = A;
         x.out = pl->ctx; x.out_ld = d; x.splits = xsplits; x.partial = pl->attn_partial; x.tickets = pl->attn_tickets;
-        x.pdl = pdl;
+        x.pdl = pdl_a;
         ARIES_TRY(decode_attention_launch(x, stream), "cross-attention");
         ARIES_TRY(skinny(SK_BIAS_RESID_F16, lw.m_o2, pl->a_ctx, d, d, lw.bo2, pl->x, d), "cross-attention output");
         if (fuse_ln) {
             ARIES_TRY(ln_skinny(SK_BIAS_GELU_BF16, lw.m_fc1, f, lw.ln3_g, lw.ln3_b, lw.b1, pl->h, f), "LN + fc1");
         } else {
-            ARIES_TRY(decode_layernorm_launch(pl->x, lw.ln3_g, lw.ln3_b, pl->y, batch, d, pdl, stream), "layer norm 3");
+            ARIES_TRY(decode_layernorm_launch(pl->x, lw.ln3_g, lw.ln3_b, pl->y, batch, d, pdl_o, stream), "layer norm 3");
             ARIES_TRY(skinny(SK_BIAS_GELU_BF16, lw.m_fc1, pl->a_y, f, d, lw.b1, pl->h, f), "fc1");
             ++n;
         }
         ARIES_TRY(skinny(SK_BIAS_RESID_F16, lw.m_fc2, pl->a_h, d, f, lw.b2, pl->x, d), "fc2");
         n += 2;
     }
-    ARIES_TRY(decode_layernorm_launch(pl->x, pl->lnf_g, pl->lnf_b, pl->y, batch, d, pdl, stream), "final layer norm");
+    ARIES_TRY(decode_layernorm_launch(pl->x, pl->lnf_g, pl->lnf_b, pl->y, batch, d, pdl_o, stream), "final layer norm");
     ARIES_TRY(skinny(SK_LOGITS_F32, pl->m_proj, pl->a_y, c.vocab, d, nullptr, pl->logits, pl->v_pad), "logits");
-    ARIES_TRY(decode_sample_launch(sp, stream), "sampling");
+    SampleParams sp2 = sp;
+    sp2.pdl = pdl_o;
+    ARIES_TRY(decode_sample_launch(sp2, stream), "sampling");
     n += 2;                       // (final LayerNorm + sampling; the skinny lambdas count themselves)
     *launches = n;
     return cudaSuccess;
@@ -504,16 +513,15 @@ cudaError_t decoder_generate(DecoderPlan* pl, const void* enc_out, int batch, co
                          skinny_pick_splits_ln(3 * d, d, pl->sm_count) > 0 && skinny_pick_splits_ln(d, d, pl->sm_count) > 0 &&
                          skinny_pick_splits_ln(c.d_ffn, d, pl->sm_count) > 0;
     const bool use_graph = env_on("ARIES_DECODE_GRAPH", true) && !o.logits_out;
-    // programmatic dependent launch pays while the step is latency-bound (measured: -10 % per step up to 32 sequences,
-    // +12 % at 64, where every kernel fills the machine and early-launched dependents only take SM slots)
-    bool pdl = env_on("ARIES_DECODE_PDL", batch <= 32);
+    // programmatic dependent launch (GEMMs and the small kernels; see run_step): -5 .. -12 % per step at every batch size
+    bool pdl = env_on("ARIES_DECODE_PDL", true);
     sp.pdl = pdl;
     int per_step = 0;
 
     if (use_graph) {
         GraphKey key{batch, prompt_len, o.max_length, o.suppress_blank, o.blank_id, o.eot, o.no_speech, o.no_timestamps,
                      o.timestamp_begin, o.max_initial_timestamp_index, o.n_forced, o.argmax_out ? 1 : 0, pdl ? 1 : 0,
-                     fuse_ln ? 1 : 0};
+                     fuse_ln ? 1 : 0, getenv("ARIES_DECODE_PDL_MASK") ? atoi(getenv("ARIES_DECODE_PDL_MASK")) : -1};
         if (!pl->graph || !(key == pl->graph_key)) {
             if (pl->graph) {
                 cudaGraphExecDestroy(pl->graph);
