@@ -89,9 +89,12 @@ struct DecoderPlan {
     unsigned *ticket = nullptr, *suppress_bits = nullptr, *attn_tickets = nullptr;
     float *score = nullptr, *nsp = nullptr, *attn_partial = nullptr;
     int* h_ndone = nullptr;                          // pinned
-    cudaGraphExec_t graph = nullptr;
-    GraphKey graph_key{};
-    bool graph_pdl = false;
+    struct GraphEntry {
+        GraphKey key;
+        cudaGraphExec_t exec;
+        int per_step;
+    };
+    std::vector<GraphEntry> graphs;                  // one step graph per (batch, prompt length, options); <= 8 kept
     cudaStream_t ds = nullptr;                       // decoding stream (graph capture needs a non-default stream)
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     float stats[5] = {0, 0, 0, 0, 0};
@@ -105,7 +108,7 @@ void decoder_plan_last_stats(const DecoderPlan* pl, float out[5]) { std::memcpy(
 
 void decoder_plan_destroy(DecoderPlan* pl) {
     if (!pl) return;
-    if (pl->graph) cudaGraphExecDestroy(pl->graph);
+    for (auto& g : pl->graphs) cudaGraphExecDestroy(g.exec);
     for (auto& e : pl->ev)
         if (e) cudaEventDestroy(e);
     if (pl->ds) cudaStreamDestroy(pl->ds);
@@ -518,25 +521,28 @@ cudaError_t decoder_generate(DecoderPlan* pl, const void* enc_out, int batch, co
     sp.pdl = pdl;
     int per_step = 0;
 
+    cudaGraphExec_t graph = nullptr;
     if (use_graph) {
         GraphKey key{batch, prompt_len, o.max_length, o.suppress_blank, o.blank_id, o.eot, o.no_speech, o.no_timestamps,
                      o.timestamp_begin, o.max_initial_timestamp_index, o.n_forced, o.argmax_out ? 1 : 0, pdl ? 1 : 0,
                      fuse_ln ? 1 : 0, getenv("ARIES_DECODE_PDL_MASK") ? atoi(getenv("ARIES_DECODE_PDL_MASK")) : -1};
-        if (!pl->graph || !(key == pl->graph_key)) {
-            if (pl->graph) {
-                cudaGraphExecDestroy(pl->graph);
-                pl->graph = nullptr;
+        for (auto& g : pl->graphs)
+            if (g.key == key) {
+                graph = g.exec;
+                per_step = g.per_step;
             }
-            for (int attempt = 0; attempt < 2 && !pl->graph; ++attempt) {
+        if (!graph) {
+            const bool want_pdl = pdl;
+            for (int attempt = 0; attempt < 2 && !graph; ++attempt) {
                 sp.pdl = pdl;
                 cudaGraph_t g = nullptr;
                 ARIES_TRY(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal), "begin capture");
                 cudaError_t e1 = run_step(pl, batch, sp, xsplits, pdl, fuse_ln, stream, &per_step);
                 cudaError_t e2 = cudaStreamEndCapture(stream, &g);
-                cudaError_t e3 = (e1 == cudaSuccess && e2 == cudaSuccess) ? cudaGraphInstantiate(&pl->graph, g, 0) : cudaErrorUnknown;
+                cudaError_t e3 = (e1 == cudaSuccess && e2 == cudaSuccess) ? cudaGraphInstantiate(&graph, g, 0) : cudaErrorUnknown;
                 if (g) cudaGraphDestroy(g);
                 if (e3 != cudaSuccess) {
-                    pl->graph = nullptr;
+                    graph = nullptr;
                     cudaGetLastError();
                     if (!pdl) {
                         if (e1 == cudaSuccess) pl->error = std::string("graph capture of the decode step failed: ") +
@@ -546,19 +552,20 @@ cudaError_t decoder_generate(DecoderPlan* pl, const void* enc_out, int batch, co
                     pdl = false;        // programmatic edges refused by this driver: capture again with plain edges
                 }
             }
-            key.pdl = pdl ? 1 : 0;
-            pl->graph_key = key;
-            pl->graph_pdl = pdl;
-            pl->stats[3] = (float)per_step;
+            (void)want_pdl;             // the entry is filed under the REQUESTED key, so the fallback is found again
+            if (pl->graphs.size() >= 8) {
+                cudaGraphExecDestroy(pl->graphs.front().exec);
+                pl->graphs.erase(pl->graphs.begin());
+            }
+            pl->graphs.push_back({key, graph, per_step});
         }
-        per_step = (int)pl->stats[3];
     }
 
     const int last_step = o.max_length - 2;      // consuming position max_length - 2 fills the last position
     int steps_run = 0;
     for (int t = 0; t <= last_step; ++t) {
         if (use_graph) {
-            ARIES_TRY(cudaGraphLaunch(pl->graph, stream), "graph launch");
+            ARIES_TRY(cudaGraphLaunch(graph, stream), "graph launch");
         } else {
             cudaError_t e = run_step(pl, batch, sp, xsplits, pdl, fuse_ln, stream, &per_step);
             if (e != cudaSuccess) return e;
