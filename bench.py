@@ -286,6 +286,36 @@ def run_decode(args, rank: int, local_rank: int, world: int) -> int:
             dist.destroy_process_group()
         return 0
     peaks = load_peaks()
+    traffic = load_traffic()
+    # the dominant kernel of the step (cross-attention over every window's cached keys / values: 36-60 % of the step)
+    # timed on its own with CUDA events through the library's kernel-level hook, same shape as inside the step
+    import ctypes
+    from whisper_aries_b200 import _lib
+    ctx = _lib.Context.get(local_rank)
+    H, A2 = shape.n_heads, shape.n_audio_ctx
+    q = torch.randn(B, shape.d_model, device=dev).bfloat16()
+    kv = torch.randn(B * A2, 2 * shape.d_model, device=dev).bfloat16()
+    xo = torch.empty((B, shape.d_model), device=dev, dtype=torch.bfloat16)
+    want = -(-4 * ctx.sm_count // (B * H))
+    xs = max(1, min(8, want))
+
+    def xattn():
+        _lib.check(ctx.lib.aries_test_decode_attention(ctx.handle, q.data_ptr(), shape.d_model, kv.data_ptr(),
+                                                       kv.data_ptr() + shape.d_model * 2, A2, 2 * shape.d_model, None, None, 0,
+                                                       None, A2, B, H, xo.data_ptr(), shape.d_model, xs, None))
+    for _ in range(3):
+        xattn()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_rep = 20
+    e0.record()
+    for _ in range(n_rep):
+        xattn()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    xattn_ms = e0.elapsed_time(e1) / n_rep
+    xattn_bytes = B * A2 * 2 * shape.d_model * 2
+    del q, kv, xo
     tokens_total = world * B * T * args.steps
     d, f, Lr, V, A = shape.d_model, shape.d_ffn, shape.n_layers, shape.vocab, shape.n_audio_ctx
     w_bytes = (14 * d * d * Lr + V * d) * 2
@@ -316,11 +346,19 @@ def run_decode(args, rank: int, local_rank: int, world: int) -> int:
                     "api": "WhisperDecoder.generate(encoder_output, prompts) wall clock (prompt upload, token download, "
                            "host-side result assembly inside the timed region; encoder output resident, as upstream keeps it)"},
             "gpu_launches": int(kernels),
-            "roofline": {"kernel": "decode step (356 kernels: skinny tcgen05 GEMMs + single-query attention over the caches)",
-                         "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": gbs / peaks["hbm_gbs"], "peak_source": peaks["source"],
-                         "bytes_per_step": {"weights": w_bytes, "cross_kv": xkv_bytes, "self_kv_mean": int(self_bytes)},
-                         "ms_per_step": ms_per_token_step, "traffic": None},
+            "roofline": {"kernel": f"decode_attention_kernel (cross-attention of one layer: {B} windows x {H} heads x {A2} keys; "
+                                   f"{shape.n_layers} launches per token step, the largest share of it)",
+                         "bound": "hbm", "achieved": xattn_bytes / (xattn_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+                         "unit": "GB/s", "frac": xattn_bytes / (xattn_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                         "peak_source": peaks["source"], "bytes_per_launch": xattn_bytes, "ms_per_launch": xattn_ms,
+                         "share_of_step": shape.n_layers * xattn_ms / ms_per_token_step,
+                         "traffic": traffic.get("decode_attention_kernel") if B == 64 and args.model == "large-v3" else None},
+            "roofline_step": {"kernel": f"whole token step ({st['kernels_per_step']} kernels: skinny tcgen05 GEMMs, single-query "
+                                        "attention over the caches, LayerNorm, sampling)",
+                              "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                              "frac": gbs / peaks["hbm_gbs"], "peak_source": peaks["source"],
+                              "bytes_per_step": {"weights": w_bytes, "cross_kv": xkv_bytes, "self_kv_mean": int(self_bytes)},
+                              "ms_per_step": ms_per_token_step},
             "phases": {"cross_kv_projection_ms": kv_ms / args.steps, "decode_loop_ms": loop_ms / args.steps,
                        "ms_per_token_step": ms_per_token_step, "kernels_per_token_step": st["kernels_per_step"]},
             "cpu_baseline": cpu}
