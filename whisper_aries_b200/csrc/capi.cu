@@ -535,20 +535,7 @@ int aries_test_decode_attention(aries_ctx* ctx, const void* q, int q_ld, void* k
     p.batch = batch; p.heads = heads; p.q = q; p.q_ld = q_ld; p.k = k; p.v = v; p.kv_rows = kv_rows; p.kv_ld = kv_ld;
     p.new_k = new_k; p.new_v = new_v; p.new_ld = new_ld; p.step = step_dev; p.n_keys_fixed = n_keys_fixed;
     p.out = out; p.out_ld = out_ld; p.splits = splits; p.pdl = 0;
-    void* scratch = nullptr;
-    cudaError_t e;
-    const size_t part = (size_t)batch * heads * splits * 66 * 4, tick = (size_t)batch * heads * 4;
-    if (splits > 1) {
-        if ((e = cudaMalloc(&scratch, part + tick)) != cudaSuccess) return fail_cuda("cudaMalloc", e);
-        cudaMemsetAsync(scratch, 0, part + tick, static_cast<cudaStream_t>(stream));
-        p.partial = static_cast<float*>(scratch);
-        p.tickets = reinterpret_cast<unsigned*>(static_cast<char*>(scratch) + part);
-    }
-    e = aries::decode_attention_launch(p, static_cast<cudaStream_t>(stream));
-    if (scratch) {
-        cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
-        cudaFree(scratch);
-    }
+    cudaError_t e = aries::decode_attention_launch(p, static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return fail_cuda("decode_attention_launch", e);
     return ARIES_OK;
 }

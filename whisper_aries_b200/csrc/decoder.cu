@@ -86,8 +86,8 @@ struct DecoderPlan {
     char* d_state = nullptr;
     int *tokens = nullptr, *step = nullptr, *done = nullptr, *last_ts = nullptr, *n_done = nullptr, *sot_index = nullptr,
         *use_ts = nullptr, *forced = nullptr, *argmax = nullptr;
-    unsigned *ticket = nullptr, *suppress_bits = nullptr, *attn_tickets = nullptr;
-    float *score = nullptr, *nsp = nullptr, *attn_partial = nullptr;
+    unsigned *ticket = nullptr, *suppress_bits = nullptr;
+    float *score = nullptr, *nsp = nullptr;
     int* h_ndone = nullptr;                          // pinned
     struct GraphEntry {
         GraphKey key;
@@ -281,8 +281,8 @@ cudaError_t decoder_plan_create(int device, int sm_count, const DecoderShapeC& c
     const size_t B = max_batch;
     const size_t s_tok = take(B * C * 4), s_forced = take(B * C * 4), s_argmax = take(B * C * 4), s_step = take(4),
                  s_done = take(B * 4), s_lts = take(B * 4), s_ndone = take(4), s_sot = take(B * 4), s_uts = take(B * 4),
-                 s_ticket = take(4), s_bits = take(((size_t)V + 31) / 32 * 4), s_atk = take(B * cfg.n_heads * 4),
-                 s_score = take(B * 4), s_nsp = take(B * 4), s_apart = take(B * cfg.n_heads * 32 * 66 * 4);
+                 s_ticket = take(4), s_bits = take(((size_t)V + 31) / 32 * 4),
+                 s_score = take(B * 4), s_nsp = take(B * 4);
     if ((e = cudaMalloc(&pl->d_state, off)) != cudaSuccess) return fail(e);
     if ((e = cudaMemset(pl->d_state, 0, off)) != cudaSuccess) return fail(e);
     char* s = pl->d_state;
@@ -290,8 +290,7 @@ cudaError_t decoder_plan_create(int device, int sm_count, const DecoderShapeC& c
     pl->step = (int*)(s + s_step); pl->done = (int*)(s + s_done); pl->last_ts = (int*)(s + s_lts);
     pl->n_done = (int*)(s + s_ndone); pl->sot_index = (int*)(s + s_sot); pl->use_ts = (int*)(s + s_uts);
     pl->ticket = (unsigned*)(s + s_ticket); pl->suppress_bits = (unsigned*)(s + s_bits);
-    pl->attn_tickets = (unsigned*)(s + s_atk); pl->score = (float*)(s + s_score); pl->nsp = (float*)(s + s_nsp);
-    pl->attn_partial = (float*)(s + s_apart);
+    pl->score = (float*)(s + s_score); pl->nsp = (float*)(s + s_nsp);
     if ((e = cudaMallocHost(&pl->h_ndone, 4)) != cudaSuccess) return fail(e);
     for (auto& ev : pl->ev)
         if ((e = cudaEventCreate(&ev)) != cudaSuccess) return fail(e);
@@ -380,7 +379,7 @@ cudaError_t run_step(DecoderPlan* pl, int batch, const SampleParams& sp, int xsp
         __nv_bfloat16* kv = pl->xkv + (size_t)l * batch * A * 2 * d;
         x.k = kv; x.v = kv + d; x.kv_rows = A; x.kv_ld = 2 * d;
         x.n_keys_fixed = A;
-        x.out = pl->ctx; x.out_ld = d; x.splits = xsplits; x.partial = pl->attn_partial; x.tickets = pl->attn_tickets;
+        x.out = pl->ctx; x.out_ld = d; x.splits = xsplits;
         x.pdl = pdl_a;
         ARIES_TRY(decode_attention_launch(x, stream), "cross-attention");
         ARIES_TRY(skinny(SK_BIAS_RESID_F16, lw.m_o2, pl->a_ctx, d, d, lw.bo2, pl->x, d), "cross-attention output");
@@ -474,7 +473,6 @@ cudaError_t decoder_generate(DecoderPlan* pl, const void* enc_out, int batch, co
     ARIES_TRY(cudaMemsetAsync(pl->done, 0, batch * 4, stream), "memset");
     ARIES_TRY(cudaMemsetAsync(pl->score, 0, batch * 4, stream), "memset");
     ARIES_TRY(cudaMemsetAsync(pl->nsp, 0, batch * 4, stream), "memset");
-    ARIES_TRY(cudaMemsetAsync(pl->attn_tickets, 0, (size_t)batch * c.n_heads * 4, stream), "memset");
     if (o.argmax_out) ARIES_TRY(cudaMemsetAsync(pl->argmax, 0xFF, (size_t)batch * C * 4, stream), "memset");
     // the host vectors above must outlive their asynchronous copies
     ARIES_TRY(cudaStreamSynchronize(stream), "synchronise (state upload)");

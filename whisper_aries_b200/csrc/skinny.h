@@ -11,8 +11,8 @@ namespace aries {
 //   out[b, n] = epilogue( sum_k X[b, k] * W[n, k] ),  b < B <= 128 sequences, W [N, K] bf16 K-major (a Linear weight).
 // One decode step multiplies a handful of rows by every weight matrix of the decoder: the op is bound by streaming W
 // from HBM once, so W is the 128-row M operand of tcgen05.mma, the sequences are the N operand (padded to NB = a
-// multiple of 16), K is split over CTAs so that >= 1 CTA per SM pulls bytes, and the last CTA of an n-tile to finish
-// reduces the partial sums in a fixed order (bit-reproducible) and applies the epilogue.
+// multiple of 16), K is split over the CTAs of a thread-block cluster so that about one CTA per SM pulls bytes, and the
+// partial sums are reduced through distributed shared memory in a fixed order (bit-reproducible).
 enum SkinnyEpilogue {
     SK_BIAS_BF16 = 0,        // out bf16 [B, ldo] = acc + bias
     SK_BIAS_GELU_BF16 = 1,   // out bf16 = gelu_erf(acc + bias)
@@ -29,8 +29,6 @@ struct SkinnyParams {
     const float* bias;  // [N] (unused by SK_LOGITS_F32)
     void* out;
     int ldo;            // elements between consecutive sequences in out
-    float* partial;     // f32 [splits][NB][n_tiles * 128] (only touched when splits > 1)
-    unsigned* tickets;  // [n_tiles], zero before the first launch; the kernel leaves them zero
     int pdl;            // launched with programmatic stream serialisation (griddepcontrol in the kernel)
     // Fused LayerNorm (small batch): when ln_x != NULL the token-row operand is not loaded by TMA but computed in the
     // kernel as LayerNorm(ln_x[b, :]) * gamma + beta (f16 residual stream in, bf16 operand written straight into the
@@ -44,7 +42,6 @@ struct SkinnyParams {
 int skinny_pick_splits(int N, int K, int sm_count);
 // same, for the fused-LayerNorm variant (every split must hold all of its K-blocks at once: <= 8); 0 if impossible
 int skinny_pick_splits_ln(int N, int K, int sm_count);
-size_t skinny_partial_bytes(int NB, int N, int splits);
 cudaError_t skinny_init_device();
 // tmap_w: [N, K] bf16, box 64 x 128; tmap_x: [>= NB rows, K] bf16, box 64 x NB.
 cudaError_t skinny_launch(int epi, const CUtensorMap& tmap_w, const CUtensorMap& tmap_x, const SkinnyParams& p,
@@ -55,7 +52,8 @@ cudaError_t skinny_launch(int epi, const CUtensorMap& tmap_w, const CUtensorMap&
 //   out[b, h*64 .. +64] = softmax(q . K^T / 8) V
 // Self-attention (n_keys_fixed == 0): first appends this step's key / value (new_k / new_v rows of the QKV buffer) to
 // the cache at position *step, then attends to positions 0 .. *step.  Cross-attention: n_keys_fixed keys, optionally
-// split over `splits` CTAs whose partial (max, sum, weighted values) are merged by the last one to finish.
+// split over a cluster of `splits` <= 8 CTAs whose partial (max, sum, weighted values) rank 0 merges through
+// distributed shared memory.
 struct DecAttnParams {
     int batch, heads;
     const void* q;          // bf16, q of (b, h) at q + b * q_ld + h * 64
@@ -72,8 +70,6 @@ struct DecAttnParams {
     void* out;              // bf16, out + b * out_ld + h * 64
     int out_ld;
     int splits;
-    float* partial;         // f32 [batch * heads][splits][66]
-    unsigned* tickets;      // [batch * heads]
     int pdl;
 };
 cudaError_t decode_attention_launch(const DecAttnParams& p, cudaStream_t stream);

@@ -462,8 +462,6 @@ int skinny_pick_splits_ln(int N, int K, int sm_count) {
     return (num_kb + kps - 1) / kps;
 }
 
-size_t skinny_partial_bytes(int, int, int) { return 0; }         // partial sums live in distributed shared memory
-
 cudaError_t skinny_init_device() {
     cudaError_t e;
     if ((e = set_smem<SK_BIAS_BF16>()) != cudaSuccess) return e;
