@@ -54,6 +54,26 @@ def test_pure_host_entry_points():
     assert lib.aries_logmel_num_frames(8000, 0) == 50
     assert lib.aries_encoder_workspace_bytes(None, 4) == 0
     assert lib.aries_logmel_destroy(None) == 0 and lib.aries_encoder_destroy(None) == 0 and lib.aries_destroy(None) == 0
+    # row f1 / f3 entry points: NULL handles are rejected with the state error, never dereferenced
+    assert lib.aries_decoder_destroy(None) == 0
+    out = (ctypes.c_float * 5)()
+    assert lib.aries_decoder_last_stats(None, out, 5) == _lib.ARIES_ESTATE and "decoder handle" in _lib.last_error()
+    assert lib.aries_decoder_generate(None, None, 1, None, 1, None, None, None, None, None, None) == _lib.ARIES_ESTATE
+    assert lib.aries_pcm_s16_to_f32(None, None, None, 0, None) == _lib.ARIES_ESTATE
+
+
+def test_decoder_shapes_and_token_ids():
+    """Row f1 host constants: Whisper's special-token layout for the two multilingual vocabularies and the decoder dims."""
+    t = synthetic.WhisperTokens.for_vocab(51866)
+    assert (t.eot, t.sot, t.transcribe, t.no_speech, t.no_timestamps, t.timestamp_begin) == (50257, 50258, 50360, 50363, 50364, 50365)
+    assert 51866 - t.timestamp_begin == 1501                       # <|0.00|> .. <|30.00|> in 0.02-s steps
+    t = synthetic.WhisperTokens.for_vocab(51865)
+    assert (t.eot, t.sot, t.transcribe, t.no_speech, t.no_timestamps, t.timestamp_begin) == (50257, 50258, 50359, 50362, 50363, 50364)
+    s = synthetic.DEC_SHAPES["large-v3"]
+    assert (s.vocab, s.d_model, s.n_heads, s.n_layers, s.d_ffn, s.n_text_ctx, s.n_audio_ctx) == (51866, 1280, 20, 32, 5120, 448, 1500)
+    w = synthetic.decoder_weights(synthetic.DEC_SHAPES["micro"], 1, tied=True)
+    assert "decoder/projection/weight" not in w and w["decoder/layer_0/attention/linear_1/weight"].shape == (256, 128)
+    assert not w["decoder/layer_0/self_attention/linear_0/bias"][128:256].any()      # Whisper's key projection has no bias
 
 
 def test_feature_extractor_surface_matches_upstream():
