@@ -417,6 +417,13 @@ def test_scheduler_transcribe_worker_returns_token_rows():
         ids = r.sequences_ids[0]
         assert out[i, 0] == len(ids) and out[i, 1:4].tolist() == prompt
         assert out[i, 4:4 + len(ids)].tolist() == ids and (out[i, 4 + len(ids):] == tok.eot).all()
+    # int16 PCM (ffmpeg's pcm_s16le) goes through the same worker: scaled by 1/32768 on the GPU
+    pcm16 = np.clip(np.round(pcm * 32768.0), -32768, 32767).astype(np.int16)
+    out16, out32 = np.zeros_like(out), np.zeros_like(out)
+    sched = ChunkScheduler([gpu_transcribe_worker(model, prompt, max_length=L, micro_batch=2, suppress_tokens=[])])
+    assert all(r.success for r in sched.run(pcm16, out16))
+    assert all(r.success for r in sched.run(pcm16.astype(np.float32) / 32768.0, out32))
+    assert np.array_equal(out16, out32)
     bad = np.zeros((5, 7), dtype=np.int32)
     res = ChunkScheduler([gpu_transcribe_worker(model, prompt, max_length=L, micro_batch=2)]).run(pcm, bad)
     assert not res[0].success and "int32" in res[0].error       # reported per shard, as the reference does (ref: :355-365)

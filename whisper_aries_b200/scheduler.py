@@ -221,10 +221,12 @@ def gpu_transcribe_worker(model, prompt: Sequence[int], max_length: int = 448, m
     def run(windows, start: int, stop: int, out) -> None:
         torch.cuda.set_device(dev)
         n_s = int(windows.shape[1])
-        if state.get("n_s") != n_s:
-            state["n_s"] = n_s
-            state["buf"] = torch.empty((micro_batch, n_s), dtype=torch.float32, device=dev)
         wt = windows if isinstance(windows, torch.Tensor) else torch.from_numpy(windows)
+        if wt.dtype not in (torch.float32, torch.int16):
+            raise ValueError("windows must be float32 or int16 PCM")
+        if state.get("n_s") != n_s or state.get("dtype") != wt.dtype:
+            state["n_s"], state["dtype"] = n_s, wt.dtype
+            state["buf"] = torch.empty((micro_batch, n_s), dtype=wt.dtype, device=dev)     # int16 is scaled on the GPU
         ot = out if isinstance(out, torch.Tensor) else torch.from_numpy(out)
         L = min(int(max_length), model.decoder.shape.n_text_ctx)
         if ot.shape[1] != L + 1 or ot.dtype != torch.int32:
