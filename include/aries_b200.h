@@ -192,6 +192,15 @@ ARIES_API int aries_decoder_generate(aries_decoder* dec, const void* enc_out_dev
                            int prompt_len, const aries_generate_opts* opts, int32_t* tokens_out, int32_t* lengths,
                            float* scores, float* no_speech_prob, void* stream);
 
+/* ctranslate2.models.Whisper.detect_language(encoder_output), which faster-whisper calls when language=None -- the
+ * reference's default ("auto" -> None, final_optimized_transcriber.py:433; result recorded at :350-351): one decoder step
+ * on <|startoftranscript|> and a softmax over the language-token logits.
+ *   lang_ids   host int32 [n_lang]: the language token ids (large-v3: 50259 .. 50358)
+ *   probs_out  host f32 [batch, n_lang], in the order of lang_ids (upstream sorts them by probability: the shim does) */
+ARIES_API int aries_decoder_detect_language(aries_decoder* dec, const void* enc_out_dev, int batch,
+                                  const aries_generate_opts* opts, const int32_t* lang_ids, int n_lang, float* probs_out,
+                                  void* stream);
+
 /* Timing of the last aries_decoder_generate (CUDA events on the decoding stream), n >= 5:
  * out[0] cross-attention K|V projection ms, out[1] decode loop ms, out[2] steps run, out[3] kernels per step,
  * out[4] kernels of the K|V projection phase. */

@@ -213,3 +213,13 @@ def generate(dec: Decoder, enc, prompts: list, tok, opts: GenerateOptions | None
             seqs[b].append(nxt)
         step += 1
     return res
+
+
+@torch.no_grad()
+def detect_language(dec: Decoder, enc, tok, lang_ids: list):
+    """``ctranslate2.models.Whisper.detect_language`` [upstream, unverified offline; same as OpenAI whisper
+    ``detect_language``]: logits of one decoder step on <|startoftranscript|>, everything but the language tokens
+    masked, softmax.  Returns f64 [B, len(lang_ids)] in the order of ``lang_ids``."""
+    enc = torch.as_tensor(enc, dtype=torch.float32)
+    lg = dec.logits(torch.full((enc.shape[0], 1), tok.sot, dtype=torch.long), enc)[:, 0].double()
+    return torch.softmax(lg[:, lang_ids], dim=-1).numpy()

@@ -451,3 +451,26 @@ def test_decode_to_the_last_position():
             assert cos >= 0.9995, f"window {b} step {t}: logits cosine {cos}"
     # the raw argmax of the graph run and of the stream run (logits download) agree everywhere: same kernels, same bits
     assert np.array_equal(extras[0]["argmax"][:, len(prompt):], np.array(forced))
+
+
+def test_detect_language_matches_oracle():
+    """One decoder step on <|sot|> and a softmax over the language tokens (ctranslate2 Whisper.detect_language)."""
+    shape, tok, otok, enc, dec, oracle, wd = _setup("micro", 3, 23)
+    ids = dec.language_ids()
+    assert ids == list(range(tok.first_lang, tok.translate)) and len(ids) == 2
+    wide = list(range(40, 140))                      # a language block as wide as Whisper's (100 tokens)
+    ref = wd.detect_language(oracle, enc.float(), otok, wide)
+    got = dec.detect_language(enc.cuda(), wide)
+    assert len(got) == 3
+    for b in range(3):
+        probs = dict(got[b])
+        assert abs(sum(probs.values()) - 1.0) < 1e-5
+        assert [p for _, p in got[b]] == sorted((p for _, p in got[b]), reverse=True)      # most probable first
+        for j, i in enumerate(wide):
+            assert abs(probs[i] - ref[b, j]) <= 0.03 * ref[b, j] + 1e-6        # logit noise 0.01 on a softmax
+        assert got[b][0][0] == wide[int(ref[b].argmax())] or (np.sort(ref[b])[-1] - np.sort(ref[b])[-2]) < 0.02 * ref[b].max()
+    with pytest.raises(ValueError):
+        dec.detect_language(enc.cuda(), [shape.vocab + 1])
+    # generate still works on the same handle afterwards (detect_language runs through the same state)
+    prompt = [tok.sot, tok.first_lang, tok.transcribe]
+    assert len(dec.generate(enc.cuda(), [prompt] * 3, max_length=10, suppress_tokens=[])) == 3

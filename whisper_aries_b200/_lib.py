@@ -73,6 +73,8 @@ PROTOTYPES = {
     "aries_decoder_destroy": (c_int, [c_void_p]),
     "aries_decoder_generate": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, ctypes.POINTER(GenerateOpts), c_void_p,
                                        c_void_p, c_void_p, c_void_p, c_void_p]),
+    "aries_decoder_detect_language": (c_int, [c_void_p, c_void_p, c_int, ctypes.POINTER(GenerateOpts), c_void_p, c_int,
+                                              c_void_p, c_void_p]),
     "aries_decoder_last_stats": (c_int, [c_void_p, c_float_p, c_int]),
     "aries_test_decoder_generate": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, ctypes.POINTER(GenerateOpts),
                                             c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -461,6 +461,26 @@ int aries_decoder_generate(aries_decoder* dec, const void* enc_out_dev, int batc
                          nullptr, scores, no_speech_prob, stream);
 }
 
+int aries_decoder_detect_language(aries_decoder* dec, const void* enc_out_dev, int batch, const aries_generate_opts* opts,
+                                  const int32_t* lang_ids, int n_lang, float* probs_out, void* stream) {
+    if (!dec || dec->magic != kMagicDec) return fail(ARIES_ESTATE, "invalid decoder handle");
+    int rc = use(dec->ctx);
+    if (rc) return rc;
+    if (!opts || !enc_out_dev) return fail(ARIES_EINVAL, "aries_decoder_detect_language: NULL argument");
+    aries::GenerateOptsC o{};
+    o.eot = opts->eot; o.sot = opts->sot; o.no_speech = opts->no_speech; o.no_timestamps = opts->no_timestamps;
+    o.timestamp_begin = opts->timestamp_begin; o.blank_id = opts->blank_id;
+    o.max_initial_timestamp_index = opts->max_initial_timestamp_index;
+    cudaError_t e = aries::decoder_detect_language(dec->plan, enc_out_dev, batch, o, lang_ids, n_lang, probs_out,
+                                                   static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) {
+        g_error = std::string("aries_decoder_detect_language: ") + aries::decoder_plan_error(dec->plan);
+        cudaGetLastError();
+        return e == cudaErrorInvalidValue ? ARIES_EINVAL : (e == cudaErrorMemoryAllocation ? ARIES_ENOMEM : ARIES_ECUDA);
+    }
+    return ARIES_OK;
+}
+
 int aries_decoder_last_stats(const aries_decoder* dec, float* out, int n) {
     if (!dec || dec->magic != kMagicDec) return fail(ARIES_ESTATE, "invalid decoder handle");
     if (!out || n < 5) return fail(ARIES_EINVAL, "aries_decoder_last_stats: need n >= 5");

@@ -15,6 +15,7 @@
 // bf16 weights / activations, f32 accumulation, f16 residual stream -- the same numeric contract as the encoder.
 #include <cuda_bf16.h>
 
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -615,6 +616,43 @@ cudaError_t decoder_generate(DecoderPlan* pl, const void* enc_out, int batch, co
     pl->stats[2] = (float)steps_run;
     pl->stats[3] = (float)per_step;
     pl->stats[4] = (float)kv_launches;
+    return cudaSuccess;
+}
+
+cudaError_t decoder_detect_language(DecoderPlan* pl, const void* enc_out, int batch, const GenerateOptsC& ids,
+                                    const int* lang_ids, int n_lang, float* probs, cudaStream_t stream) {
+    const int V = pl->cfg.vocab;
+    if (!lang_ids || !probs || n_lang < 1) {
+        pl->error = "detect_language: no language ids";
+        return cudaErrorInvalidValue;
+    }
+    for (int i = 0; i < n_lang; ++i)
+        if (lang_ids[i] < 0 || lang_ids[i] >= V) {
+            pl->error = "detect_language: language id outside the vocabulary";
+            return cudaErrorInvalidValue;
+        }
+    // one step of the ordinary decode path on the prompt [<|startoftranscript|>] with the logits brought to the host
+    GenerateOptsC o = ids;
+    o.max_length = 2;
+    o.suppress_blank = 0;
+    o.suppress_tokens = nullptr;
+    o.n_suppress = 0;
+    o.forced = nullptr;
+    o.n_forced = 0;
+    o.argmax_out = nullptr;
+    std::vector<float> logits((size_t)batch * V);
+    o.logits_out = logits.data();
+    std::vector<int> prompts(batch, ids.sot), toks((size_t)batch * 2);
+    cudaError_t e = decoder_generate(pl, enc_out, batch, prompts.data(), 1, o, toks.data(), nullptr, nullptr, nullptr, stream);
+    if (e != cudaSuccess) return e;
+    for (int b = 0; b < batch; ++b) {
+        const float* lg = logits.data() + (size_t)b * V;
+        float m = lg[lang_ids[0]];
+        for (int i = 1; i < n_lang; ++i) m = lg[lang_ids[i]] > m ? lg[lang_ids[i]] : m;
+        double sum = 0.0;
+        for (int i = 0; i < n_lang; ++i) sum += std::exp((double)(lg[lang_ids[i]] - m));
+        for (int i = 0; i < n_lang; ++i) probs[(size_t)b * n_lang + i] = (float)(std::exp((double)(lg[lang_ids[i]] - m)) / sum);
+    }
     return cudaSuccess;
 }
 

@@ -41,6 +41,11 @@ cudaError_t decoder_generate(DecoderPlan* pl, const void* enc_out, int batch, co
                              const GenerateOptsC& opts, int* tokens_out, int* lengths, float* scores,
                              float* no_speech_prob, cudaStream_t stream);
 
+// ctranslate2 Whisper.detect_language: one decoder step on <|startoftranscript|>, softmax over the language-token logits.
+// probs: host [batch, n_lang] (order of lang_ids).  Synchronises.
+cudaError_t decoder_detect_language(DecoderPlan* pl, const void* enc_out, int batch, const GenerateOptsC& ids,
+                                    const int* lang_ids, int n_lang, float* probs, cudaStream_t stream);
+
 // Timing / launch counts of the last decoder_generate: [0] cross-KV projection ms, [1] decode loop ms, [2] steps run,
 // [3] kernels per step, [4] kernels of the cross-KV phase.
 void decoder_plan_last_stats(const DecoderPlan* pl, float out[5]);

@@ -108,6 +108,37 @@ class WhisperDecoder:
         if len({len(p) for p in prompts}) != 1 or len(prompts[0]) == 0:
             raise ValueError("all prompts of a batch must have the same, non-zero length")
 
+    def language_ids(self) -> list:
+        """Ids of the language tokens: everything between <|startoftranscript|>'s successor and <|translate|>."""
+        t = self.tokens
+        return list(range(t.first_lang, min(t.translate, t.transcribe)))
+
+    def detect_language(self, encoder_output, lang_ids=None):
+        """``ctranslate2.models.Whisper.detect_language``: for every window the language tokens with their probability,
+        most probable first -- upstream returns ``("<|en|>", p)`` pairs, here ``(token id, p)`` (no tokenizer in this
+        library).  faster-whisper calls it when ``language=None``, the reference's default (ref:
+        final_optimized_transcriber.py:433, recorded at :350-351)."""
+        import torch
+        self._check_inputs(encoder_output, [[self.tokens.sot]] * encoder_output.shape[0])
+        ids = [int(i) for i in (lang_ids if lang_ids is not None else self.language_ids())]
+        if not ids:
+            raise ValueError("no language token ids")
+        arr = np.ascontiguousarray(np.asarray(ids, dtype=np.int32))
+        opts, _keep = self._opts(2, False, (), 50)
+        enc = encoder_output.contiguous()
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        out = []
+        for b0 in range(0, enc.shape[0], self.max_batch):
+            part = enc[b0:b0 + self.max_batch]
+            probs = np.zeros((part.shape[0], len(ids)), dtype=np.float32)
+            _lib.check(self._ctx.lib.aries_decoder_detect_language(self._handle, part.data_ptr(), part.shape[0],
+                                                                   ctypes.byref(opts), arr.ctypes.data, len(ids),
+                                                                   probs.ctypes.data, stream))
+            for row in probs:
+                order = np.argsort(-row, kind="stable")
+                out.append([(ids[i], float(row[i])) for i in order])
+        return out
+
     def generate(self, encoder_output, prompts, *, beam_size: int = 1, patience: float = 1, num_hypotheses: int = 1,
                  length_penalty: float = 1, repetition_penalty: float = 1, no_repeat_ngram_size: int = 0,
                  max_length: int = 448, return_scores: bool = False, return_no_speech_prob: bool = False,

@@ -181,6 +181,12 @@ class WhisperModel:
             raise RuntimeError("this WhisperModel was built without decoder weights (pass decoder_shape=...)")
         return self.decoder.generate(encoder_output, prompts, **kw)
 
+    def detect_language(self, encoder_output, lang_ids=None):
+        """``ctranslate2.models.Whisper.detect_language`` on the encoder output (language=None path of ``transcribe``)."""
+        if self.decoder is None:
+            raise RuntimeError("this WhisperModel was built without decoder weights (pass decoder_shape=...)")
+        return self.decoder.detect_language(encoder_output, lang_ids)
+
     def encode(self, features):
         return self.encoder.encode(features)
 
