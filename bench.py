@@ -3,6 +3,7 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--windows 64] [--model large-v3]
     python bench.py --mode decode [--windows 64] [--tokens 64]      # row f1: greedy generate on the encoder output
+    python bench.py --mode transcribe [--windows 64] [--tokens 64]  # int16 PCM -> token ids through the scheduler
 
 A step = one pass of the hot path over one batch of synthetic 30-s / 16 kHz windows per GPU (BASELINE.json config 3:
 "large-v3 batch of 64 x 30-s chunks"; weak scaling: every rank owns 64 windows, no collective on the data path).
@@ -368,6 +369,87 @@ def run_decode(args, rank: int, local_rank: int, world: int) -> int:
     return 0
 
 
+def run_transcribe(args, rank: int, local_rank: int, world: int) -> int:
+    """--mode transcribe: the whole widened path through the public API -- pinned int16 PCM windows -> ChunkScheduler ->
+    gpu_transcribe_worker (H2D, s16 -> f32, log-mel, encoder, cross K|V, greedy decode of `tokens` ids per window) -> token
+    rows on the host.  Wall clock, host buffers, copies inside the timed region; audio-seconds per second."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: whisper_aries_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    from whisper_aries_b200 import ChunkScheduler, WhisperModel, gpu_transcribe_worker, synthetic
+    eshape, dshape = synthetic.SHAPES[args.model], synthetic.DEC_SHAPES[args.model]
+    w = dict(synthetic.encoder_weights(eshape, 1234))
+    w.update(synthetic.decoder_weights_fast(dshape, 0))
+    B, T = args.windows, args.tokens
+    model = WhisperModel(eshape, w, device="cuda", device_index=local_rank, decoder_shape=dshape,
+                         max_batch=min(args.micro_batch, 128))
+    del w
+    tok = model.decoder.tokens
+    prompt = [tok.sot, tok.first_lang, tok.transcribe]
+    L = len(prompt) + T
+    base = synthetic.batch_signals(min(B, 12), first_seed=rank * B)
+    pcm = np.concatenate([base] * (-(-B // base.shape[0])))[:B]
+    pcm16 = torch.from_numpy(np.clip(np.round(pcm * 32768.0), -32768, 32767).astype(np.int16)).pin_memory()
+    out = torch.zeros((B, L + 1), dtype=torch.int32).pin_memory()
+    sched = ChunkScheduler([gpu_transcribe_worker(model, prompt, max_length=L, micro_batch=args.micro_batch,
+                                                  suppress_tokens=[tok.eot])])
+
+    def step():
+        res = sched.run(pcm16, out)
+        if not all(r.success for r in res):
+            raise RuntimeError(f"transcribe step failed: {[r.error for r in res if not r.success]}")
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        step()
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step()
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        barrier()
+    assert int(out[:, 0].min()) == T
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    if rank == 0:
+        value = world * B * WINDOW_SECONDS * args.steps / dt
+        st = model.decoder.last_stats()
+        line = {"metric": f"audio-sec/sec (PCM -> token ids: log-mel + encoder + greedy decode, {args.model})", "value": value,
+                "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": f"{args.model}: {B} x 30-s int16 windows per GPU per step -> {T} token ids each "
+                                       f"(rows a + f1 + f3 through ChunkScheduler / gpu_transcribe_worker, micro-batch "
+                                       f"{args.micro_batch})", "windows_per_gpu": B, "tokens_per_window": T},
+                "clocks": clocks.summary(),
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": int(pcm16.numel() * 2),
+                        "d2h_bytes_per_step": int(out.numel() * 4),
+                        "api": "ChunkScheduler(gpu_transcribe_worker(WhisperModel)).run(pinned int16 pcm, pinned int32 tokens)"},
+                "gpu_launches": None,
+                "tokens_per_s": world * B * T * args.steps / dt,
+                "last_micro_batch": {"cross_kv_ms": st["cross_kv_ms"], "decode_ms": st["decode_ms"], "steps": st["steps"],
+                                     "kernels_per_step": st["kernels_per_step"]}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main() -> int:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -379,8 +461,9 @@ def main() -> int:
     ap.add_argument("--model", default="large-v3")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--mode", default="encode", choices=["encode", "decode"],
-                    help="encode = the headline log-mel + encoder path; decode = row f1, greedy generate")
+    ap.add_argument("--mode", default="encode", choices=["encode", "decode", "transcribe"],
+                    help="encode = the headline log-mel + encoder path; decode = row f1, greedy generate on a resident "
+                         "encoder output; transcribe = int16 PCM -> token ids through the scheduler (rows a + f1 + f3)")
     ap.add_argument("--tokens", type=int, default=64, help="--mode decode: sampled tokens per window")
     args = ap.parse_args()
 
@@ -391,6 +474,8 @@ def main() -> int:
         return run_reference(args, rank, world)
     if args.mode == "decode":
         return run_decode(args, rank, local_rank, world)
+    if args.mode == "transcribe":
+        return run_transcribe(args, rank, local_rank, world)
 
     import numpy as np
     import torch
