@@ -531,7 +531,6 @@ cudaError_t decoder_generate(DecoderPlan* pl, const void* enc_out, int batch, co
                 per_step = g.per_step;
             }
         if (!graph) {
-            const bool want_pdl = pdl;
             for (int attempt = 0; attempt < 2 && !graph; ++attempt) {
                 sp.pdl = pdl;
                 cudaGraph_t g = nullptr;
@@ -551,7 +550,7 @@ cudaError_t decoder_generate(DecoderPlan* pl, const void* enc_out, int batch, co
                     pdl = false;        // programmatic edges refused by this driver: capture again with plain edges
                 }
             }
-            (void)want_pdl;             // the entry is filed under the REQUESTED key, so the fallback is found again
+            // (the entry is filed under the REQUESTED key, so a fallback without programmatic edges is found again)
             if (pl->graphs.size() >= 8) {
                 cudaGraphExecDestroy(pl->graphs.front().exec);
                 pl->graphs.erase(pl->graphs.begin());
