@@ -293,6 +293,13 @@ def test_generate_stops_at_eot_and_keeps_state_clean():
     assert res[1].sequences_ids[0][:3] == [9, 8, 7] and len(res[1].sequences_ids[0]) > 3
     again = dec.generate(enc.cuda(), prompts, max_length=max_length, suppress_tokens=[])
     assert [r.sequences_ids for r in again] == [r.sequences_ids for r in free]
+    # a finished window stops reading its caches (attention is skipped for it): the others must not notice.  Window 0 is
+    # ended at once, windows 1 and 2 are "forced" onto their own free-run ids, so their continuation must equal the free run
+    k = 4
+    forced = [[tok.eot] * k, free[1].sequences_ids[0][:k], free[2].sequences_ids[0][:k]]
+    res, _ = dec.generate(enc.cuda(), prompts, max_length=max_length, suppress_tokens=[], _forced=forced)
+    assert res[0].sequences_ids[0] == []
+    assert res[1].sequences_ids[0] == free[1].sequences_ids[0] and res[2].sequences_ids[0] == free[2].sequences_ids[0]
 
 
 def test_generate_rejects_bad_arguments():

@@ -58,6 +58,12 @@ __global__ void __launch_bounds__(kThreads) decode_attention_kernel(const DecAtt
     const int grp = lane >> 3, sub = lane & 7;       // 8 lanes per key row; lane `sub` owns dims 8 sub .. 8 sub + 7
 
     pdl_wait();
+    // A window that has emitted EOT only repeats EOT (decode_sample_kernel): it stops reading its caches -- 245.8 MB per
+    // step for large-v3's cross-attention.  All CTAs of a cluster share b, so they leave together.
+    if (p.done != nullptr && p.done[b] != 0) {
+        pdl_trigger();
+        return;
+    }
 
     int n_keys = p.n_keys_fixed;
     const __nv_bfloat16* kbase = reinterpret_cast<const __nv_bfloat16*>(p.k) + (size_t)b * p.kv_rows * p.kv_ld + h * 64;

@@ -364,7 +364,7 @@ cudaError_t run_step(DecoderPlan* pl, int batch, const SampleParams& sp, int xsp
         a.kv_rows = C; a.kv_ld = d;
         a.new_k = qkv + d; a.new_v = qkv + 2 * d; a.new_ld = 3 * d;
         a.step = pl->step; a.n_keys_fixed = 0;
-        a.out = pl->ctx; a.out_ld = d; a.splits = 1; a.pdl = pdl_a;
+        a.out = pl->ctx; a.out_ld = d; a.splits = 1; a.pdl = pdl_a; a.done = pl->done;
         ARIES_TRY(decode_attention_launch(a, stream), "self-attention");
         ARIES_TRY(skinny(SK_BIAS_RESID_F16, lw.m_o, pl->a_ctx, d, d, lw.bo, pl->x, d), "self-attention output");
         if (fuse_ln) {
@@ -381,7 +381,7 @@ cudaError_t run_step(DecoderPlan* pl, int batch, const SampleParams& sp, int xsp
         x.k = kv; x.v = kv + d; x.kv_rows = A; x.kv_ld = 2 * d;
         x.n_keys_fixed = A;
         x.out = pl->ctx; x.out_ld = d; x.splits = xsplits;
-        x.pdl = pdl_a;
+        x.pdl = pdl_a; x.done = pl->done;
         ARIES_TRY(decode_attention_launch(x, stream), "cross-attention");
         ARIES_TRY(skinny(SK_BIAS_RESID_F16, lw.m_o2, pl->a_ctx, d, d, lw.bo2, pl->x, d), "cross-attention output");
         if (fuse_ln) {

@@ -71,6 +71,7 @@ struct DecAttnParams {
     int out_ld;
     int splits;
     int pdl;
+    const int* done;        // optional [batch]: sequences that have emitted EOT skip the kernel (their cache is not read)
 };
 cudaError_t decode_attention_launch(const DecAttnParams& p, cudaStream_t stream);
 
