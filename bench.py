@@ -470,6 +470,10 @@ def main() -> int:
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        # stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...", printed when the image exports
+        # NCCL_DEBUG) goes to stderr instead
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if args.impl == "reference":
         return run_reference(args, rank, world)
     if args.mode == "decode":
