@@ -471,8 +471,10 @@ def main() -> int:
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...", printed when the image exports
-        # NCCL_DEBUG) goes to stderr instead
+        # stdout carries exactly one JSON line: NCCL's banner ("NCCL version ...", printed on stdout at debug level
+        # VERSION, which this image configures) is raised to WARN, where NCCL honours NCCL_DEBUG_FILE, and sent to stderr
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if args.impl == "reference":
         return run_reference(args, rank, world)
