@@ -6,7 +6,8 @@
 // final_optimized_transcriber.py:326 with beam_size=1, temperature=0 at :432-441) [upstream, unverified offline].
 //
 //   once per batch of windows:  K|V_l = enc_out W_kv,l^T + b   (the encoder's tcgen05 GEMM, M = B*1500, N = 2d) x n_layers
-//   per token (356 kernels for large-v3, programmatic dependent launch, one graph):
+//   per token (356 kernels for large-v3, 260 with LayerNorm folded into the GEMMs at <= 8 windows; programmatic
+//   dependent launch, one graph):
 //     embed -> n_layers x { LN -> QKV (skinny GEMM) -> self-attention over the cache (+append) -> O (+residual)
 //                           LN -> Q  (skinny GEMM) -> cross-attention over K|V_l            -> O (+residual)
 //                           LN -> fc1 (+GELU)      -> fc2 (+residual) }
