@@ -481,3 +481,30 @@ def test_detect_language_matches_oracle():
     # generate still works on the same handle afterwards (detect_language runs through the same state)
     prompt = [tok.sot, tok.first_lang, tok.transcribe]
     assert len(dec.generate(enc.cuda(), [prompt] * 3, max_length=10, suppress_tokens=[])) == 3
+
+
+@pytest.mark.parametrize("batch", [2, 9])
+def test_odd_width_decoder_uses_the_generic_layernorm(batch):
+    """d_model = 192 (3 heads; not a multiple of 128, so the register-resident LayerNorm kernel does not apply): 2 windows
+    take the fused-LayerNorm GEMMs with a partly filled chunk row, 9 windows the generic LayerNorm kernel."""
+    from oracle import synth as osynth, whisper_decoder as wd
+    from whisper_aries_b200 import WhisperDecoder, synthetic
+    shape = synthetic.DecoderShape("nano", 300, 192, 3, 2, 320)
+    oshape = osynth.DecoderShape("nano", 300, 192, 3, 2, 320)
+    tok = synthetic.WhisperTokens.for_vocab(shape.vocab)
+    w = synthetic.decoder_weights(shape, 11)
+    dec = WhisperDecoder(shape, w, tokens=tok, device="cuda:0", max_batch=16)
+    oracle = wd.Decoder(osynth.decoder_weights(oshape, 11), oshape, round_weights_bf16=True)
+    g = torch.Generator().manual_seed(batch)
+    enc = torch.randn(batch, shape.n_audio_ctx, shape.d_model, generator=g).bfloat16()
+    prompt = [tok.sot, tok.first_lang, tok.transcribe, tok.no_timestamps]
+    forced = [[(7 * b + 3 * i) % 150 for i in range(8)] for b in range(batch)]
+    L = len(prompt) + 8
+    res, extras = dec.generate(enc.cuda(), [prompt] * batch, max_length=L, suppress_tokens=[], _forced=forced,
+                               _want_logits=True)
+    assert dec.last_stats()["kernels_per_step"] == (8 if batch <= 8 else 11) * shape.n_layers + 4
+    seqs = torch.tensor([prompt + f for f in forced])[:, :L - 1]
+    ref = oracle.logits(seqs, enc.float())
+    logits = torch.from_numpy(extras[0]["logits"]).transpose(0, 1)
+    cos = torch.nn.functional.cosine_similarity(logits.reshape(-1, shape.vocab), ref.reshape(-1, shape.vocab), dim=-1)
+    assert cos.min().item() >= 0.9995, cos.min().item()
