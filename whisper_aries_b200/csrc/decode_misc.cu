@@ -298,8 +298,7 @@ cudaError_t decode_layernorm_launch(const void* x_f16, const float* gamma, const
                                     int pdl, cudaStream_t stream) {
     if (rows <= 0 || d % 2 != 0) return cudaErrorInvalidValue;
     // Whisper widths (multiples of 128 the encoder kernel is instantiated for): the row stays in registers, one pass
-    if (layernorm_launch_pdl(x_f16, gamma, beta, y_bf16, rows, d, 1e-5f, stream, pdl != 0) == cudaSuccess) return cudaSuccess;
-    cudaGetLastError();
+    if (layernorm_supports(d)) return layernorm_launch_pdl(x_f16, gamma, beta, y_bf16, rows, d, 1e-5f, stream, pdl != 0);
     const __half* x = reinterpret_cast<const __half*>(x_f16);
     __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(y_bf16);
     void* args[] = {&x, &gamma, &beta, &y, &rows, &d};

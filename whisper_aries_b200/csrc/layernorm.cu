@@ -85,6 +85,12 @@ cudaError_t launch(const __half* x, const float* g, const float* b, void* y, lon
 
 }  // namespace
 
+bool layernorm_supports(int d) {
+    if (d <= 0 || d % 128 != 0) return false;
+    const int nv = d / 128;
+    return (nv >= 1 && nv <= 6) || nv == 8 || nv == 10 || nv == 12 || nv == 16;
+}
+
 cudaError_t layernorm_launch(const void* x_f16, const float* gamma, const float* beta, void* y, long long rows, int d,
                              float eps, cudaStream_t stream) {
     return layernorm_launch_pdl(x_f16, gamma, beta, y, rows, d, eps, stream, false);
