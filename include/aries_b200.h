@@ -1,4 +1,4 @@
-/* aries_b200.h — C ABI of the B200-native log-mel + Whisper-encoder path.
+/* aries_b200.h — C ABI of the B200-native log-mel + Whisper-encoder path (and, widened, the greedy decoder).
  *
  * Drop-in boundary for the hot path Whisper-Aries obtains from faster-whisper 1.1.1 / CTranslate2 4.6.0
  * (requirements.txt:12,9), which the reference enters at final_optimized_transcriber.py:326
@@ -6,6 +6,8 @@
  * conversation_transcriber.py:72-77).  Upstream, that call runs
  *     FeatureExtractor.__call__(waveform, padding=160)            -> aries_logmel_run / aries_logmel_run_host
  *     WhisperModel.encode(features) -> ctranslate2 Whisper.encode -> aries_encoder_run / aries_encoder_run_host
+ *     ctranslate2 Whisper.detect_language(encoder_output)         -> aries_decoder_detect_language      
+ *     ctranslate2 Whisper.generate(encoder_output, prompts, ...)  -> aries_decoder_generate             (row f1)
  * per 30-second window.  Each entry point below names the upstream interface it replaces.
  *
  * Conventions
