@@ -508,3 +508,17 @@ def test_odd_width_decoder_uses_the_generic_layernorm(batch):
     logits = torch.from_numpy(extras[0]["logits"]).transpose(0, 1)
     cos = torch.nn.functional.cosine_similarity(logits.reshape(-1, shape.vocab), ref.reshape(-1, shape.vocab), dim=-1)
     assert cos.min().item() >= 0.9995, cos.min().item()
+
+
+def test_growing_the_cross_attention_cache_invalidates_cached_graphs():
+    """The cross-attention cache grows with the batch; step graphs captured against the old allocation must not survive
+    it: 2 windows, then 4 (reallocation), then the same 2 again -> identical ids and scores."""
+    shape, tok, otok, enc, dec, oracle, wd = _setup("micro", 4, 23)
+    prompt = [tok.sot, tok.first_lang, tok.transcribe]
+    kw = dict(max_length=len(prompt) + 12, suppress_tokens=[], return_scores=True)
+    first = dec.generate(enc[:2].cuda(), [prompt] * 2, **kw)
+    big = dec.generate(enc.cuda(), [prompt] * 4, **kw)
+    again = dec.generate(enc[:2].cuda(), [prompt] * 2, **kw)
+    assert [r.sequences_ids for r in again] == [r.sequences_ids for r in first]
+    assert [r.scores for r in again] == [r.scores for r in first]
+    assert [r.sequences_ids for r in big[:2]] == [r.sequences_ids for r in first]      # windows are independent

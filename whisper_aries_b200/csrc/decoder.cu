@@ -433,6 +433,9 @@ cudaError_t decoder_generate(DecoderPlan* pl, const void* enc_out, int batch, co
     // ---- cross-attention keys / values of every layer (once per batch of windows)
     const size_t xkv_bytes = (size_t)L * batch * A * 2 * d * 2;
     if (xkv_bytes > pl->xkv_cap) {
+        // the cached step graphs have the old cache's address baked in: they go with it
+        for (auto& g : pl->graphs) cudaGraphExecDestroy(g.exec);
+        pl->graphs.clear();
         cudaFree(pl->xkv);
         pl->xkv = nullptr;
         pl->xkv_cap = 0;
