@@ -315,6 +315,12 @@ def test_generate_rejects_bad_arguments():
         dec.generate(enc.cuda(), [[tok.sot], [tok.sot, tok.transcribe]])
     with pytest.raises(ValueError):
         dec.generate(enc.cuda(), [[shape.vocab + 5, 1, 2]] * 2)
+    with pytest.raises(ValueError):
+        dec.generate(enc.cuda(), p, max_length=10, _forced=[[shape.vocab], [1]])
+    # a suppress list that forbids every id ends the sequence instead of emitting garbage
+    res = dec.generate(enc.cuda(), [[tok.sot, tok.first_lang, tok.transcribe, tok.no_timestamps]] * 2, max_length=10,
+                       suppress_tokens=list(range(shape.vocab)))
+    assert [r.sequences_ids[0] for r in res] == [[], []]
 
 
 def test_encode_then_generate_end_to_end():

@@ -256,10 +256,11 @@ __global__ void __launch_bounds__(kSampleThreads) decode_sample_kernel(const Sam
                     chosen = ts.i;
                     lse = ts_lse;
                 }
+                if (chosen < 0 || chosen >= V) chosen = p.eot;       // every id forbidden (a degenerate suppress list): end
                 if (p.argmax_out) p.argmax_out[(size_t)b * p.tokens_ld + pos] = chosen;
                 int nxt = chosen;
                 if (p.forced && n_sampled < p.n_forced) nxt = p.forced[(size_t)b * p.forced_ld + n_sampled];
-                p.score[b] += lg[nxt] - lse;
+                if (lse > -INFINITY) p.score[b] += lg[nxt] - lse;
                 toks[pos] = nxt;
                 if (nxt == p.eot) {
                     p.done[b] = 1;

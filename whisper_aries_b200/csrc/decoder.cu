@@ -469,6 +469,11 @@ cudaError_t decoder_generate(DecoderPlan* pl, const void* enc_out, int batch, co
     std::vector<int> h_forced;
     if (o.forced && o.n_forced > 0) {
         h_forced.assign(o.forced, o.forced + (size_t)batch * o.n_forced);
+        for (int t : h_forced)
+            if (bad_id(t)) {
+                pl->error = "forced token id outside the vocabulary";
+                return cudaErrorInvalidValue;
+            }
         ARIES_TRY(cudaMemcpyAsync(pl->forced, h_forced.data(), h_forced.size() * 4, cudaMemcpyHostToDevice, stream),
                   "upload forced tokens");
     }
