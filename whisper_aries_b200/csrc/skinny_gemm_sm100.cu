@@ -15,6 +15,8 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include "ptx.cuh"
 #include "skinny.h"
 
@@ -34,8 +36,12 @@ constexpr uint32_t kTmemCols = 128;
 constexpr int kMaxSplits = 8;
 
 __host__ __device__ inline int stage_bytes(int NB) { return kWBytes + NB * BK * 2; }
-inline int smem_bytes(int NB, bool ln = false) {
-    const int pipe = (ln ? kStagesLn : kStages) * stage_bytes(NB);
+// MODE 0: token rows by TMA, 4-stage ring (two CTAs per SM: grids beyond one wave, i.e. the logits projection)
+// MODE 1: fused LayerNorm, 8 resident stages    MODE 2: token rows by TMA, 8 stages (one CTA per SM: with programmatic
+// dependent launch up to 8 weight blocks per CTA are in flight before the previous kernel has finished)
+constexpr int kModeRing4 = 0, kModeLn = 1, kModeRing8 = 2;
+inline int smem_bytes(int NB, int mode = kModeRing4) {
+    const int pipe = (mode == kModeRing4 ? kStages : kStagesLn) * stage_bytes(NB);
     const int part = NB * BMW * 4;
     return (pipe > part ? pipe : part) + 256 + 1024;
 }
@@ -133,11 +139,12 @@ __device__ __forceinline__ void store_four(const SkinnyParams& p, int b, int n, 
         if (n + e < p.N) store_one<EPI>(p, b, n + e, vv[e], rr[e]);
 }
 
-template <int EPI, bool LN>
+template <int EPI, int MODE>
 __global__ void __launch_bounds__(kThreads)
 skinny_gemm_tcgen05(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
                     const SkinnyParams p) {
-    constexpr int kStages = LN ? aries::kStagesLn : aries::kStages;      // shadows the namespace constant
+    constexpr bool LN = MODE == kModeLn;
+    constexpr int kStages = (MODE == kModeRing4) ? aries::kStages : aries::kStagesLn;      // shadows the namespace constant
     extern __shared__ uint8_t smem_raw[];
     __shared__ float s_gamma[LN ? kStagesLn * BK : 1], s_beta[LN ? kStagesLn * BK : 1];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -402,11 +409,17 @@ skinny_gemm_tcgen05(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
 template <int EPI>
 cudaError_t launch_epi(const CUtensorMap& tw, const CUtensorMap& tx, const SkinnyParams& p, cudaStream_t stream) {
     const int n_tiles = (p.N + BMW - 1) / BMW;
-    const bool ln = p.ln_x != nullptr;
+    // deep ring whenever the grid fits one CTA per SM anyway (every decode GEMM but the logits projection)
+    static const bool ring8 = [] {                   // ARIES_SKINNY_RING8=1 enables the deep ring (off until measured)
+        const char* e = getenv("ARIES_SKINNY_RING8");
+        return e && e[0] == '1';
+    }();
+    const int mode = p.ln_x != nullptr ? kModeLn
+                     : (ring8 && p.NB <= 64 && n_tiles * p.splits <= 160 ? kModeRing8 : kModeRing4);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(n_tiles, p.splits);
     cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = smem_bytes(p.NB, ln);
+    cfg.dynamicSmemBytes = smem_bytes(p.NB, mode);
     cfg.stream = stream;
     cudaLaunchAttribute attr[2];
     int na = 0;
@@ -424,17 +437,21 @@ cudaError_t launch_epi(const CUtensorMap& tw, const CUtensorMap& tx, const Skinn
     }
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    if (ln) return cudaLaunchKernelEx(&cfg, skinny_gemm_tcgen05<EPI, true>, tw, tx, p);
-    return cudaLaunchKernelEx(&cfg, skinny_gemm_tcgen05<EPI, false>, tw, tx, p);
+    if (mode == kModeLn) return cudaLaunchKernelEx(&cfg, skinny_gemm_tcgen05<EPI, kModeLn>, tw, tx, p);
+    if (mode == kModeRing8) return cudaLaunchKernelEx(&cfg, skinny_gemm_tcgen05<EPI, kModeRing8>, tw, tx, p);
+    return cudaLaunchKernelEx(&cfg, skinny_gemm_tcgen05<EPI, kModeRing4>, tw, tx, p);
 }
 
 template <int EPI>
 cudaError_t set_smem() {
-    cudaError_t e = cudaFuncSetAttribute(skinny_gemm_tcgen05<EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(skinny_gemm_tcgen05<EPI, kModeRing4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          smem_bytes(128));
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(skinny_gemm_tcgen05<EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                smem_bytes(16, true));
+    e = cudaFuncSetAttribute(skinny_gemm_tcgen05<EPI, kModeRing8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             smem_bytes(64, kModeRing8));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(skinny_gemm_tcgen05<EPI, kModeLn>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                smem_bytes(16, kModeLn));
 }
 
 }  // namespace
