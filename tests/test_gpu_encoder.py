@@ -1,7 +1,9 @@
 """GPU parity: the encoder forward through the drop-in surface (WhisperModel.encode / aries_encoder_run) against the
 fp32 torch oracle, the golden fixtures (oracle + HF transformers) and the greedy-decode probe.
 Tolerances (north_star: "within bf16 tolerance, max-abs error and cosine >= 0.999 stated"): outputs are LayerNorm-ed
-(unit scale); we require cosine >= 0.999 on the whole tensor AND on the worst row, and max-abs <= 0.12."""
+(unit scale); we require cosine >= 0.999 on the whole tensor AND on the worst row, and max-abs <= 0.12 -- for every
+shape, large-v3 and medium included.  Measured on a B200 (profiles/r02/parity.json): large-v3 cosine 0.99996, worst row
+0.99998, max-abs 0.035 (one window and the 64-window launch alike); medium 0.99996 / 0.99998 / 0.032."""
 import os
 
 import numpy as np
@@ -89,7 +91,7 @@ def test_large_v3_single_window_vs_oracle():
     out = model.encode(feats)
     ref = oenc.encoder_forward(feats, w, shape)
     cmp = oenc.compare(out.cpu(), ref)
-    assert cmp["cosine"] >= COS and cmp["min_row_cosine"] >= 0.995 and cmp["max_abs"] <= 0.2, cmp
+    assert cmp["cosine"] >= COS and cmp["min_row_cosine"] >= COS and cmp["max_abs"] <= MAX_ABS, cmp
     probe, toks, margin = GreedyProbe.pick(ref, shape.d_model, shape.n_heads, steps=12, max_tries=64, n_layers=1)
     got, _ = probe.greedy(out.cpu(), steps=12)
     assert torch.equal(got, toks)
@@ -115,7 +117,7 @@ def test_medium_alt_shape_vs_oracle():
     assert out.shape == (2, 1500, 1024)
     ref = oenc.encoder_forward(feats[:1], w, shape)
     cmp = oenc.compare(out[:1].cpu(), ref)
-    assert cmp["cosine"] >= COS and cmp["min_row_cosine"] >= 0.995 and cmp["max_abs"] <= 0.2, cmp
+    assert cmp["cosine"] >= COS and cmp["min_row_cosine"] >= COS and cmp["max_abs"] <= MAX_ABS, cmp
     two_step = model.encode(model.feature_extractor(torch.from_numpy(pcm).cuda(), frames_out=3000))
     assert torch.equal(out, two_step)
 
@@ -147,4 +149,23 @@ def test_one_hour_stream_sharded_like_config4():
     k = 77
     feats = omel.log_mel_window(windows[k].numpy(), shape.n_mels)[None]
     cmp = oenc.compare(out[k:k + 1], oenc.encoder_forward(feats, w, shape))
-    assert cmp["cosine"] >= COS and cmp["max_abs"] <= 0.2, cmp
+    assert cmp["cosine"] >= COS and cmp["min_row_cosine"] >= COS and cmp["max_abs"] <= MAX_ABS, cmp
+
+
+def test_benchmarked_launch_b64_large_v3_vs_oracle_and_batch_invariance():
+    """BASELINE config 3, the launch bench.py times: ONE ``encode_audio`` call over 64 large-v3 windows (M = 96 000
+    GEMM rows, h = 983 MB, qk = 492 MB).  Four scattered windows are compared with the fp32 oracle at the documented
+    bounds, and each must be byte-identical to the same window encoded alone (batch invariance: no tile of the
+    64-window launch may see a neighbouring window's rows)."""
+    model, shape, w = model_for("large-v3")
+    pcm = osynth.batch_signals(64, 0)
+    dev = torch.from_numpy(pcm).cuda()
+    big = model.encode_audio(dev)
+    torch.cuda.synchronize()
+    assert big.shape == (64, 1500, shape.d_model) and torch.isfinite(big.float()).all()
+    for k in (0, 21, 42, 63):
+        alone = model.encode_audio(dev[k:k + 1])
+        assert torch.equal(alone[0], big[k]), f"window {k}: the 64-window launch differs from the single-window launch"
+        feats = omel.log_mel_window(pcm[k], shape.n_mels)[None]
+        cmp = oenc.compare(big[k:k + 1].cpu(), oenc.encoder_forward(feats, w, shape))
+        assert cmp["cosine"] >= COS and cmp["min_row_cosine"] >= COS and cmp["max_abs"] <= MAX_ABS, (k, cmp)
