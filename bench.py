@@ -225,7 +225,7 @@ def cpu_decode_sample(model: str, n_tokens: int):
 cpu_decode_sample.cache = {}
 
 
-def run_decode(args, rank: int, local_rank: int, world: int) -> int:
+def run_decode(args, rank: int, local_rank: int, world: int, sub: bool = False):
     """--mode decode: greedy ``generate`` (ctranslate2 Whisper.generate, beam 1) for `windows` windows per GPU and
     `tokens` sampled positions per window on a resident bf16 encoder output (synthetic, LayerNorm-ed scale), random-init
     large-v3-shaped decoder.  Weak scaling, no collective.  HBM-bound: per step the decoder reads its weights once and
@@ -236,6 +236,8 @@ def run_decode(args, rank: int, local_rank: int, world: int) -> int:
         raise SystemExit("bench.py needs a B200: whisper_aries_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if sub:
+        world = 1                       # a sub-object of the default line: rank 0's GPU only, no process group touched
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -364,13 +366,17 @@ def run_decode(args, rank: int, local_rank: int, world: int) -> int:
             "phases": {"cross_kv_projection_ms": kv_ms / args.steps, "decode_loop_ms": loop_ms / args.steps,
                        "ms_per_token_step": ms_per_token_step, "kernels_per_token_step": st["kernels_per_step"]},
             "cpu_baseline": cpu}
+    if sub:
+        del dec, enc
+        torch.cuda.empty_cache()
+        return line
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
-def run_transcribe(args, rank: int, local_rank: int, world: int) -> int:
+def run_transcribe(args, rank: int, local_rank: int, world: int, sub: bool = False, model=None):
     """--mode transcribe: the whole widened path through the public API -- pinned int16 PCM windows -> ChunkScheduler ->
     gpu_transcribe_worker (H2D, s16 -> f32, log-mel, encoder, cross K|V, greedy decode of `tokens` ids per window) -> token
     rows on the host.  Wall clock, host buffers, copies inside the timed region; audio-seconds per second."""
@@ -381,17 +387,23 @@ def run_transcribe(args, rank: int, local_rank: int, world: int) -> int:
         raise SystemExit("bench.py needs a B200: whisper_aries_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if sub:
+        world = 1
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    from whisper_aries_b200 import ChunkScheduler, WhisperModel, gpu_transcribe_worker, synthetic
+    from whisper_aries_b200 import ChunkScheduler, WhisperDecoder, WhisperModel, gpu_transcribe_worker, synthetic
     eshape, dshape = synthetic.SHAPES[args.model], synthetic.DEC_SHAPES[args.model]
-    w = dict(synthetic.encoder_weights(eshape, 1234))
-    w.update(synthetic.decoder_weights_fast(dshape, 0))
     B, T = args.windows, args.tokens
-    model = WhisperModel(eshape, w, device="cuda", device_index=local_rank, decoder_shape=dshape,
-                         max_batch=min(args.micro_batch, 128))
-    del w
+    if model is None:
+        w = dict(synthetic.encoder_weights(eshape, 1234))
+        w.update(synthetic.decoder_weights_fast(dshape, 0))
+        model = WhisperModel(eshape, w, device="cuda", device_index=local_rank, decoder_shape=dshape,
+                             max_batch=min(args.micro_batch, 128))
+        del w
+    elif model.decoder is None:                     # sub-object: reuse the encoder replica already resident on this GPU
+        model.decoder = WhisperDecoder(dshape, synthetic.decoder_weights_fast(dshape, 0), device=f"cuda:{local_rank}",
+                                       max_batch=min(args.micro_batch, 128))
     tok = model.decoder.tokens
     prompt = [tok.sot, tok.first_lang, tok.transcribe]
     L = len(prompt) + T
@@ -445,10 +457,100 @@ def run_transcribe(args, rank: int, local_rank: int, world: int) -> int:
                 "tokens_per_s": world * B * T * args.steps / dt,
                 "last_micro_batch": {"cross_kv_ms": st["cross_kv_ms"], "decode_ms": st["decode_ms"], "steps": st["steps"],
                                      "kernels_per_step": st["kernels_per_step"]}}
+        if sub:
+            sched.close()
+            model.decoder.close()
+            model.decoder = None
+            torch.cuda.empty_cache()
+            return line
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def build_replicas(model_name: str, weights: dict, n_gpus: int, first=None):
+    """One WhisperModel replica per GPU of this process (full weight copy each: 1.27 GB bf16 for large-v3), built in
+    parallel threads -- the ctypes call that converts and uploads the weights releases the GIL."""
+    from whisper_aries_b200 import WhisperModel
+    models = [first] + [None] * (n_gpus - 1) if first is not None else [None] * n_gpus
+    errs = []
+
+    def make(i):
+        try:
+            models[i] = WhisperModel(model_name, weights, device="cuda", device_index=i)
+        except Exception as exc:                                   # pragma: no cover
+            errs.append(f"gpu {i}: {type(exc).__name__}: {exc}")
+
+    ts = [threading.Thread(target=make, args=(i,)) for i in range(n_gpus) if models[i] is None]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    if errs:
+        raise RuntimeError("; ".join(errs))
+    return models
+
+
+def measure_inprocess_job(models, n_windows: int, seed0: int, reps: int = 3, micro_batch: int | None = None) -> dict:
+    """north_star (3) / BASELINE configs 4 and 5: ONE process shards ``n_windows`` 30-s windows over ``len(models)`` GPUs
+    (ChunkScheduler, one worker thread + replica per GPU, static block partition, no collective) and gathers the bf16
+    encoder states into ONE pinned host buffer.  Strong scaling: the job is fixed, wall clock runs from the first H2D
+    to the last row on the host.  Returns the best and median of ``reps`` runs after one warm-up run."""
+    import numpy as np
+    import torch
+    from whisper_aries_b200 import synthetic
+    from whisper_aries_b200.scheduler import ChunkScheduler, gpu_worker, partition_windows
+    shape = models[0].shape
+    n_gpus = len(models)
+    base = synthetic.batch_signals(min(n_windows, 12), first_seed=seed0)
+    pcm = torch.from_numpy(np.concatenate([base] * (-(-n_windows // base.shape[0])))[:n_windows].copy()).pin_memory()
+    out = torch.empty((n_windows, shape.n_ctx, shape.d_model), dtype=torch.bfloat16).pin_memory()
+    shard = -(-n_windows // n_gpus)
+    mb = micro_batch or min(64, max(8, -(-shard // 2)))           # two micro-batches per shard: copies overlap compute
+    times = []
+    with ChunkScheduler([gpu_worker(m, micro_batch=mb) for m in models]) as sched:
+        for it in range(reps + 1):
+            for m in models:
+                torch.cuda.synchronize(m.encoder.device)
+            t0 = time.perf_counter()
+            res = sched.run(pcm, out)
+            dt = time.perf_counter() - t0
+            if not all(r.success for r in res):
+                raise RuntimeError(f"in-process job failed: {[r.error for r in res if not r.success]}")
+            if it:
+                times.append(dt)
+        per_worker = [round(r.processing_time * 1e3, 2) for r in res]
+    times.sort()
+    audio = n_windows * WINDOW_SECONDS
+    checksum = float(out[:: max(1, n_windows // 8)].float().abs().mean())
+    return {"windows": n_windows, "n_gpus": n_gpus, "windows_per_gpu": [b - a for a, b in partition_windows(n_windows, n_gpus)],
+            "micro_batch": mb, "reps": reps, "wall_ms_best": times[0] * 1e3, "wall_ms_median": times[len(times) // 2] * 1e3,
+            "audio_s_per_s": audio / times[len(times) // 2], "audio_s_per_s_best": audio / times[0],
+            "last_run_worker_ms": per_worker, "h2d_bytes": int(pcm.numel() * 4), "d2h_bytes": int(out.numel() * 2),
+            "checksum_mean_abs": checksum,
+            "api": "ChunkScheduler([gpu_worker(replica_i)]).run(pinned pcm, ONE pinned gather buffer); wall clock, first H2D -> last row on host"}
+
+
+def parity_object(model, model_name: str, weights: dict) -> dict:
+    """One window of the benchmarked model against the CPU oracle, outside every timed region (the oracle is the checker)."""
+    import numpy as np
+    import torch
+    from oracle import encoder as oenc, logmel as omel, synth as osynth
+    shape = osynth.SHAPES[model_name]
+    pcm = osynth.am_chirp(1)
+    want_mel = omel.log_mel(pcm, shape.n_mels)
+    got_mel = model.feature_extractor(pcm)
+    ref = oenc.encoder_forward(omel.pad_or_trim(want_mel)[None], weights, shape)
+    got = model.encode_audio(torch.from_numpy(pcm).to(model.encoder.device)[None])
+    cmp = oenc.compare(got.cpu(), ref)
+    return {"window": "am_chirp(seed 1), 30 s", "mel_max_abs": float(np.abs(got_mel - want_mel).max()), "mel_tolerance": 1e-4,
+            "encoder_max_abs": cmp["max_abs"], "encoder_cosine": cmp["cosine"], "encoder_min_row_cosine": cmp["min_row_cosine"],
+            "encoder_bounds": {"cosine": 0.999, "min_row_cosine": 0.999, "max_abs": 0.12},
+            "ok": bool(np.abs(got_mel - want_mel).max() <= 1e-4 and cmp["cosine"] >= 0.999 and
+                       cmp["min_row_cosine"] >= 0.999 and cmp["max_abs"] <= 0.12),
+            "oracle": "oracle/logmel.py + oracle/encoder.py, fp32 on the host (parity unpinned vs faster-whisper/CTranslate2: "
+                      "not installable offline); full report: profiles/r02/parity.json"}
 
 
 def main() -> int:
@@ -463,6 +565,8 @@ def main() -> int:
     ap.add_argument("--model", default="large-v3")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the sub-objects measured after the timed region (parity, config4, config5, decode, transcribe)")
     ap.add_argument("--mode", default="encode", choices=["encode", "decode", "transcribe"],
                     help="encode = the headline log-mel + encoder path; decode = row f1, greedy generate on a resident "
                          "encoder output; transcribe = int16 PCM -> token ids through the scheduler (rows a + f1 + f3)")
@@ -573,9 +677,16 @@ def main() -> int:
                "api": "ChunkScheduler(gpu_worker(WhisperModel)).run(pinned pcm, pinned out)",
                "micro_batch": args.micro_batch}
 
+    # Rank 0 goes on to the in-process multi-GPU jobs (configs 4 / 5) and needs every GPU of the box to itself: the other
+    # ranks drop their replicas and park on the rendezvous store (a host-side wait: an NCCL barrier would spin on their GPUs).
+    store = dist.distributed_c10d._get_default_store() if world > 1 else None
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        torch.cuda.empty_cache()                         # this rank's GPU stays idle from here on (its ~5 GB stay allocated)
+        try:
+            store.wait(["aries_bench_extras_done"], __import__("datetime").timedelta(seconds=1500))
+        except Exception:
+            pass
+        dist.destroy_process_group()
         return 0
 
     # ---------------------------------------------------------------- roofline objects (rank 0's kernels)
@@ -624,6 +735,62 @@ def main() -> int:
                                   f"faster-whisper compute_type=int8; faster-whisper/ctranslate2 not installable offline)",
                         "fp32_value": n_sample * WINDOW_SECONDS / r32["total_s"]}
 
+    # ---------------------------------------------------------------- outside every timed region: parity + widened jobs
+    del pcm_dev, out_dev, out_host, pcm_host
+    torch.cuda.empty_cache()
+    extras = {}
+    if not args.no_extras:
+        def guarded(name, fn):
+            t0 = time.perf_counter()
+            try:
+                extras[name] = fn()
+            except Exception as exc:                              # an extra must never cost the headline line
+                extras[name] = {"error": f"{type(exc).__name__}: {exc}"}
+            if isinstance(extras[name], dict):
+                extras[name]["bench_seconds"] = round(time.perf_counter() - t0, 2)
+
+        n_dev = min(world, torch.cuda.device_count())
+        torch.set_num_threads(max(1, os.cpu_count() or 1))       # the oracle (parity checker) may use the whole host
+        weights = synthetic.encoder_weights(shape, 1234)
+        guarded("parity", lambda: parity_object(model, args.model, weights))
+
+        def config4():
+            # BASELINE config 4: 1-hour stream = 120 windows, strong scaling over the N GPUs of this run (seed 7)
+            models = build_replicas(args.model, weights, n_dev, first=model)
+            r = measure_inprocess_job(models, 120, 7000)
+            if n_dev > 1:
+                r["one_gpu"] = {k: v for k, v in measure_inprocess_job(models[:1], 120, 7000).items()
+                                if k in ("wall_ms_median", "audio_s_per_s", "micro_batch")}
+            r["config"] = f"BASELINE config 4: {args.model}, 120 x 30-s windows (1 h) over {n_dev} GPU(s), one process"
+            for m in models[1:]:
+                m.encoder.close()
+            return r
+
+        guarded("config4", config4)
+        del weights
+
+        def config5():
+            # BASELINE config 5: Whisper medium (80 bins, d 1024, 16 heads, 24 layers), 128 windows over the N GPUs
+            mshape = synthetic.SHAPES["medium"]
+            mw = synthetic.encoder_weights(mshape, 1234)
+            models = build_replicas("medium", mw, n_dev)
+            r = measure_inprocess_job(models, 128, 500)
+            r["config"] = f"BASELINE config 5: medium, 128 x 30-s windows over {n_dev} GPU(s), one process (alt-shape path)"
+            r["encoder_tflops"] = 128 * mshape.flops_per_window / (r["wall_ms_median"] * 1e-3) / 1e12
+            for m in models:
+                m.encoder.close()
+            return r
+
+        guarded("config5", config5)
+        if world == 1:
+            import copy
+            sub = copy.copy(args)
+            sub.steps, sub.warmup, sub.tokens, sub.no_cpu_baseline, sub.windows, sub.micro_batch = 2, 1, 16, True, 64, 64
+            guarded("decode", lambda: run_decode(sub, 0, local_rank, 1, sub=True))
+            guarded("transcribe", lambda: run_transcribe(sub, 0, local_rank, 1, sub=True, model=model))
+    if store is not None:
+        store.set("aries_bench_extras_done", "1")
+
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
@@ -634,6 +801,7 @@ def main() -> int:
             "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
             "roofline": roofline, "roofline_mel": roofline_mel, "encoder_tflops": encoder_tflops,
             "encoder_frac_of_bf16_peak": encoder_tflops / peak_tf, "kernels": kernels, "cpu_baseline": cpu_baseline}
+    line.update(extras)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -160,3 +160,83 @@ def test_reference_chunk_plan_and_zero_copy_windows():
     assert np.array_equal(w[:6].reshape(-1), pcm[: 6 * 480000])
     assert chunk_windows(pcm, 5, 5).shape == (0, 480000)
     assert chunk_windows(pcm, 0, 100).shape == (1, 480000)
+
+
+def test_dynamic_queue_self_schedules_and_threads_persist():
+    """The reference's self-scheduling (ref: final_optimized_transcriber.py:243-246, :256-299): items on ONE shared queue,
+    a slow worker takes fewer of them, results come back in window order, and the worker threads survive ``run``."""
+    import threading
+    import time
+    windows = np.arange(24 * 2, dtype=np.float32).reshape(24, 2)
+    taken = {0: 0, 1: 0}
+    idents = {0: set(), 1: set()}
+
+    def make(worker_id, delay):
+        def run(w, start, stop, o):
+            time.sleep(delay)
+            taken[worker_id] += stop - start
+            idents[worker_id].add(threading.get_ident())
+            o[start:stop, 0] = w[start:stop].sum(axis=1)
+        return run
+
+    sched = ChunkScheduler([make(0, 0.001), make(1, 0.05)], policy="dynamic", chunk=2)
+    for _ in range(2):
+        out = np.zeros((24, 1), np.float32)
+        res = sched.run(windows, out)
+        assert [r.chunk_id for r in res] == list(range(12)) and all(r.success for r in res)
+        assert [(r.start, r.stop) for r in res] == [(i, i + 2) for i in range(0, 24, 2)]
+        assert np.array_equal(out[:, 0], windows.sum(axis=1))
+    assert taken[0] > taken[1] > 0 and taken[0] + taken[1] == 48
+    assert len(idents[0]) == 1 and len(idents[1]) == 1           # the same two threads served both calls
+    sched.close()
+    with pytest.raises(RuntimeError):
+        sched.run(windows, np.zeros((24, 1), np.float32))
+    assert [(w.start, w.stop) for w in ChunkScheduler([make(0, 0)] * 2, policy="dynamic").plan(17)] == \
+        [(0, 3), (3, 6), (6, 9), (9, 12), (12, 15), (15, 17)]
+    with pytest.raises(ValueError):
+        ChunkScheduler([], policy="static")
+    with pytest.raises(ValueError):
+        ChunkScheduler([make(0, 0)], policy="round-robin")
+
+
+def test_collector_timeout_keeps_waiting_while_a_worker_lives_and_a_failed_item_does_not_stop_its_worker():
+    import time
+    windows = np.zeros((4, 1), np.float32)
+
+    def slow(w, start, stop, o):
+        if start == 0:
+            time.sleep(0.3)                                       # three collector timeouts pass; the thread is alive
+        if start == 1:
+            raise ValueError("bad window")
+        o[start:stop] = 1
+
+    with ChunkScheduler([slow], policy="dynamic", chunk=1, result_timeout=0.1) as sched:
+        out = np.zeros((4, 1), np.float32)
+        res = sched.run(windows, out)
+    assert [r.success for r in res] == [True, False, True, True] and "bad window" in res[1].error
+    assert out[:, 0].tolist() == [1, 0, 1, 1] and res[0].processing_time >= 0.3
+
+
+def test_lengths_reach_the_worker_and_ragged_tail_keeps_its_length():
+    from whisper_aries_b200 import chunk_windows
+    from whisper_aries_b200.scheduler import _length_runs
+    pcm = np.arange(10, dtype=np.float32) + 1
+    w, n = chunk_windows(pcm, 0, 10, 4, return_lengths=True)
+    assert w.shape == (3, 4) and n.tolist() == [4, 4, 2] and w[2].tolist() == [9, 10, 0, 0]
+    w, n = chunk_windows(pcm, 0, 8, 4, return_lengths=True)
+    assert n.tolist() == [4, 4]
+    assert _length_runs(n, 0, 2, 4) == [(0, 2, 4)] and _length_runs(None, 1, 3, 4) == [(1, 3, 4)]
+    assert _length_runs(np.array([4, 4, 2, 4]), 0, 4, 4) == [(0, 2, 4), (2, 3, 2), (3, 4, 4)]
+    with pytest.raises(ValueError):
+        _length_runs(np.array([4, 0]), 0, 2, 4)
+    seen = []
+
+    def worker(win, start, stop, o, lengths=None):
+        seen.append(None if lengths is None else [int(v) for v in lengths[start:stop]])
+
+    w, n = chunk_windows(pcm, 0, 10, 4, return_lengths=True)
+    sched = ChunkScheduler([worker])
+    assert all(r.success for r in sched.run(w, np.zeros((3, 1)), lengths=n)) and seen == [[4, 4, 2]]
+    with pytest.raises(ValueError):
+        sched.run(w, np.zeros((3, 1)), lengths=n[:2])
+    sched.close()

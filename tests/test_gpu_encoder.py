@@ -169,3 +169,83 @@ def test_benchmarked_launch_b64_large_v3_vs_oracle_and_batch_invariance():
         feats = omel.log_mel_window(pcm[k], shape.n_mels)[None]
         cmp = oenc.compare(big[k:k + 1].cpu(), oenc.encoder_forward(feats, w, shape))
         assert cmp["cosine"] >= COS and cmp["min_row_cosine"] >= COS and cmp["max_abs"] <= MAX_ABS, (k, cmp)
+
+
+def test_ragged_tail_window_matches_pad_or_trim_of_the_features():
+    """A 65-s call = two full windows + a 5-s tail.  With ``lengths`` the tail runs with its true sample count, so its
+    features are ``pad_or_trim(log_mel(tail))`` -- 0.0 after the last real frame (faster-whisper's ``pad_or_trim``) --
+    and not the log-mel of zero PCM (which would put about -0.6 in every padded frame)."""
+    from whisper_aries_b200.scheduler import ChunkScheduler, chunk_windows, gpu_worker
+    model, shape, w = model_for("micro")
+    pcm = np.concatenate([osynth.window_signal(90), osynth.window_signal(91), osynth.window_signal(92)[:80000]])
+    windows, lengths = chunk_windows(pcm, 0, pcm.shape[0], return_lengths=True)
+    assert lengths.tolist() == [480000, 480000, 80000]
+    out = torch.empty((3, 1500, shape.d_model), dtype=torch.bfloat16).pin_memory()
+    with ChunkScheduler([gpu_worker(model, micro_batch=2)]) as sched:
+        assert all(r.success for r in sched.run(torch.from_numpy(windows).pin_memory(), out, lengths=lengths))
+    tail = omel.log_mel_window(pcm[960000:], shape.n_mels)
+    assert (tail[:, 501:] == 0).all() and np.abs(tail[:, :500]).max() > 0.1          # the oracle pads FEATURES with 0.0
+    got_mel = model.feature_extractor(torch.from_numpy(pcm[960000:]).cuda(), frames_out=3000).cpu().numpy()
+    assert np.abs(got_mel - tail).max() <= 1e-4
+    feats = np.stack([omel.log_mel_window(windows[0], shape.n_mels), omel.log_mel_window(windows[1], shape.n_mels), tail])
+    cmp = oenc.compare(out, oenc.encoder_forward(feats, w, shape))
+    assert cmp["cosine"] >= COS and cmp["min_row_cosine"] >= COS and cmp["max_abs"] <= MAX_ABS, cmp
+    # without lengths the tail is zero PCM: a different (non-upstream) input, visibly so
+    out0 = torch.empty_like(out).pin_memory()
+    with ChunkScheduler([gpu_worker(model, micro_batch=2)]) as sched:
+        sched.run(torch.from_numpy(windows).pin_memory(), out0)
+    assert torch.equal(out0[:2], out[:2]) and not torch.equal(out0[2], out[2])
+
+
+def test_encode_long_uses_whole_call_features_like_upstream_transcribe():
+    """``encode_long``: features over the whole 65-s call (ONE clamp maximum; frames at the 30-s boundaries see real
+    samples on both sides), sliced at seek = 0, 3000, 6000 with content_frames = frames - 1, each ``pad_or_trim``-ed."""
+    model, shape, w = model_for("micro")
+    pcm = np.concatenate([0.05 * osynth.window_signal(93), osynth.window_signal(94), osynth.window_signal(95)[:80000]])
+    full = omel.log_mel(pcm, shape.n_mels)                         # [80, 6501]
+    content = full.shape[1] - 1
+    feats = np.stack([omel.pad_or_trim(full[:, k * 3000: min((k + 1) * 3000, content)]) for k in range(3)])
+    got = model.encode_long(pcm)
+    assert got.shape == (3, 1500, shape.d_model)
+    cmp = oenc.compare(got.cpu(), oenc.encoder_forward(feats, w, shape))
+    assert cmp["cosine"] >= COS and cmp["min_row_cosine"] >= COS and cmp["max_abs"] <= MAX_ABS, cmp
+    # the quiet first window is clamped by the loud second one's maximum: per-window features differ there
+    per_window = omel.log_mel_window(pcm[:480000], shape.n_mels)
+    assert np.abs(per_window - feats[0]).max() > 1e-3
+
+
+def test_encode_pcm_rejects_a_wrong_out_buffer():
+    model, shape, _ = model_for("micro")
+    pcm = torch.zeros((2, 480000), device="cuda")
+    for bad in (torch.empty((2, 1500, shape.d_model), dtype=torch.float16, device="cuda"),
+                torch.empty((1, 1500, shape.d_model), dtype=torch.bfloat16, device="cuda"),
+                torch.empty((2, 1500, 2 * shape.d_model), dtype=torch.bfloat16, device="cuda")[:, :, ::2],
+                torch.empty((2, 1500, shape.d_model), dtype=torch.bfloat16)):
+        with pytest.raises(ValueError, match="out must be"):
+            model.encode_audio(pcm, out=bad)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs in one process")
+def test_in_process_scheduler_over_all_gpus_reproduces_the_one_gpu_bytes():
+    """north_star (3): ONE process, one worker thread + one model replica per GPU, one pinned gather buffer.
+    The N-GPU bytes must equal the 1-GPU bytes for both policies (static blocks and the dynamic queue)."""
+    from whisper_aries_b200 import WhisperModel, synthetic
+    from whisper_aries_b200.scheduler import ChunkScheduler, gpu_worker
+    n_gpu = torch.cuda.device_count()
+    shape = synthetic.SHAPES["tiny"]
+    w = synthetic.encoder_weights(shape, 1234)
+    models = [WhisperModel("tiny", w, device="cuda", device_index=i) for i in range(n_gpu)]
+    pcm = torch.from_numpy(osynth.batch_signals(4 * n_gpu + 3, 300)).pin_memory()
+    n = pcm.shape[0]
+    one = torch.empty((n, 1500, shape.d_model), dtype=torch.bfloat16).pin_memory()
+    with ChunkScheduler([gpu_worker(models[0], micro_batch=4)]) as s1:
+        assert all(r.success for r in s1.run(pcm, one))
+    for policy in ("static", "dynamic"):
+        many = torch.zeros((n, 1500, shape.d_model), dtype=torch.bfloat16).pin_memory()
+        with ChunkScheduler([gpu_worker(m, micro_batch=4) for m in models], policy=policy, chunk=3) as sN:
+            res = sN.run(pcm, many)
+            assert all(r.success for r in res), [r.error for r in res]
+            assert len({r.worker_id for r in res if r.n_windows}) == n_gpu or policy == "dynamic"
+            assert torch.equal(many, one), policy
+            many.zero_()
+            assert all(r.success for r in sN.run(pcm, many)) and torch.equal(many, one)     # threads are reused

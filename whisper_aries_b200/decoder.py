@@ -38,6 +38,7 @@ class WhisperDecoder:
         self.tokens = tokens or WhisperTokens.for_vocab(self.shape.vocab)
         self.suppress_ids = [int(t) for t in suppress_ids]
         self.max_batch = int(max_batch)
+        self._warned_no_suppress = False
         self.device_index = _lib.device_index_of(device)
         self.device = torch.device("cuda", self.device_index)
         self._ctx = _lib.Context.get(self.device_index)
@@ -81,6 +82,13 @@ class WhisperDecoder:
         ids = []
         for s in suppress_tokens or ():
             if int(s) == -1:
+                if not self.suppress_ids and not self._warned_no_suppress:
+                    # upstream reads them from the model's config.json; a decoder built from a weights dict has none
+                    import warnings
+                    warnings.warn("suppress_tokens=-1 requested but this decoder has no suppress_ids (pass "
+                                  "suppress_ids=... or load a model directory with config.json): decoding WITHOUT "
+                                  "non-speech token suppression", RuntimeWarning, stacklevel=3)
+                    self._warned_no_suppress = True
                 ids.extend(self.suppress_ids)        # upstream: -1 expands to the model config's suppress_ids
             else:
                 ids.append(int(s))
@@ -168,15 +176,13 @@ class WhisperDecoder:
             part = enc[b0:b0 + self.max_batch]
             B = part.shape[0]
             pr = np.ascontiguousarray(np.asarray(prompts[b0:b0 + B], dtype=np.int32))
-            toks = np.empty((B, max_length), dtype=np.int32)
-            lens = np.zeros(B, dtype=np.int32)
-            scores = np.zeros(B, dtype=np.float32)
-            nsp = np.zeros(B, dtype=np.float32)
             if _forced is None and not _want_logits:
-                _lib.check(lib.aries_decoder_generate(self._handle, part.data_ptr(), B, pr.ctypes.data, P,
-                                                      ctypes.byref(opts), toks.ctypes.data, lens.ctypes.data,
-                                                      scores.ctypes.data, nsp.ctypes.data, stream))
+                toks, lens, scores, nsp = self._generate_arrays(part, pr, opts, max_length, stream)
             else:
+                toks = np.empty((B, max_length), dtype=np.int32)
+                lens = np.zeros(B, dtype=np.int32)
+                scores = np.zeros(B, dtype=np.float32)
+                nsp = np.zeros(B, dtype=np.float32)
                 forced = np.ascontiguousarray(np.asarray(_forced[b0:b0 + B], dtype=np.int32)) if _forced is not None \
                     else np.zeros((B, 0), dtype=np.int32)
                 argmax = np.full((B, max_length), -1, dtype=np.int32)
@@ -204,3 +210,38 @@ class WhisperDecoder:
         if _forced is not None or _want_logits:
             return results, extras
         return results
+
+    def _generate_arrays(self, part, prompts_i32, opts, max_length: int, stream):
+        """One ``aries_decoder_generate`` call for <= max_batch windows -> (tokens [B, max_length] int32 = prompt, sampled
+        ids, EOT padding; sampled-id counts [B]; cumulative log-probs [B]; no-speech probabilities [B])."""
+        B, P = prompts_i32.shape
+        toks = np.empty((B, max_length), dtype=np.int32)
+        lens = np.zeros(B, dtype=np.int32)
+        scores = np.zeros(B, dtype=np.float32)
+        nsp = np.zeros(B, dtype=np.float32)
+        _lib.check(self._ctx.lib.aries_decoder_generate(self._handle, part.data_ptr(), B, prompts_i32.ctypes.data, P,
+                                                        ctypes.byref(opts), toks.ctypes.data, lens.ctypes.data,
+                                                        scores.ctypes.data, nsp.ctypes.data, stream))
+        return toks, lens, scores, nsp
+
+    def generate_ids(self, encoder_output, prompt, *, max_length: int = 448, max_initial_timestamp_index: int = 50,
+                     suppress_blank: bool = True, suppress_tokens=(-1,)):
+        """Batch form used by ``gpu_transcribe_worker``: the same greedy ``generate`` with ONE prompt for every window,
+        returning arrays instead of per-window result objects -> (tokens int32 ``[B, max_length]``, counts ``[B]``)."""
+        import torch
+        B = encoder_output.shape[0]
+        self._check_inputs(encoder_output, [list(prompt)] * B)
+        max_length = min(int(max_length), self.shape.n_text_ctx)
+        if len(prompt) >= max_length:
+            raise ValueError("the prompt leaves no room to generate (prompt length >= max_length)")
+        opts, _keep = self._opts(max_length, suppress_blank, suppress_tokens, max_initial_timestamp_index)
+        enc = encoder_output.contiguous()
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        toks, lens = [], []
+        for b0 in range(0, B, self.max_batch):
+            part = enc[b0:b0 + self.max_batch]
+            pr = np.ascontiguousarray(np.tile(np.asarray(prompt, dtype=np.int32), (part.shape[0], 1)))
+            t, n, _, _ = self._generate_arrays(part, pr, opts, max_length, stream)
+            toks.append(t)
+            lens.append(n)
+        return np.concatenate(toks), np.concatenate(lens)

@@ -119,9 +119,15 @@ class WhisperEncoder:
         if pcm.stride(1) != 1:
             pcm = pcm.contiguous()
         batch, n = pcm.shape
+        if pcm.device != self.device:
+            raise ValueError(f"pcm is on {pcm.device}, this encoder on {self.device}")
         ws = self._workspace(batch)
+        want = (batch, self.shape.n_ctx, self.shape.d_model)
         if out is None:
-            out = torch.empty((batch, self.shape.n_ctx, self.shape.d_model), dtype=torch.bfloat16, device=self.device)
+            out = torch.empty(want, dtype=torch.bfloat16, device=self.device)
+        elif not (isinstance(out, torch.Tensor) and out.is_cuda and out.device == self.device and
+                  out.dtype == torch.bfloat16 and tuple(out.shape) == want and out.is_contiguous()):
+            raise ValueError(f"out must be a contiguous CUDA bfloat16 tensor {want} on {self.device}")
         stream = torch.cuda.current_stream(self.device).cuda_stream
         _lib.check(self._ctx.lib.aries_encode_pcm(self._handle, extractor._mel(), pcm.data_ptr(), batch, n,
                                                   pcm.stride(0), out.data_ptr(), ws.data_ptr(), ws.numel(), stream))
@@ -197,6 +203,26 @@ class WhisperModel:
         if isinstance(pcm, torch.Tensor) and pcm.dtype == torch.int16:
             pcm = pcm_s16_to_f32(pcm)
         return self.encoder.encode_pcm(self.feature_extractor, pcm, out=out)
+
+    def encode_long(self, pcm):
+        """One waveform longer than 30 s, exactly as upstream's ``transcribe`` feeds it to the encoder when it steps
+        ``seek`` by full windows: features over the WHOLE call (one clamp maximum, STFT frames that straddle a 30-s
+        boundary see real samples on both sides, ref call site final_optimized_transcriber.py:326 with 185-s chunks),
+        ``content_frames = frames - 1``, then ``pad_or_trim(features[:, seek:seek + 3000])`` per window -> CUDA bf16
+        ``[ceil(content_frames / 3000), 1500, d_model]``.  ``pcm``: 1-D float32 (numpy or torch, host or device)."""
+        import torch
+        x = pcm if isinstance(pcm, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(pcm, dtype=np.float32))
+        if x.dim() != 1 or x.numel() == 0:
+            raise ValueError("encode_long expects a non-empty 1-D waveform")
+        x = x.to(device=self.encoder.device, dtype=torch.float32)
+        feats = self.feature_extractor(x)                                   # [n_mels, (N + 160) // 160], device
+        content = feats.shape[-1] - 1
+        n_win = max(1, -(-content // 3000))
+        batch = torch.zeros((n_win, feats.shape[0], 3000), dtype=torch.float32, device=feats.device)
+        for k in range(n_win):
+            seg = feats[:, k * 3000: min((k + 1) * 3000, content)]
+            batch[k, :, : seg.shape[1]] = seg
+        return self.encoder.encode(batch)
 
 
 def pcm_s16_to_f32(pcm_s16, out=None):

@@ -15,9 +15,10 @@ Two launch styles share the partition function:
   * one process per GPU under torchrun      -> ``partition_windows(n, world_size)[rank]`` (bench.py --gpus N)."""
 from __future__ import annotations
 
+import queue
 import threading
 import time
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Callable, Optional, Sequence
 
 import numpy as np
@@ -60,8 +61,12 @@ def partition_windows(n_windows: int, n_parts: int) -> list[tuple[int, int]]:
 
 
 def split_into_windows(pcm: np.ndarray, n_samples: int = N_SAMPLES) -> np.ndarray:
-    """1-D f32 PCM -> ``[ceil(len / n_samples), n_samples]``, the last window zero-padded (what ``pad_or_trim`` of the
-    features amounts to for the final 30-s segment)."""
+    """1-D f32 PCM -> ``[ceil(len / n_samples), n_samples]``, the last window zero-padded IN THE SAMPLE DOMAIN.
+
+    Note that this is not what upstream's ``pad_or_trim`` does to a short final segment: faster-whisper zero-fills the
+    missing *feature frames* (0.0), whereas zero PCM gives log10(1e-10) clamped to ``(max - 8 + 4) / 4`` in every padded
+    frame.  To reproduce upstream on a ragged tail keep its true length: ``chunk_windows(..., return_lengths=True)``
+    and pass ``lengths`` to ``ChunkScheduler.run`` -- the kernel then writes 0.0 after the last real frame."""
     x = np.asarray(pcm, dtype=np.float32).reshape(-1)
     n_win = max(1, -(-x.shape[0] // n_samples))
     if x.shape[0] == n_win * n_samples:
@@ -94,56 +99,175 @@ def plan_reference_chunks(n_samples: int, chunk_length_s: float = 180.0, overlap
     return out
 
 
-def chunk_windows(pcm: np.ndarray, start: int, stop: int, n_samples: int = N_SAMPLES) -> np.ndarray:
+def chunk_windows(pcm: np.ndarray, start: int, stop: int, n_samples: int = N_SAMPLES, return_lengths: bool = False):
     """30-s windows ``[k, n_samples]`` of ``pcm[start:stop]``: a strided VIEW of the caller's buffer for the full
-    windows (no copy, so a pinned buffer stays pinned); only a ragged last window is copied into a zero-padded row."""
+    windows (no copy, so a pinned buffer stays pinned); only a ragged last window is copied into a zero-padded row.
+
+    ``return_lengths=True`` also returns the valid samples per window (int64 ``[k]``).  Workers given those lengths
+    run the ragged tail with its true sample count, so its features are ``pad_or_trim(log_mel(tail))`` -- zeros after
+    the last real frame, as upstream (faster-whisper ``pad_or_trim``) -- instead of the log-mel of zero PCM."""
     x = np.asarray(pcm).reshape(-1)[start:stop]
     full, rest = divmod(x.shape[0], n_samples)
     if rest == 0:
-        return x.reshape(full, n_samples) if full else np.zeros((0, n_samples), x.dtype)
+        w = x.reshape(full, n_samples) if full else np.zeros((0, n_samples), x.dtype)
+        return (w, np.full(full, n_samples, np.int64)) if return_lengths else w
     tail = np.zeros((1, n_samples), dtype=x.dtype)
     tail[0, :rest] = x[full * n_samples:]
-    if full == 0:
-        return tail
-    return np.concatenate([x[: full * n_samples].reshape(full, n_samples), tail])      # (copy: ragged input only)
+    w = tail if full == 0 else np.concatenate([x[: full * n_samples].reshape(full, n_samples), tail])   # (copy: ragged input only)
+    if return_lengths:
+        return w, np.array([n_samples] * full + [rest], np.int64)
+    return w
 
 
-# A worker consumes windows [start, stop) of `windows` and writes rows [start, stop) of `out`.
-Worker = Callable[[np.ndarray, int, int, object], None]
+def _length_runs(lengths, s: int, e: int, n_s: int):
+    """Maximal runs ``(a, b, n)`` of windows [s, e) sharing one valid length ``n`` (``lengths=None``: one full run)."""
+    if lengths is None:
+        return [(s, e, n_s)]
+    runs, a = [], s
+    for i in range(s + 1, e + 1):
+        if i == e or int(lengths[i]) != int(lengths[a]):
+            n = int(lengths[a])
+            if n <= 0 or n > n_s:
+                raise ValueError(f"window {a}: length {n} outside 1..{n_s}")
+            runs.append((a, i, n))
+            a = i
+    return runs
 
 
-@dataclass
+# A worker consumes windows [start, stop) of `windows` and writes rows [start, stop) of `out`.  A worker that
+# understands ragged windows also accepts ``lengths=`` (valid samples per window, see ``chunk_windows``).
+Worker = Callable[..., None]
+
+_STOP = object()          # poison pill (ref: final_optimized_transcriber.py:268 ``if work_item is None: break``)
+
+
 class ChunkScheduler:
-    """Runs one worker thread per device over a static block partition and gathers in window order."""
-    workers: Sequence[Worker]
-    results: list = field(default_factory=list)
+    """One persistent worker thread per device; work items are handed out over queues and gathered in window order.
 
-    def run(self, windows, out) -> list[ChunkResult]:
-        n = int(windows.shape[0])
-        parts = partition_windows(n, len(self.workers))
-        works = [ChunkWork(i, a, b, i) for i, (a, b) in enumerate(parts)]
-        results: list[Optional[ChunkResult]] = [None] * len(works)
+    ``policy="static"`` (default, what the mel+encoder path wants: every window costs the same): one contiguous block
+    of ``ceil(n / G)`` windows per worker.  ``policy="dynamic"``: the job is cut into items of ``chunk`` windows on ONE
+    shared ``queue.Queue`` that the workers drain as they become free -- the reference's self-scheduling
+    (ref: final_optimized_transcriber.py:243-246 queues, :256-299 worker loop), which is what shards that finish at
+    ragged times need (``gpu_transcribe_worker``: windows stop decoding when they emit EOT).
 
-        def body(w: ChunkWork):
+    The collector waits ``result_timeout`` seconds per result (ref: :470, 120 s) and gives up only when no worker
+    thread is alive any more (ref: :483-490); a failing item becomes ``ChunkResult(success=False, error=...)`` and the
+    worker moves on to its next item (ref: :280-293, :355-365).  Threads are started on the first ``run`` and stay
+    alive across calls until ``close()`` (the reference spawns and joins them per file, ref: :367-388, :395-408)."""
+
+    def __init__(self, workers: Sequence[Worker], *, policy: str = "static", chunk: Optional[int] = None,
+                 result_timeout: float = 120.0):
+        if policy not in ("static", "dynamic"):
+            raise ValueError("policy must be 'static' or 'dynamic'")
+        if not workers:
+            raise ValueError("ChunkScheduler needs at least one worker")
+        if chunk is not None and chunk <= 0:
+            raise ValueError("chunk must be positive")
+        self.workers = list(workers)
+        self.policy = policy
+        self.chunk = chunk
+        self.result_timeout = float(result_timeout)
+        self.results: list[ChunkResult] = []
+        self._threads: list[threading.Thread] = []
+        self._inboxes: list[queue.Queue] = []
+        self._lock = threading.Lock()
+        self._closed = False
+
+    # ------------------------------------------------------------------ worker threads
+    def _loop(self, worker_id: int, inbox: "queue.Queue") -> None:
+        worker = self.workers[worker_id]
+        while True:
+            job = inbox.get()
+            if job is _STOP:
+                return
+            work, windows, out, lengths, results = job
+            res = ChunkResult(work.chunk_id, work.start, work.stop, worker_id)
             t0 = time.perf_counter()
-            res = ChunkResult(w.chunk_id, w.start, w.stop, w.worker_id)
             try:
-                if w.stop > w.start:
-                    self.workers[w.worker_id](windows, w.start, w.stop, out)
+                if work.stop > work.start:
+                    if lengths is None:
+                        worker(windows, work.start, work.stop, out)
+                    else:
+                        worker(windows, work.start, work.stop, out, lengths=lengths)
             except Exception as exc:                      # one bad shard must not sink the call (ref: :355-365)
                 res.success = False
                 res.error = f"{type(exc).__name__}: {exc}"
             res.processing_time = time.perf_counter() - t0
-            results[w.chunk_id] = res
+            results.put(res)
 
-        threads = [threading.Thread(target=body, args=(w,), daemon=True, name=f"aries-shard-{w.chunk_id}")
-                   for w in works]
-        for t in threads:
+    def _ensure_threads(self) -> None:
+        if self._closed:
+            raise RuntimeError("ChunkScheduler is closed")
+        if self._threads:
+            return
+        shared = queue.Queue() if self.policy == "dynamic" else None
+        for i in range(len(self.workers)):
+            inbox = shared if shared is not None else queue.Queue()
+            t = threading.Thread(target=self._loop, args=(i, inbox), daemon=True, name=f"aries-worker-{i}")
+            self._inboxes.append(inbox)
+            self._threads.append(t)
             t.start()
-        for t in threads:
-            t.join()
-        self.results = [r for r in results if r is not None]
-        return self.results
+
+    def close(self) -> None:
+        """Stop the worker threads (poison pill per thread, as the reference's ``stop_workers``, ref: :395-408)."""
+        with self._lock:
+            if self._closed:
+                return
+            self._closed = True
+            for inbox in self._inboxes:
+                inbox.put(_STOP)
+            for t in self._threads:
+                t.join(timeout=5.0)
+            self._threads, self._inboxes = [], []
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ one job
+    def plan(self, n_windows: int) -> list[ChunkWork]:
+        """The work items of a job of ``n_windows`` windows under this scheduler's policy."""
+        if self.policy == "static":
+            return [ChunkWork(i, a, b, i) for i, (a, b) in enumerate(partition_windows(n_windows, len(self.workers)))]
+        step = self.chunk or max(1, -(-n_windows // (4 * len(self.workers))))
+        return [ChunkWork(i, a, min(a + step, n_windows), -1) for i, a in enumerate(range(0, n_windows, step))]
+
+    def run(self, windows, out, lengths=None) -> list[ChunkResult]:
+        """Process every window of ``windows`` into the rows of ``out`` (one preallocated, ideally pinned, gather
+        buffer: order is restored by construction).  ``lengths`` = valid samples per window (``chunk_windows(...,
+        return_lengths=True)``); ``None`` means every window is full."""
+        n = int(windows.shape[0])
+        if lengths is not None and len(lengths) != n:
+            raise ValueError("lengths must hold one entry per window")
+        with self._lock:
+            self._ensure_threads()
+            works = self.plan(n)
+            results: "queue.Queue" = queue.Queue()        # per job: a late result of an abandoned job cannot leak in
+            for w in works:
+                inbox = self._inboxes[w.worker_id if self.policy == "static" else 0]
+                inbox.put((w, windows, out, lengths, results))
+            got: dict[int, ChunkResult] = {}
+            while len(got) < len(works):
+                try:
+                    r = results.get(timeout=self.result_timeout)
+                    got[r.chunk_id] = r
+                except queue.Empty:
+                    if not any(t.is_alive() for t in self._threads):
+                        break                              # ref: :483-490 "All workers stopped, breaking..."
+            for w in works:
+                if w.chunk_id not in got:
+                    got[w.chunk_id] = ChunkResult(w.chunk_id, w.start, w.stop, w.worker_id, success=False,
+                                                  error="no result: every worker thread has stopped")
+            self.results = [got[w.chunk_id] for w in works]
+            return self.results
 
 
 def gpu_worker(model, micro_batch: int = 16) -> Worker:
@@ -157,7 +281,7 @@ def gpu_worker(model, micro_batch: int = 16) -> Worker:
     d, t = model.shape.d_model, model.shape.n_ctx
     state = {}
 
-    def run(windows, start: int, stop: int, out) -> None:
+    def run(windows, start: int, stop: int, out, lengths=None) -> None:
         torch.cuda.set_device(dev)
         n_s = int(windows.shape[1])
         wt = windows if isinstance(windows, torch.Tensor) else torch.from_numpy(windows)
@@ -189,7 +313,8 @@ def gpu_worker(model, micro_batch: int = 16) -> Worker:
                 comp.wait_event(state["h2d_done"][i])
                 if k >= 2:
                     comp.wait_event(state["d2h_done"][i])       # out buffer i drained by step k-2's D2H
-                model.encode_audio(state["bufs"][i][: e - s], out=state["outs"][i][: e - s])
+                for a, b, n in _length_runs(lengths, s, e, n_s):      # a ragged tail runs with its true length
+                    model.encode_audio(state["bufs"][i][a - s: b - s, :n], out=state["outs"][i][a - s: b - s])
                 state["comp_done"][i].record(comp)
             with torch.cuda.stream(copy):
                 copy.wait_event(state["comp_done"][i])
@@ -217,11 +342,9 @@ def gpu_transcribe_worker(model, prompt: Sequence[int], max_length: int = 448, m
         raise ValueError("gpu_transcribe_worker needs a WhisperModel built with decoder weights (decoder_shape=...)")
     dev = model.encoder.device
     prompt = [int(t) for t in prompt]
-    P = len(prompt)
-    eot = model.decoder.tokens.eot
     state = {}
 
-    def run(windows, start: int, stop: int, out) -> None:
+    def run(windows, start: int, stop: int, out, lengths=None) -> None:
         torch.cuda.set_device(dev)
         n_s = int(windows.shape[1])
         wt = windows if isinstance(windows, torch.Tensor) else torch.from_numpy(windows)
@@ -229,23 +352,46 @@ def gpu_transcribe_worker(model, prompt: Sequence[int], max_length: int = 448, m
             raise ValueError("windows must be float32 or int16 PCM")
         if state.get("n_s") != n_s or state.get("dtype") != wt.dtype:
             state["n_s"], state["dtype"] = n_s, wt.dtype
-            state["buf"] = torch.empty((micro_batch, n_s), dtype=wt.dtype, device=dev)     # int16 is scaled on the GPU
+            # int16 is scaled on the GPU; two staging buffers: the next micro-batch's H2D overlaps this one's decode
+            state["bufs"] = [torch.empty((micro_batch, n_s), dtype=wt.dtype, device=dev) for _ in range(2)]
+            state["enc"] = torch.empty((micro_batch, model.shape.n_ctx, model.shape.d_model), dtype=torch.bfloat16, device=dev)
+            state["copy"] = torch.cuda.Stream(dev)
+            state["comp"] = torch.cuda.Stream(dev)
+            state["h2d_done"] = [torch.cuda.Event() for _ in range(2)]
+            state["comp_done"] = [torch.cuda.Event() for _ in range(2)]
         ot = out if isinstance(out, torch.Tensor) else torch.from_numpy(out)
         L = min(int(max_length), model.decoder.shape.n_text_ctx)
         if ot.shape[1] != L + 1 or ot.dtype != torch.int32:
             raise ValueError(f"out must be int32 [n_windows, {L + 1}]")
-        for s in range(start, stop, micro_batch):
+        on = ot.numpy()                                        # host rows are filled with one vectorised store each
+        copy, comp = state["copy"], state["comp"]
+        steps = list(range(start, stop, micro_batch))
+
+        def upload(k):
+            s = steps[k]
             e = min(s + micro_batch, stop)
-            buf = state["buf"][: e - s]
-            buf.copy_(wt[s:e], non_blocking=True)
-            enc = model.encode_audio(buf)
-            res = model.decoder.generate(enc, [prompt] * (e - s), max_length=L, **generate_kw)
-            for i, r in enumerate(res):
-                ids = r.sequences_ids[0]
-                row = ot[s + i]
-                row[0] = len(ids)
-                row[1:1 + P] = torch.tensor(prompt, dtype=torch.int32)
-                row[1 + P:1 + P + len(ids)] = torch.tensor(ids, dtype=torch.int32) if ids else torch.empty(0, dtype=torch.int32)
-                row[1 + P + len(ids):] = eot
+            i = k & 1
+            with torch.cuda.stream(copy):
+                if k >= 2:
+                    copy.wait_event(state["comp_done"][i])
+                state["bufs"][i][: e - s].copy_(wt[s:e], non_blocking=True)
+                state["h2d_done"][i].record(copy)
+
+        if steps:
+            upload(0)
+        for k, s in enumerate(steps):
+            e = min(s + micro_batch, stop)
+            i = k & 1
+            if k + 1 < len(steps):
+                upload(k + 1)
+            with torch.cuda.stream(comp):
+                comp.wait_event(state["h2d_done"][i])
+                enc = state["enc"][: e - s]
+                for a, b, n in _length_runs(lengths, s, e, n_s):
+                    model.encode_audio(state["bufs"][i][a - s: b - s, :n], out=enc[a - s: b - s])
+                state["comp_done"][i].record(comp)
+                toks, lens = model.decoder.generate_ids(enc, prompt, max_length=L, **generate_kw)   # syncs on `comp`
+            on[s:e, 0] = lens
+            on[s:e, 1:] = toks
 
     return run
