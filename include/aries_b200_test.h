@@ -20,6 +20,17 @@ ARIES_API int aries_test_gemm(aries_ctx* ctx, int epi, int M, int N, int K, cons
                     const void* resid, const float* pos, int pos_rows, void* out, void* out2, int n_split,
                     int t_rows, int t_pad, void* stream);
 
+/* The LayerNorm-folded GEMM epilogues and the statistics hand-over (csrc/gemm.h):
+ *   epi 2 (bias + residual -> f16) with stats_out != NULL also writes (sum, sum of squares) per row and per slice of
+ *     aries_test_gemm_stats_parts(N) column slices: stats_out f32 [M, parts, 2];
+ *   epi 5: out bf16 = gelu(rstd (a b^T - mean c1) + bias), epi 6: the same without GELU, split / transposed like epi 4;
+ *     a = f16 [M, K] (the residual stream), b = f16 [N, K] (gamma-scaled weights), mean / rstd from stats_in
+ *     f32 [M, stats_parts, 2] over ln_dim columns, eps 1e-5. */
+ARIES_API int aries_test_gemm_ln(aries_ctx* ctx, int epi, int M, int N, int K, const void* a, const void* b, const float* bias,
+                       const float* c1, const void* stats_in, int stats_parts, int ln_dim, const void* resid, void* out,
+                       void* out2, int n_split, int t_rows, int t_pad, void* stats_out, void* stream);
+ARIES_API int aries_test_gemm_stats_parts(int N);
+
 /* y bf16 [rows, d] = LayerNorm(x f32 [rows, d]) * gamma + beta, eps 1e-5. */
 ARIES_API int aries_test_layernorm(aries_ctx* ctx, const void* x /* f16 */, const float* gamma, const float* beta, void* y,
                          int64_t rows, int d, void* stream);

@@ -141,3 +141,86 @@ def test_scheduler_accepts_int16_windows():
     assert all(r.success for r in sched.run(torch.from_numpy(pcm16).pin_memory(), out16))
     assert all(r.success for r in sched.run(torch.from_numpy(pcm16.astype(np.float32) / 32768.0).pin_memory(), out32))
     assert torch.equal(out16, out32)
+
+
+@pytest.mark.parametrize("shape", [(300, 128, 128), (700, 384, 384), (1500, 1280, 1280), (2900, 1024, 4096)])
+def test_residual_epilogue_leaves_layernorm_partials(ctx, shape):
+    """Producing side of the LayerNorm fold: the residual epilogue (epi 2) also writes, per output row and per column
+    slice, the sum and the sum of squares of what it stores; summed over the slices they must give the row's mean and
+    variance of the f16 stream (f32 arithmetic: rel 1e-4 on the sums of squares)."""
+    from whisper_aries_b200 import _lib
+    M, N, K = shape
+    g = torch.Generator().manual_seed(M + N)
+    a = (torch.randn(M, K, generator=g) * 0.5).cuda().bfloat16()
+    b = (torch.randn(N, K, generator=g) * 0.05).cuda().bfloat16()
+    bias = torch.randn(N, generator=g).cuda()
+    resid = (torch.randn(M, N, generator=g) * 3 + 0.7).cuda().half()
+    parts = ctx.lib.aries_test_gemm_stats_parts(N)
+    assert parts == N // (128 if N % 256 == 0 else 64)
+    out = torch.empty((M, N), device="cuda", dtype=torch.float16)
+    stats = torch.full((M, parts, 2), float("nan"), device="cuda")
+    _lib.check(ctx.lib.aries_test_gemm_ln(ctx.handle, 2, M, N, K, ptr(a), ptr(b), ptr(bias), None, None, 0, 0, ptr(resid),
+                                          ptr(out), None, 0, 0, 0, ptr(stats), None))
+    torch.cuda.synchronize()
+    x = out.float()
+    assert torch.isfinite(stats).all()
+    s1, s2 = stats[:, :, 0].sum(1), stats[:, :, 1].sum(1)
+    assert (s1 - x.sum(1)).abs().max().item() <= 1e-3 * N ** 0.5 * 4          # f16 rounding of the stored values
+    assert ((s2 - (x * x).sum(1)).abs() / (x * x).sum(1)).max().item() <= 1e-3
+    w = N // parts                                                             # every slice on its own, too
+    assert (stats[:, :, 0] - x.view(M, parts, w).sum(2)).abs().max().item() <= 0.05
+
+
+@pytest.mark.parametrize("shape", [(300, 128, 128), (700, 1536, 384), (1500, 5120, 1280), (2900, 4096, 1024)])
+def test_layernorm_folded_gelu_gemm(ctx, shape):
+    """Consuming side (epi 5): f16 stream x f16 gamma-scaled weights, rstd (acc - mean c1) + c2, GELU -- against
+    gelu(LayerNorm(x) W^T + b) in f32 torch.  The stream has a non-zero mean and per-row scale, as a residual stream does."""
+    from whisper_aries_b200 import _lib
+    M, N, K = shape
+    g = torch.Generator().manual_seed(M + N + 1)
+    x = ((torch.randn(M, K, generator=g) * (0.5 + 2 * torch.rand(M, 1, generator=g)) + 0.8)).cuda().half()
+    W = (torch.randn(N, K, generator=g) * 0.04).cuda()
+    bias = (torch.randn(N, generator=g) * 0.1).cuda()
+    gamma = (1 + 0.1 * torch.randn(K, generator=g)).cuda()
+    beta = (0.1 * torch.randn(K, generator=g)).cuda()
+    Wf = (W * gamma).half()
+    c1 = Wf.float().sum(1)
+    c2 = (W.double() @ beta.double()).float() + bias
+    parts = ctx.lib.aries_test_gemm_stats_parts(K)
+    xs = x.float().view(M, parts, K // parts)
+    stats = torch.stack([xs.sum(2), (xs * xs).sum(2)], dim=2).contiguous()
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    _lib.check(ctx.lib.aries_test_gemm_ln(ctx.handle, 5, M, N, K, ptr(x), ptr(Wf), ptr(c2), ptr(c1), ptr(stats), parts, K,
+                                          None, ptr(out), None, 0, 0, 0, None, None))
+    torch.cuda.synchronize()
+    y = torch.nn.functional.layer_norm(x.float(), (K,), gamma, beta, 1e-5)
+    ref = torch.nn.functional.gelu(y @ W.t() + bias)
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 4e-3 + ref.abs().max().item() * 2 ** -7, err                 # bf16 output + f16 weight rounding
+
+
+def test_layernorm_folded_qkv_split(ctx):
+    from whisper_aries_b200 import _lib
+    B, T, d, t_pad = 2, 300, 256, 304
+    M, N, K = B * T, 3 * d, d
+    g = torch.Generator().manual_seed(9)
+    x = (torch.randn(M, K, generator=g) * 1.5 - 0.4).cuda().half()
+    W = (torch.randn(N, K, generator=g) * 0.05).cuda()
+    bias = (torch.randn(N, generator=g) * 0.1).cuda()
+    gamma = (1 + 0.1 * torch.randn(K, generator=g)).cuda()
+    beta = (0.1 * torch.randn(K, generator=g)).cuda()
+    Wf = (W * gamma).half()
+    c1, c2 = Wf.float().sum(1), (W.double() @ beta.double()).float() + bias
+    parts = ctx.lib.aries_test_gemm_stats_parts(K)
+    xs = x.float().view(M, parts, K // parts)
+    stats = torch.stack([xs.sum(2), (xs * xs).sum(2)], dim=2).contiguous()
+    qk = torch.full((M, 2 * d), float("nan"), device="cuda", dtype=torch.bfloat16)
+    vt = torch.zeros((B, d // 64, 64, t_pad), device="cuda", dtype=torch.bfloat16)
+    _lib.check(ctx.lib.aries_test_gemm_ln(ctx.handle, 6, M, N, K, ptr(x), ptr(Wf), ptr(c2), ptr(c1), ptr(stats), parts, K,
+                                          None, ptr(qk), ptr(vt), 2 * d, T, t_pad, None, None))
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.layer_norm(x.float(), (K,), gamma, beta, 1e-5) @ W.t() + bias
+    tol = 4e-3 + ref.abs().max().item() * 2 ** -7
+    assert (qk.float() - ref[:, :2 * d]).abs().max().item() <= tol
+    v = ref[:, 2 * d:].view(B, T, d // 64, 64).permute(0, 2, 3, 1)
+    assert (vt[..., :T].float() - v).abs().max().item() <= tol

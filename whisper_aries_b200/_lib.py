@@ -87,6 +87,9 @@ PROTOTYPES = {
                                             c_void_p]),
     "aries_test_gemm": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "aries_test_gemm_ln": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "aries_test_gemm_stats_parts": (c_int, [c_int]),
     "aries_test_layernorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "aries_test_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "aries_test_attention_trace": (c_int, [c_void_p, c_void_p, c_size_t]),

@@ -588,6 +588,37 @@ int aries_test_gemm(aries_ctx* ctx, int epi, int M, int N, int K, const void* a,
     return ARIES_OK;
 }
 
+int aries_test_gemm_ln(aries_ctx* ctx, int epi, int M, int N, int K, const void* a, const void* b, const float* bias,
+                       const float* c1, const void* stats_in, int stats_parts, int ln_dim, const void* resid, void* out,
+                       void* out2, int n_split, int t_rows, int t_pad, void* stats_out, void* stream) {
+    int rc = use(ctx);
+    if (rc) return rc;
+    if ((rc = ensure_kernels(ctx))) return rc;
+    if (M <= 0 || N % 128 || K % 64 || epi < 0 || epi >= aries::EPI_COUNT) return fail(ARIES_EINVAL, "aries_test_gemm_ln: bad shape");
+    CUtensorMap ta, tb;
+    const unsigned long long da[2] = {(unsigned long long)K, (unsigned long long)M}, sa[2] = {2, (unsigned long long)K * 2};
+    const unsigned long long db[2] = {(unsigned long long)K, (unsigned long long)N};
+    const unsigned ba[2] = {64, 128}, bb[2] = {64, (unsigned)aries::gemm_b_box_rows()};
+    cudaError_t e;
+    if ((e = aries::make_tmap_bf16(&ta, a, 2, da, sa, ba)) != cudaSuccess) return fail_cuda("tensor map A", e);
+    if ((e = aries::make_tmap_bf16(&tb, b, 2, db, sa, bb)) != cudaSuccess) return fail_cuda("tensor map B", e);
+    aries::GemmParams p{};
+    p.M = M; p.N = N; p.K = K; p.a_cols = K;
+    p.p_in = M; p.t_valid = M; p.p_out = M; p.row_off = 0; p.ldo = N;
+    p.bias = bias; p.resid = resid; p.out = out;
+    p.c1 = c1; p.stats_in = static_cast<const float2*>(stats_in); p.stats_parts = stats_parts; p.ln_dim = ln_dim;
+    p.ln_eps = 1e-5f; p.stats_out = static_cast<float2*>(stats_out);
+    if (epi == aries::EPI_LN_QKV_SPLIT_BF16) {
+        p.p_in = t_rows; p.t_valid = t_rows; p.p_out = t_rows; p.ldo = n_split;
+        p.out2 = out2; p.n_split = n_split; p.t_pad = t_pad;
+    }
+    if ((e = aries::gemm_launch(epi, ta, tb, p, ctx->sm_count, static_cast<cudaStream_t>(stream))) != cudaSuccess)
+        return fail_cuda("gemm_launch", e);
+    return ARIES_OK;
+}
+
+int aries_test_gemm_stats_parts(int N) { return aries::gemm_stats_parts(N); }
+
 int aries_test_layernorm(aries_ctx* ctx, const void* x, const float* gamma, const float* beta, void* y, int64_t rows,
                          int d, void* stream) {
     int rc = use(ctx);

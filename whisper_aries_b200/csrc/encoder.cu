@@ -6,13 +6,18 @@
 //   mel f32 [B, n_mels, frames] --(transpose, bf16)--> [B, 3002, c_pad]               (zero row before / after)
 //   conv1 k3 s1 p1 + GELU   = implicit GEMM, K = 3 c_pad, A rows overlap in memory   -> c1 bf16 [B, 3002, d]
 //   conv2 k3 s2 p1 + GELU + positions = implicit GEMM, K = 3 d over row PAIRS         -> x  f32  [B*1500, d]
-//   n_layers x { LN -> QKV GEMM (+bias; V stored transposed) -> fused attention -> O GEMM (+bias +residual)
-//                LN -> fc1 GEMM (+bias +GELU)                -> fc2 GEMM (+bias +residual) }
+//   n_layers x { QKV GEMM with LayerNorm folded in (V stored transposed) -> fused attention -> O GEMM (+bias +residual)
+//                fc1 GEMM with LayerNorm folded in (+GELU)               -> fc2 GEMM (+bias +residual) }
 //   final LN -> bf16 [B, 1500, d]
+// LayerNorm never runs as a pass of its own inside the layers (north_star (2)): the epilogue that writes the residual
+// stream (conv2, O, fc2) also leaves per-row (sum, sum of squares) partials, the consuming GEMM multiplies the f16
+// stream itself by gamma-scaled f16 weights and applies  rstd (acc - mean c1) + c2  in its epilogue (gemm.h).  Only
+// ln_post, whose output IS the result, is a LayerNorm kernel.
 // bf16 operands, f32 accumulation in TMEM, f16 residual stream (what CTranslate2's float16 mode keeps; 8x finer
 // than bf16, and half the HBM traffic of f32 for the two residual epilogues and LayerNorm), f32 LayerNorm statistics
 // and softmax.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <cstdio>
 #include <cstring>
@@ -46,7 +51,8 @@ inline unsigned short f32_to_bf16(float f) {
 }
 
 struct LayerW {
-    const float *ln1_g, *ln1_b, *bqkv, *bo, *ln2_g, *ln2_b, *b1, *b2;
+    // c1_* = row sums of the gamma-scaled f16 weights, c2_* = beta folded through the weights + bias (gemm.h, EPI_LN_*)
+    const float *c1_qkv, *c2_qkv, *bo, *c1_fc1, *c2_fc1, *b2;
     CUtensorMap m_qkv, m_o, m_fc1, m_fc2;
 };
 
@@ -65,7 +71,7 @@ struct EncoderPlan {
     // activation tensor maps, cached per (workspace, batch)
     const void* cached_ws = nullptr;
     int cached_batch = 0;
-    CUtensorMap a_mel{}, a_c1{}, a_y{}, a_ctx{}, a_h{};
+    CUtensorMap a_mel{}, a_c1{}, a_x{}, a_ctx{}, a_h{};
     AttnMaps a_attn{};
     int last_launches = 0;
     Profiler prof;
@@ -75,7 +81,7 @@ struct EncoderPlan {
 namespace {
 
 struct WsLayout {
-    size_t melT, x, y, ctx, qk, vt, h, mel, total;
+    size_t melT, x, stats, ctx, qk, vt, h, mel, total;
 };
 
 WsLayout ws_layout(const EncoderPlan& pl, int batch) {
@@ -90,7 +96,7 @@ WsLayout ws_layout(const EncoderPlan& pl, int batch) {
     };
     w.melT = take(B * kRowsPadded * pl.c_pad * 2);
     w.x = take(B * T * d * 2);
-    w.y = take(B * T * d * 2);
+    w.stats = take(B * T * (size_t)gemm_stats_parts((int)d) * sizeof(float2));
     w.ctx = take(B * T * d * 2);
     w.qk = take(B * T * 2 * d * 2);
     w.vt = take(B * d * pl.t_pad * 2);
@@ -193,8 +199,31 @@ cudaError_t encoder_plan_create(int device, int sm_count, const EncoderShapeC& c
         return at;
     };
 
+    // LayerNorm fold (gemm.h): W' = gamma (.) W rounded to f16, c1[n] = sum_k W'[n,k] (of the ROUNDED values, so that the
+    // mean cancels exactly), c2[n] = sum_k beta[k] W[n,k] + bias[n]; sums in f64.
+    auto put_ln_folded = [&](const float* w, const float* bias, const float* gamma, const float* beta, int n_out, int n_in,
+                             size_t* o_w, size_t* o_c1, size_t* o_c2) {
+        *o_w = reserve((size_t)n_out * n_in * 2);
+        *o_c1 = reserve((size_t)n_out * 4);
+        *o_c2 = reserve((size_t)n_out * 4);
+        __half* dst = reinterpret_cast<__half*>(blob.data() + *o_w);
+        float* c1 = reinterpret_cast<float*>(blob.data() + *o_c1);
+        float* c2 = reinterpret_cast<float*>(blob.data() + *o_c2);
+        for (int n = 0; n < n_out; ++n) {
+            double s1 = 0.0, s2 = 0.0;
+            const float* row = w + (size_t)n * n_in;
+            for (int k = 0; k < n_in; ++k) {
+                const __half h = __float2half_rn(row[k] * gamma[k]);
+                dst[(size_t)n * n_in + k] = h;
+                s1 += (double)__half2float(h);
+                s2 += (double)beta[k] * (double)row[k];
+            }
+            c1[n] = (float)s1;
+            c2[n] = (float)(s2 + (double)bias[n]);
+        }
+    };
     struct Offs {
-        size_t ln1_g, ln1_b, wqkv, bqkv, wo, bo, ln2_g, ln2_b, w1, b1, w2, b2;
+        size_t wqkv, c1_qkv, c2_qkv, wo, bo, w1, c1_fc1, c2_fc1, w2, b2;
     };
     std::vector<Offs> offs(L);
     size_t o_conv1w = 0, o_conv1b = 0, o_conv2w = 0, o_conv2b = 0, o_pos = 0, o_lnf_g = 0, o_lnf_b = 0;
@@ -220,26 +249,18 @@ cudaError_t encoder_plan_create(int device, int sm_count, const EncoderShapeC& c
         const std::string p = "encoder/layer_" + std::to_string(i);
         const float* w;
         Offs& o = offs[i];
-        ok &= (w = need(p + "/self_attention/layer_norm/gamma", {d})) != nullptr;
-        if (w) o.ln1_g = put_f32(w, d);
-        ok &= (w = need(p + "/self_attention/layer_norm/beta", {d})) != nullptr;
-        if (w) o.ln1_b = put_f32(w, d);
-        ok &= (w = need(p + "/self_attention/linear_0/weight", {3 * d, d})) != nullptr;
-        if (w) o.wqkv = put_bf16(w, (size_t)3 * d * d);
-        ok &= (w = need(p + "/self_attention/linear_0/bias", {3 * d})) != nullptr;
-        if (w) o.bqkv = put_f32(w, (size_t)3 * d);
+        const float *g1 = need(p + "/self_attention/layer_norm/gamma", {d}), *be1 = need(p + "/self_attention/layer_norm/beta", {d});
+        const float *wq = need(p + "/self_attention/linear_0/weight", {3 * d, d}), *bq = need(p + "/self_attention/linear_0/bias", {3 * d});
+        ok &= g1 && be1 && wq && bq;
+        if (g1 && be1 && wq && bq) put_ln_folded(wq, bq, g1, be1, 3 * d, d, &o.wqkv, &o.c1_qkv, &o.c2_qkv);
         ok &= (w = need(p + "/self_attention/linear_1/weight", {d, d})) != nullptr;
         if (w) o.wo = put_bf16(w, (size_t)d * d);
         ok &= (w = need(p + "/self_attention/linear_1/bias", {d})) != nullptr;
         if (w) o.bo = put_f32(w, d);
-        ok &= (w = need(p + "/ffn/layer_norm/gamma", {d})) != nullptr;
-        if (w) o.ln2_g = put_f32(w, d);
-        ok &= (w = need(p + "/ffn/layer_norm/beta", {d})) != nullptr;
-        if (w) o.ln2_b = put_f32(w, d);
-        ok &= (w = need(p + "/ffn/linear_0/weight", {f, d})) != nullptr;
-        if (w) o.w1 = put_bf16(w, (size_t)f * d);
-        ok &= (w = need(p + "/ffn/linear_0/bias", {f})) != nullptr;
-        if (w) o.b1 = put_f32(w, f);
+        const float *g2 = need(p + "/ffn/layer_norm/gamma", {d}), *be2 = need(p + "/ffn/layer_norm/beta", {d});
+        const float *w1 = need(p + "/ffn/linear_0/weight", {f, d}), *b1 = need(p + "/ffn/linear_0/bias", {f});
+        ok &= g2 && be2 && w1 && b1;
+        if (g2 && be2 && w1 && b1) put_ln_folded(w1, b1, g2, be2, f, d, &o.w1, &o.c1_fc1, &o.c2_fc1);
         ok &= (w = need(p + "/ffn/linear_1/weight", {d, f})) != nullptr;
         if (w) o.w2 = put_bf16(w, (size_t)d * f);
         ok &= (w = need(p + "/ffn/linear_1/bias", {d})) != nullptr;
@@ -273,8 +294,8 @@ cudaError_t encoder_plan_create(int device, int sm_count, const EncoderShapeC& c
     for (int i = 0; i < L; ++i) {
         LayerW& lw = pl->layers[i];
         const Offs& o = offs[i];
-        lw.ln1_g = F(o.ln1_g); lw.ln1_b = F(o.ln1_b); lw.bqkv = F(o.bqkv); lw.bo = F(o.bo);
-        lw.ln2_g = F(o.ln2_g); lw.ln2_b = F(o.ln2_b); lw.b1 = F(o.b1); lw.b2 = F(o.b2);
+        lw.c1_qkv = F(o.c1_qkv); lw.c2_qkv = F(o.c2_qkv); lw.bo = F(o.bo);
+        lw.c1_fc1 = F(o.c1_fc1); lw.c2_fc1 = F(o.c2_fc1); lw.b2 = F(o.b2);
         if ((e = map2d(&lw.m_qkv, base + o.wqkv, d, 3ull * d, gemm_b_box_rows())) != cudaSuccess) return fail(e);
         if ((e = map2d(&lw.m_o, base + o.wo, d, d, gemm_b_box_rows())) != cudaSuccess) return fail(e);
         if ((e = map2d(&lw.m_fc1, base + o.w1, d, f, gemm_b_box_rows())) != cudaSuccess) return fail(e);
@@ -309,7 +330,8 @@ cudaError_t encoder_run(EncoderPlan* pl, const float* mel, int batch, int frames
     char* ws = static_cast<char*>(workspace);
     void* melT = ws + w.melT;
     void* x = ws + w.x;                                  // residual stream, f16
-    void* y = ws + w.y;
+    float2* stats = reinterpret_cast<float2*>(ws + w.stats);   // LayerNorm partials of the residual stream's rows
+    const int parts = gemm_stats_parts(d);
     void* ctx = ws + w.ctx;
     void* qk = ws + w.qk;
     void* vt = ws + w.vt;
@@ -320,7 +342,7 @@ cudaError_t encoder_run(EncoderPlan* pl, const float* mel, int batch, int frames
     if (pl->cached_ws != workspace || pl->cached_batch != batch) {
         ARIES_TRY(map2d(&pl->a_mel, melT, cp, (unsigned long long)batch * kRowsPadded, 128), "tensor map (mel)");
         ARIES_TRY(map2d(&pl->a_c1, c1, 2ull * d, (unsigned long long)batch * (kRowsPadded / 2), 128), "tensor map (conv1 out)");
-        ARIES_TRY(map2d(&pl->a_y, y, d, M, 128), "tensor map (y)");
+        ARIES_TRY(map2d(&pl->a_x, x, d, M, 128), "tensor map (x)");
         ARIES_TRY(map2d(&pl->a_ctx, ctx, d, M, 128), "tensor map (ctx)");
         ARIES_TRY(map2d(&pl->a_h, h, f, M, 128), "tensor map (h)");
         ARIES_TRY(attention_make_maps(qk, vt, batch, T, d, c.n_heads, pl->t_pad, &pl->a_attn), "tensor map (attention)");
@@ -356,7 +378,7 @@ cudaError_t encoder_run(EncoderPlan* pl, const float* mel, int batch, int frames
     g = GemmParams{};
     g.M = batch * (kRowsPadded / 2); g.N = d; g.K = 3 * d; g.a_cols = 2 * d;
     g.p_in = kRowsPadded / 2; g.t_valid = T; g.p_out = T; g.row_off = 0; g.ldo = d;
-    g.bias = pl->conv2_b; g.pos = pl->pos; g.out = x;
+    g.bias = pl->conv2_b; g.pos = pl->pos; g.out = x; g.stats_out = stats;
     pl->prof.begin(KC_CONV2, stream);
     ARIES_TRY(gemm_launch(EPI_BIAS_GELU_POS_F16, pl->a_c1, pl->m_conv2, g, pl->sm_count, stream), "conv2");
     pl->prof.end(stream);
@@ -371,37 +393,33 @@ cudaError_t encoder_run(EncoderPlan* pl, const float* mel, int batch, int frames
     AttnParams ap{batch, T, d, c.n_heads, ctx};
     for (int i = 0; i < c.n_layers; ++i) {
         const LayerW& lw = pl->layers[i];
-        pl->prof.begin(KC_LAYERNORM, stream);
-        ARIES_TRY(layernorm_launch(x, lw.ln1_g, lw.ln1_b, y, M, d, kLnEps, stream), "layer norm 1");
-        pl->prof.end(stream);
         g = plain(3 * d, d);
         g.p_in = T; g.t_valid = T; g.p_out = T; g.ldo = 2 * d;
-        g.bias = lw.bqkv; g.out = qk; g.out2 = vt; g.n_split = 2 * d; g.t_pad = pl->t_pad;
+        g.bias = lw.c2_qkv; g.c1 = lw.c1_qkv; g.stats_in = stats; g.stats_parts = parts; g.ln_dim = d; g.ln_eps = kLnEps;
+        g.out = qk; g.out2 = vt; g.n_split = 2 * d; g.t_pad = pl->t_pad;
         pl->prof.begin(KC_QKV, stream);
-        ARIES_TRY(gemm_launch(EPI_QKV_SPLIT_BF16, pl->a_y, lw.m_qkv, g, pl->sm_count, stream), "qkv projection");
+        ARIES_TRY(gemm_launch(EPI_LN_QKV_SPLIT_BF16, pl->a_x, lw.m_qkv, g, pl->sm_count, stream), "qkv projection");
         pl->prof.end(stream);
         pl->prof.begin(KC_ATTENTION, stream);
         ARIES_TRY(attention_launch(pl->a_attn, ap, stream), "attention");
         pl->prof.end(stream);
         g = plain(d, d);
-        g.bias = lw.bo; g.resid = x; g.out = x;
+        g.bias = lw.bo; g.resid = x; g.out = x; g.stats_out = stats;
         pl->prof.begin(KC_OPROJ, stream);
         ARIES_TRY(gemm_launch(EPI_BIAS_RESID_F16, pl->a_ctx, lw.m_o, g, pl->sm_count, stream), "output projection");
         pl->prof.end(stream);
-        pl->prof.begin(KC_LAYERNORM, stream);
-        ARIES_TRY(layernorm_launch(x, lw.ln2_g, lw.ln2_b, y, M, d, kLnEps, stream), "layer norm 2");
-        pl->prof.end(stream);
         g = plain(f, d);
-        g.bias = lw.b1; g.out = h;
+        g.bias = lw.c2_fc1; g.c1 = lw.c1_fc1; g.stats_in = stats; g.stats_parts = parts; g.ln_dim = d; g.ln_eps = kLnEps;
+        g.out = h;
         pl->prof.begin(KC_FC1, stream);
-        ARIES_TRY(gemm_launch(EPI_BIAS_GELU_BF16, pl->a_y, lw.m_fc1, g, pl->sm_count, stream), "fc1");
+        ARIES_TRY(gemm_launch(EPI_LN_GELU_BF16, pl->a_x, lw.m_fc1, g, pl->sm_count, stream), "fc1");
         pl->prof.end(stream);
         g = plain(d, f);
-        g.bias = lw.b2; g.resid = x; g.out = x;
+        g.bias = lw.b2; g.resid = x; g.out = x; g.stats_out = stats;
         pl->prof.begin(KC_FC2, stream);
         ARIES_TRY(gemm_launch(EPI_BIAS_RESID_F16, pl->a_h, lw.m_fc2, g, pl->sm_count, stream), "fc2");
         pl->prof.end(stream);
-        launches += 7;
+        launches += 5;
     }
     pl->prof.begin(KC_LAYERNORM, stream);
     ARIES_TRY(layernorm_launch(x, pl->lnf_g, pl->lnf_b, out_bf16, M, d, kLnEps, stream), "final layer norm");

@@ -135,7 +135,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             // ~13 instructions and ~80 cycles of issue per MMA -- more than half of the 135 cycles a 128x256x16 MMA
             // occupies the tensor pipe.  The four K = 16 steps of a stage go out as one statement.
             static_assert(BK == 64, "one x4 group per stage");
-            constexpr uint32_t idesc = umma_idesc_bf16(BM * CG, BN, false, false);
+            constexpr bool kLnFold = (EPI == EPI_LN_GELU_BF16 || EPI == EPI_LN_QKV_SPLIT_BF16);
+            constexpr uint32_t idesc = kLnFold ? umma_idesc_f16(BM * CG, BN) : umma_idesc_bf16(BM * CG, BN, false, false);
             constexpr uint64_t desc_hi64 = umma_smem_desc_hi(16, 1024);   // K-major SW128: SBO = 8 rows * 128 B
             constexpr uint32_t desc_hi = (uint32_t)(desc_hi64 >> 32);
             const uint32_t desc_lo0 = (uint32_t)(desc_hi64 & 0xFFFFFFFFu) | ((base >> 4) & 0x3FFF);
@@ -206,6 +207,39 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             const int t_own = r_own - b_own * p.p_in;
             const bool valid_own = (r_own < p.M) && (t_own < p.t_valid);
 
+            // LayerNorm fold, consuming side: mean / rstd of this thread's own row from the producer's partials, then
+            // handed to the coalesced layout (rows 4 i + sub_row) by shuffles -- once per tile
+            constexpr bool kLn = (EPI == EPI_LN_GELU_BF16 || EPI == EPI_LN_QKV_SPLIT_BF16);
+            constexpr bool kQkv = (EPI == EPI_QKV_SPLIT_BF16 || EPI == EPI_LN_QKV_SPLIT_BF16);
+            constexpr bool kGelu = (EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_GELU_POS_F16 || EPI == EPI_LN_GELU_BF16);
+            float mean_own = 0.0f, rstd_own = 1.0f;
+            float nmean_c[8], rstd_c[8];                      // (-rstd mean, rstd) of rows 4 i + sub_row
+            if (kLn) {
+                if (r_own < p.M) {
+                    const float2* st = p.stats_in + (long long)r_own * p.stats_parts;
+                    float s1 = 0.0f, s2 = 0.0f;
+                    for (int k = 0; k < p.stats_parts; ++k) {
+                        const float2 v = __ldg(st + k);
+                        s1 += v.x;
+                        s2 += v.y;
+                    }
+                    const float inv_d = 1.0f / (float)p.ln_dim;
+                    mean_own = s1 * inv_d;
+                    rstd_own = rsqrtf(fmaxf(s2 * inv_d - mean_own * mean_own, 0.0f) + p.ln_eps);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    nmean_c[i] = __shfl_sync(0xffffffffu, -mean_own * rstd_own, 4 * i + sub_row);
+                    rstd_c[i] = __shfl_sync(0xffffffffu, rstd_own, 4 * i + sub_row);
+                }
+            }
+            // LayerNorm fold, producing side: (sum, sum of squares) of what this warp stores, per row of the coalesced layout
+            constexpr bool kMayProduce = (EPI == EPI_BIAS_RESID_F16 || EPI == EPI_BIAS_GELU_POS_F16);
+            const bool produce = kMayProduce && p.stats_out != nullptr;
+            float st_s[8], st_q[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) st_s[i] = st_q[i] = 0.0f;
+
             // residual / position rows do not depend on the accumulator: fetch chunk 0's before waiting for the MMA
             // and chunk c+1's while chunk c is transposed, so their DRAM latency is off the critical path
             constexpr bool kHasAdd = (EPI == EPI_BIAS_RESID_F16 || EPI == EPI_BIAS_GELU_POS_F16);
@@ -238,7 +272,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 tmem_ld_32x32b_x32(taddr, acc);
                 tmem_ld_wait_on(acc);
                 const int nc = n0 + c * 32;
-                if (EPI == EPI_QKV_SPLIT_BF16 && nc >= p.n_split) {
+                if (kQkv && nc >= p.n_split) {
                     // values: out2[b][head][c][t]; for a fixed column the warp's 32 rows are 32 consecutive t
                     if (valid_own) {
                         const float4* bias4 = reinterpret_cast<const float4*>(p.bias + nc);
@@ -247,10 +281,19 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             const float4 bb = __ldg(bias4 + j);
-                            o2[(long long)(4 * j + 0) * p.t_pad] = __float2bfloat16_rn(__uint_as_float(acc[4 * j + 0]) + bb.x);
-                            o2[(long long)(4 * j + 1) * p.t_pad] = __float2bfloat16_rn(__uint_as_float(acc[4 * j + 1]) + bb.y);
-                            o2[(long long)(4 * j + 2) * p.t_pad] = __float2bfloat16_rn(__uint_as_float(acc[4 * j + 2]) + bb.z);
-                            o2[(long long)(4 * j + 3) * p.t_pad] = __float2bfloat16_rn(__uint_as_float(acc[4 * j + 3]) + bb.w);
+                            float4 a4 = make_float4(__uint_as_float(acc[4 * j + 0]), __uint_as_float(acc[4 * j + 1]),
+                                                    __uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3]));
+                            if (kLn) {
+                                const float4 cc = __ldg(reinterpret_cast<const float4*>(p.c1 + nc) + j);
+                                a4.x = fmaf(-mean_own, cc.x, a4.x) * rstd_own;
+                                a4.y = fmaf(-mean_own, cc.y, a4.y) * rstd_own;
+                                a4.z = fmaf(-mean_own, cc.z, a4.z) * rstd_own;
+                                a4.w = fmaf(-mean_own, cc.w, a4.w) * rstd_own;
+                            }
+                            o2[(long long)(4 * j + 0) * p.t_pad] = __float2bfloat16_rn(a4.x + bb.x);
+                            o2[(long long)(4 * j + 1) * p.t_pad] = __float2bfloat16_rn(a4.y + bb.y);
+                            o2[(long long)(4 * j + 2) * p.t_pad] = __float2bfloat16_rn(a4.z + bb.z);
+                            o2[(long long)(4 * j + 3) * p.t_pad] = __float2bfloat16_rn(a4.w + bb.w);
                         }
                     }
                     continue;
@@ -266,11 +309,25 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 // phase 2: 8 lanes per row; bias / activation / residual applied on the way out.  The residual /
                 // position loads of all 8 rows are issued together, before anything depends on them.
                 const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + nc) + c4);
+                float4 cc = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (kLn) cc = __ldg(reinterpret_cast<const float4*>(p.c1 + nc) + c4);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int rl = 4 * i + sub_row;
                     float4 v = stage[rl * 8 + (c4 ^ (rl & 7))];
-                    if (EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_GELU_POS_F16) {
+                    if (kLn) {
+                        // rstd acc + (c2 - rstd mean c1): two packed FMAs per pair, bias (= c2, in `bb`) included
+                        const float2 nm = make_float2(nmean_c[i], nmean_c[i]), rs = make_float2(rstd_c[i], rstd_c[i]);
+                        const float2 lo = __ffma2_rn(rs, make_float2(v.x, v.y),
+                                                     __ffma2_rn(nm, make_float2(cc.x, cc.y), make_float2(bb.x, bb.y)));
+                        const float2 hi = __ffma2_rn(rs, make_float2(v.z, v.w),
+                                                     __ffma2_rn(nm, make_float2(cc.z, cc.w), make_float2(bb.z, bb.w)));
+                        v = make_float4(lo.x, lo.y, hi.x, hi.y);
+                        if (kGelu) {
+                            const float2 g0 = gelu_poly2(lo), g1 = gelu_poly2(hi);
+                            v = make_float4(g0.x, g0.y, g1.x, g1.y);
+                        }
+                    } else if (kGelu) {
                         const float2 lo = gelu_poly2(__fadd2_rn(make_float2(v.x, v.y), make_float2(bb.x, bb.y)));
                         const float2 hi = gelu_poly2(__fadd2_rn(make_float2(v.z, v.w), make_float2(bb.z, bb.w)));
                         v = make_float4(lo.x, lo.y, hi.x, hi.y);
@@ -279,7 +336,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     }
                     const bool ok = (valid_c >> i) & 1u;
                     const unsigned off = row_off_c[i] + nc + 4 * c4;
-                    if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_QKV_SPLIT_BF16) {
+                    if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || kQkv || kLn) {
                         uint2 q;
                         q.x = pack_bf16x2(v.x, v.y);
                         q.y = pack_bf16x2(v.z, v.w);
@@ -296,9 +353,31 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                         q.x = *reinterpret_cast<const unsigned*>(&lo);
                         q.y = *reinterpret_cast<const unsigned*>(&hi);
                         if (ok) *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.out) + off) = q;
+                        if (kMayProduce) {
+                            st_s[i] += (r0 + r1) + (r2 + r3);
+                            st_q[i] = fmaf(r0, r0, fmaf(r1, r1, fmaf(r2, r2, fmaf(r3, r3, st_q[i]))));
+                        }
                     }
                 }
                 __syncwarp();
+            }
+            if (produce) {
+                // the 8 lanes of a row hold partials of this warp's BN / 2 columns: reduce, lane c4 == 0 writes the slice
+                const int parts = p.N / (BN / 2);
+                const int slice = (tile % num_n) * 2 + half;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float a = st_s[i], b = st_q[i];
+#pragma unroll
+                    for (int o = 1; o < 8; o <<= 1) {
+                        a += __shfl_xor_sync(0xffffffffu, a, o);
+                        b += __shfl_xor_sync(0xffffffffu, b, o);
+                    }
+                    if (c4 == 0 && ((valid_c >> i) & 1u)) {
+                        const long long orow = (long long)(row_off_c[i] / (unsigned)p.ldo);
+                        p.stats_out[orow * parts + slice] = make_float2(a, b);
+                    }
+                }
             }
             tc_fence_before();
             __syncwarp();
@@ -365,6 +444,8 @@ cudaError_t launch_bn(int epi, const CUtensorMap& ta, const CUtensorMap& tb, con
         case EPI_BIAS_RESID_F16: return launch_one<BN, EPI_BIAS_RESID_F16>(ta, tb, p, sm_count, stream);
         case EPI_BIAS_GELU_POS_F16: return launch_one<BN, EPI_BIAS_GELU_POS_F16>(ta, tb, p, sm_count, stream);
         case EPI_QKV_SPLIT_BF16: return launch_one<BN, EPI_QKV_SPLIT_BF16>(ta, tb, p, sm_count, stream);
+        case EPI_LN_GELU_BF16: return launch_one<BN, EPI_LN_GELU_BF16>(ta, tb, p, sm_count, stream);
+        case EPI_LN_QKV_SPLIT_BF16: return launch_one<BN, EPI_LN_QKV_SPLIT_BF16>(ta, tb, p, sm_count, stream);
     }
     return cudaErrorInvalidValue;
 }
@@ -390,6 +471,8 @@ cudaError_t set_smem_bn() {
     if ((e = set_smem<BN, EPI_BIAS_GELU_BF16>()) != cudaSuccess) return e;
     if ((e = set_smem<BN, EPI_BIAS_RESID_F16>()) != cudaSuccess) return e;
     if ((e = set_smem<BN, EPI_QKV_SPLIT_BF16>()) != cudaSuccess) return e;
+    if ((e = set_smem<BN, EPI_LN_GELU_BF16>()) != cudaSuccess) return e;
+    if ((e = set_smem<BN, EPI_LN_QKV_SPLIT_BF16>()) != cudaSuccess) return e;
     return set_smem<BN, EPI_BIAS_GELU_POS_F16>();
 }
 }  // namespace
@@ -404,6 +487,9 @@ cudaError_t gemm_init_device() {
 cudaError_t gemm_launch(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int sm_count,
                         cudaStream_t stream) {
     if (p.K % BK != 0 || p.N % 128 != 0 || p.a_cols % BK != 0 || p.M <= 0) return cudaErrorInvalidValue;
+    if ((epi == EPI_LN_GELU_BF16 || epi == EPI_LN_QKV_SPLIT_BF16) &&
+        (!p.stats_in || !p.c1 || p.stats_parts <= 0 || p.ln_dim <= 0))
+        return cudaErrorInvalidValue;
     return gemm_block_n(p.N) == 256 ? launch_bn<256>(epi, ta, tb, p, sm_count, stream)
                                     : launch_bn<128>(epi, ta, tb, p, sm_count, stream);
 }

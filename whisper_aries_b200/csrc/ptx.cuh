@@ -105,6 +105,12 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N, b
            | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+// Same kind::f16 descriptor with f16 x f16 operands (formats 0) -> f32: the LayerNorm-folded GEMMs read the f16 residual
+// stream as their A operand and keep gamma-scaled weights in f16.
+__host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t M, uint32_t N) {
+    return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
 // tcgen05.mma / tcgen05.commit are issued by ONE thread.  Every lane of the issuing warp executes the wrappers below
 // (with identical, warp-uniform operands) and the instruction itself is predicated on elect.sync.  Under an ordinary
 // divergent `if (lane == 0)` ptxas wraps each tcgen05 instruction in a loop over the active lanes (~13 instructions,
