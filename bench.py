@@ -707,12 +707,27 @@ def main() -> int:
                 "flops_per_launch": gemm_flops_per_step * args.steps / max(gemm_launches, 1),
                 "ms_per_launch": gemm_ms / max(gemm_launches, 1), "launches": gemm_launches,
                 "traffic": traffic.get("gemm_bf16_tcgen05")}
+    # log-mel: the WHOLE mel path of the step (every launch between PCM and the conv1 operand), against the HBM figure
+    # BASELINE.json asks to be quoted (algorithmic bytes = f32 PCM in + f32 [n_mels, 3000] out per window, SURVEY.md 8d,
+    # although the fused path writes bf16 time-major and never stores f32 mel).  The kernel is FP32-issue-bound, not
+    # HBM-bound: the FMA-pipe / issue-slot utilisation from the committed ncu capture sit beside it.
     mel_bytes = B * (480000 * 4 + shape.n_mels * 3000 * 4)
-    mel_ms, mel_n = prof["logmel_tiles"]
-    mel_gbs = mel_bytes * mel_n / (mel_ms * 1e-3) / 1e9 if mel_ms > 0 else 0.0
-    roofline_mel = {"kernel": "logmel_tiles_kernel", "bound": "hbm", "achieved": mel_gbs, "peak": peaks["hbm_gbs"],
+    mel_classes = ["logmel_tiles", "logmel_clamp", "mel_transpose"]
+    mel_ms = sum(prof[k][0] for k in mel_classes)
+    mel_launches = sum(prof[k][1] for k in mel_classes)
+    mel_passes = max(prof["logmel_tiles"][1], 1)
+    mel_gbs = mel_bytes * mel_passes / (mel_ms * 1e-3) / 1e9 if mel_ms > 0 else 0.0
+    tiles_ms = prof["logmel_tiles"][0] / mel_passes
+    mel_ncu = traffic.get("logmel_tiles_kernel_ncu", {})
+    roofline_mel = {"kernel": "whole log-mel path: logmel_tiles_kernel<time-major bf16> + logmel_clamp_tm_kernel "
+                              "(PCM f32 -> conv1 operand; no f32 mel in HBM, no transpose launch)",
+                    "bound": "hbm", "achieved": mel_gbs, "peak": peaks["hbm_gbs"],
                     "unit": "GB/s", "frac": mel_gbs / peaks["hbm_gbs"], "peak_source": peaks["source"],
-                    "bytes_per_launch": mel_bytes, "ms_per_launch": mel_ms / max(mel_n, 1),
+                    "bytes_per_launch": mel_bytes, "ms_per_step": mel_ms / mel_passes,
+                    "launches_per_step": mel_launches / mel_passes,
+                    "tiles_kernel_only": {"ms": tiles_ms, "frac": (mel_bytes / (tiles_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]) if tiles_ms > 0 else 0.0},
+                    "fp32_pipe_frac": mel_ncu.get("fma_pipe_frac"), "issue_slot_frac": mel_ncu.get("issue_active_frac"),
+                    "binding": "fp32 issue (ncu: issue slots / FMA pipe, profiles/r02/ncu_full_mel-fused.txt), not HBM",
                     "traffic": traffic.get("logmel_tiles_kernel")}
     attn_ms, attn_n = prof["attention"]
     attn_flops = B * 4.0 * T * T * d

@@ -75,6 +75,37 @@ def diag_melperf():
               f"{gb / (avg * 1e-3):.0f} GB/s avg  ({best * 1e3 / B:.2f} us/window)", flush=True)
 
 
+def diag_melfused():
+    """The fused PCM -> conv1-operand kernels of aries_encode_pcm (per-kernel CUDA events of the library's profiler),
+    next to the f32 FeatureExtractor path, same process and clocks: 64 windows, 128 mel bins."""
+    from whisper_aries_b200 import WhisperModel, synthetic
+    B = 64
+    shape = synthetic.EncoderShape("mel128-toy", 128, 128, 2, 2, 512)
+    model = WhisperModel(shape, synthetic.encoder_weights(shape, 1), device="cuda", device_index=0)
+    xs = torch.from_numpy(osynth.batch_signals(6, 0)).to(dev).repeat(11, 1)[:B].contiguous()
+    fe = model.feature_extractor
+    out = torch.empty((B, 128, 3000), device=dev)
+    fe(xs[:1])
+    lib, h = fe._ctx.lib, fe._handle
+    for rep in range(3):
+        for _ in range(3):
+            model.encode_audio(xs)
+        model.encoder.set_profiling(True)
+        model.encoder.collect_profile()
+        n = 20
+        for _ in range(n):
+            model.encode_audio(xs)
+        torch.cuda.synchronize()
+        prof = model.encoder.collect_profile()
+        model.encoder.set_profiling(False)
+
+        def run():
+            _lib.check(lib.aries_logmel_run(h, xs.data_ptr(), B, 480000, xs.stride(0), 160, out.data_ptr(), 3000, None))
+        best, avg = timed(run, iters=20)
+        print(f"melfused B={B}: fused tiles {prof['logmel_tiles'][0] / n * 1e3:.1f} us + clamp {prof['logmel_clamp'][0] / n * 1e3:.1f} us"
+              f" | f32 path (tiles + clamp) best {best * 1e3:.1f} us avg {avg * 1e3:.1f} us", flush=True)
+
+
 def gemm_ref(a, b, bias, epi, resid=None, pos=None, pos_rows=0):
     acc = a.float() @ b.float().t() + bias
     if epi in (1, 3):
@@ -248,6 +279,8 @@ if __name__ == "__main__":
             diag_ln()
         elif what == "attn":
             diag_attn()
+        elif what == "melfused":
+            diag_melfused()
         elif what.startswith("enc-"):
             parts = what.split("-", 1)[1].split(":")
             name = parts[0]

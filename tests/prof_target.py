@@ -1,5 +1,5 @@
 """Small profiling targets for ncu (run under gpurun):
-    python tests/prof_target.py mel|attn|ln|gemm-o|gemm-fc1|gemm-fc2|gemm-qkv|dec-xattn|dec-skinny|dec-logits"""
+    python tests/prof_target.py mel|mel-fused|attn|ln|gemm-o|gemm-fc1|gemm-fc2|gemm-qkv|dec-xattn|dec-skinny|dec-logits"""
 import ctypes
 import sys
 
@@ -26,6 +26,16 @@ if what == "mel":
     out = torch.empty((B, 128, 3000), device=dev)
     for _ in range(3):
         fe(xs, frames_out=3000)
+    torch.cuda.synchronize()
+elif what == "mel-fused":
+    # the fused PCM -> conv1-operand launch of aries_encode_pcm (128 mel bins) in front of a toy encoder
+    from whisper_aries_b200 import WhisperModel
+    B = 64
+    shape = synthetic.EncoderShape("mel128-toy", 128, 128, 2, 2, 512)
+    model = WhisperModel(shape, synthetic.encoder_weights(shape, 1), device="cuda", device_index=0)
+    xs = torch.from_numpy(synthetic.batch_signals(6, 0)).to(dev).repeat(11, 1)[:B].contiguous()
+    for _ in range(3):
+        model.encode_audio(xs)
     torch.cuda.synchronize()
 elif what == "attn":
     B_, T_, H = 8, 1500, 20

@@ -119,9 +119,103 @@ def test_decoder_variables_round_trip(tmp_path):
             assert np.abs(got[k] - v).max() <= 2 ** -11 * np.abs(v).max()
         else:
             assert np.array_equal(got[k], v), k
-    assert np.array_equal(got["decoder/projection/weight"], got["decoder/embeddings/weight"])     # the alias
+    # the tied projection is not materialised a second time: the decoder takes its tied path (one matrix in HBM)
+    assert "decoder/projection/weight" not in got and info["tied_projection"] is True
     with pytest.raises((KeyError, ValueError)):
         enc_only = tmp_path / "enc"
         enc_only.mkdir()
         ct2_model.write_model_bin(str(enc_only / "model.bin"), dict(osynth.encoder_weights(osynth.SHAPES["micro"], 7)))
         ct2_model.load_decoder_weights(str(enc_only))
+
+
+def _ct2_fixture_bytes(entries, aliases, spec=b"WhisperSpec", revision=3, version=6):
+    """A ``model.bin`` assembled byte by byte from CTranslate2's documented serialisation -- NOT through
+    ``ct2_model.write_model_bin`` -- following ``ModelSpec._serialize`` (python/ctranslate2/specs/model_spec.py, 4.x):
+
+        model.write(struct.pack("I", CURRENT_BINARY_VERSION))          # 6
+        _write_string(self.name); model.write(struct.pack("I", self.revision))
+        model.write(struct.pack("I", len(variables)))
+        for name, value in variables:
+            _write_string(name); model.write(struct.pack("B", len(value.shape)))
+            for dim in value.shape: model.write(struct.pack("I", dim))
+            model.write(struct.pack("B", value.dtype id)); model.write(struct.pack("I", value.num_bytes()))
+            model.write(value.to_bytes())
+        model.write(struct.pack("I", len(aliases)))
+        for alias, variable_name in aliases: _write_string(alias); _write_string(variable_name)
+        _write_string(s) = pack("H", len(s) + 1) + s.encode("utf-8") + pack("B", 0)
+
+    with the C++ ``DataType`` ids FLOAT32 0, INT8 1, INT16 2, INT32 3, FLOAT16 4, BFLOAT16 5 (include/ctranslate2/types.h).
+    ``entries``: (name bytes, shape tuple, dtype id, payload bytes)."""
+    def wstr(b):
+        return struct.pack("<H", len(b) + 1) + b + b"\x00"
+    out = bytearray()
+    out += struct.pack("<I", version) + wstr(spec) + struct.pack("<I", revision) + struct.pack("<I", len(entries))
+    for name, shape, dtype_id, payload in entries:
+        out += wstr(name) + struct.pack("<B", len(shape))
+        for dim in shape:
+            out += struct.pack("<I", dim)
+        out += struct.pack("<B", dtype_id) + struct.pack("<I", len(payload)) + payload
+    out += struct.pack("<I", len(aliases))
+    for alias, target in aliases:
+        out += wstr(alias) + wstr(target)
+    return bytes(out)
+
+
+def test_reader_against_a_fixture_built_from_the_published_serialisation(tmp_path):
+    """Row f2 pinned against something other than its own writer: every byte below comes from struct.pack calls laid
+    out as CTranslate2's converter writes them; expected values are computed by hand here (int8 / scale, int16 / scalar
+    scale, IEEE half and bfloat16 bit patterns)."""
+    # float32 vector
+    f32 = struct.pack("<4f", 1.5, -2.25, 0.0, 3.0e-3)
+    # int8 matrix [2, 3] with per-row scales (weight = q / scale): rows scaled by 127 / amax
+    q8 = struct.pack("<6b", 127, -64, 0, -127, 1, 32)
+    s8 = struct.pack("<2f", 254.0, 63.5)
+    # int16 matrix [1, 2] with ONE scalar scale (rank-0 variable)
+    q16 = struct.pack("<2h", 1000, -32767)
+    s16 = struct.pack("<f", 2000.0)
+    # float16: 0x3C00 = 1.0, 0xC000 = -2.0, 0x3555 ~ 0.333251953125; bfloat16: 0x3F80 = 1.0, 0xBF00 = -0.5, 0x4049 = 3.140625
+    f16 = struct.pack("<3H", 0x3C00, 0xC000, 0x3555)
+    bf16 = struct.pack("<3H", 0x3F80, 0xBF00, 0x4049)
+    entries = [
+        (b"encoder/conv1/bias", (4,), 0, f32),
+        (b"encoder/layer_0/ffn/linear_0/weight", (2, 3), 1, q8),
+        (b"encoder/layer_0/ffn/linear_0/weight_scale", (2,), 0, s8),
+        (b"encoder/layer_0/ffn/linear_1/weight", (1, 2), 2, q16),
+        (b"encoder/layer_0/ffn/linear_1/weight_scale", (), 0, s16),
+        (b"encoder/layer_norm/gamma", (3,), 4, f16),
+        (b"decoder/layer_norm/beta", (3,), 5, bf16),
+        (b"decoder/embeddings/weight", (1, 3), 4, f16),
+    ]
+    blob = _ct2_fixture_bytes(entries, [(b"decoder/projection/weight", b"decoder/embeddings/weight")])
+    # spot-check the framing itself: version, "WhisperSpec\0" with its length prefix, revision, count
+    assert blob[:4] == b"\x06\x00\x00\x00" and blob[4:6] == b"\x0c\x00" and blob[6:18] == b"WhisperSpec\x00"
+    assert blob[18:22] == b"\x03\x00\x00\x00" and blob[22:26] == b"\x08\x00\x00\x00"
+    path = tmp_path / "model.bin"
+    path.write_bytes(blob)
+    variables, meta = ct2_model.read_model_bin(str(path))
+    assert meta["spec"] == "WhisperSpec" and meta["revision"] == 3 and meta["binary_version"] == 6
+    assert meta["aliases"] == {"decoder/projection/weight": "decoder/embeddings/weight"}
+    assert variables["encoder/layer_0/ffn/linear_0/weight"].dtype == np.int8
+    assert variables["encoder/layer_0/ffn/linear_1/weight_scale"].shape == ()
+    enc, _ = ct2_model._select((variables, meta), "encoder/")
+    assert np.array_equal(enc["encoder/conv1/bias"], np.array([1.5, -2.25, 0.0, 3.0e-3], np.float32))
+    assert np.allclose(enc["encoder/layer_0/ffn/linear_0/weight"],
+                       np.array([[127 / 254.0, -64 / 254.0, 0.0], [-127 / 63.5, 1 / 63.5, 32 / 63.5]]), rtol=0, atol=1e-7)
+    assert np.allclose(enc["encoder/layer_0/ffn/linear_1/weight"], np.array([[0.5, -32767 / 2000.0]]), rtol=0, atol=1e-6)
+    assert np.array_equal(enc["encoder/layer_norm/gamma"], np.array([1.0, -2.0, 0.333251953125], np.float32))
+    assert not any(k.endswith("_scale") for k in enc)
+    dec, _ = ct2_model._select((variables, meta), "decoder/")
+    assert np.array_equal(dec["decoder/layer_norm/beta"], np.array([1.0, -0.5, 3.140625], np.float32))
+    assert dec["decoder/projection/weight"] is dec["decoder/embeddings/weight"]          # alias shares the array
+    # and the package's own writer emits the same bytes for the same float32 / float16 content (writer pinned too)
+    own = tmp_path / "own.bin"
+    ct2_model.write_model_bin(str(own), {"encoder/conv1/bias": np.array([1.5, -2.25, 0.0, 3.0e-3], np.float32),
+                                         "encoder/layer_norm/gamma": np.array([1.0, -2.0, 0.333251953125], np.float32)},
+                              dtypes={"encoder/layer_norm/gamma": "float16"}, aliases={"a/b": "encoder/conv1/bias"})
+    want = _ct2_fixture_bytes([(b"encoder/conv1/bias", (4,), 0, f32), (b"encoder/layer_norm/gamma", (3,), 4, f16)],
+                              [(b"a/b", b"encoder/conv1/bias")])
+    assert own.read_bytes() == want
+    # truncation anywhere inside the variable table is reported, not mis-parsed
+    (tmp_path / "cut.bin").write_bytes(blob[:60])
+    with pytest.raises(ValueError):
+        ct2_model.read_model_bin(str(tmp_path / "cut.bin"))

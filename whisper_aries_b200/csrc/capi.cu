@@ -343,13 +343,26 @@ int aries_encode_pcm(aries_encoder* enc, aries_mel* mel, const float* pcm_dev, i
         return fail(ARIES_EINVAL, "aries_encode_pcm: need batch > 0 and 0 < n_samples <= 480000 (one 30-second window)");
     const size_t need = aries::encoder_workspace_bytes(enc->plan, batch);
     if (!workspace || workspace_bytes < need) return fail(ARIES_EINVAL, "aries_encode_pcm: workspace too small");
-    float* mel_buf = aries::encoder_workspace_mel(enc->plan, workspace, batch);
+    if (!pcm_dev || pcm_stride < n_samples) return fail(ARIES_EINVAL, "aries_encode_pcm: NULL pcm or pcm_stride < n_samples");
+    if (reinterpret_cast<uintptr_t>(workspace) & 255) return fail(ARIES_EINVAL, "aries_encode_pcm: workspace must be 256-byte aligned");
+    // one launch: PCM -> log-mel -> bf16 time-major conv1 operand inside the workspace (the f32 mel never exists in HBM)
+    int c_pad = 0;
+    void* operand = aries::encoder_workspace_conv1_operand(enc->plan, workspace, batch, &c_pad);
     aries::Profiler* prof = aries::encoder_plan_profiler(enc->plan);
-    mel->prof = prof->enabled() ? prof : nullptr;
-    rc = aries_logmel_run(mel, pcm_dev, batch, n_samples, pcm_stride, 160, mel_buf, 3000, stream);
-    mel->prof = nullptr;
-    if (rc) return rc;
-    return aries_encoder_run(enc, mel_buf, batch, 3000, out_dev, workspace, workspace_bytes, stream);
+    cudaError_t e = aries::logmel_run_time_major(mel->plan, pcm_dev, batch, n_samples, pcm_stride, 160, operand, 3000, c_pad,
+                                                 static_cast<cudaStream_t>(stream), &mel->last_launches,
+                                                 prof->enabled() ? prof : nullptr);
+    if (e == cudaErrorInvalidValue)
+        return fail(ARIES_EINVAL, "aries_encode_pcm: the fused path supports n_mels <= 128 (every Whisper size); use "
+                                  "aries_logmel_run + aries_encoder_run for wider filter banks");
+    if (e != cudaSuccess) return fail_cuda("aries_encode_pcm (log-mel)", e);
+    e = aries::encoder_run(enc->plan, nullptr, batch, 3000, out_dev, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) {
+        g_error = std::string("aries_encode_pcm: ") + aries::encoder_plan_error(enc->plan);
+        cudaGetLastError();
+        return e == cudaErrorInvalidValue ? ARIES_EINVAL : ARIES_ECUDA;
+    }
+    return ARIES_OK;
 }
 
 int aries_pcm_s16_to_f32(aries_ctx* ctx, const int16_t* pcm_s16_dev, float* out_dev, int64_t n, void* stream) {

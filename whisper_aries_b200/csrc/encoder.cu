@@ -81,7 +81,7 @@ struct EncoderPlan {
 namespace {
 
 struct WsLayout {
-    size_t melT, x, stats, ctx, qk, vt, h, mel, total;
+    size_t melT, x, stats, ctx, qk, vt, h, total;
 };
 
 WsLayout ws_layout(const EncoderPlan& pl, int batch) {
@@ -102,7 +102,6 @@ WsLayout ws_layout(const EncoderPlan& pl, int batch) {
     w.vt = take(B * d * pl.t_pad * 2);
     const size_t hb = B * T * (size_t)c.d_ffn * 2, c1 = B * kRowsPadded * d * 2;
     w.h = take(hb > c1 ? hb : c1);
-    w.mel = take(B * (size_t)c.n_mels * kFramesIn * 4);
     w.total = off;
     return w;
 }
@@ -318,7 +317,9 @@ cudaError_t encoder_run(EncoderPlan* pl, const float* mel, int batch, int frames
                         size_t ws_bytes, cudaStream_t stream) {
     const auto& c = pl->cfg;
     const int d = c.d_model, f = c.d_ffn, T = c.n_ctx, cp = pl->c_pad;
-    if (batch <= 0 || frames <= 0 || frames > kFramesIn) {
+    // mel == nullptr: the time-major conv1 operand (encoder_workspace_conv1_operand) has already been written by the
+    // fused log-mel kernel; otherwise mel is f32 [batch, n_mels, frames] in upstream's layout and is transposed here
+    if (batch <= 0 || (mel && (frames <= 0 || frames > kFramesIn))) {
         pl->error = "invalid batch / frames";
         return cudaErrorInvalidValue;
     }
@@ -359,10 +360,12 @@ cudaError_t encoder_run(EncoderPlan* pl, const float* mel, int batch, int frames
     ARIES_TRY(cudaMemset2DAsync(static_cast<char*>(c1) + (size_t)(kRowsPadded - 1) * d * 2, (size_t)kRowsPadded * d * 2, 0,
                                 (size_t)d * 2, batch, stream), "memset");
 
-    pl->prof.begin(KC_TRANSPOSE, stream);
-    ARIES_TRY(mel_to_time_major(mel, batch, c.n_mels, frames, melT, cp, stream), "mel transpose");
-    pl->prof.end(stream);
-    ++launches;
+    if (mel) {
+        pl->prof.begin(KC_TRANSPOSE, stream);
+        ARIES_TRY(mel_to_time_major(mel, batch, c.n_mels, frames, melT, cp, stream), "mel transpose");
+        pl->prof.end(stream);
+        ++launches;
+    }
 
     GemmParams g{};
     // conv1: row r = b * 3002 + t reads padded rows t, t+1, t+2 (taps 0..2); writes padded row t + 1
@@ -431,8 +434,9 @@ cudaError_t encoder_run(EncoderPlan* pl, const float* mel, int batch, int frames
 
 Profiler* encoder_plan_profiler(EncoderPlan* pl) { return &pl->prof; }
 
-float* encoder_workspace_mel(const EncoderPlan* pl, void* workspace, int batch) {
-    return reinterpret_cast<float*>(static_cast<char*>(workspace) + ws_layout(*pl, batch).mel);
+void* encoder_workspace_conv1_operand(const EncoderPlan* pl, void* workspace, int batch, int* c_pad) {
+    *c_pad = pl->c_pad;
+    return static_cast<char*>(workspace) + ws_layout(*pl, batch).melT;
 }
 
 }  // namespace aries

@@ -24,11 +24,13 @@ cudaError_t encoder_plan_create(int device, int sm_count, const EncoderShapeC& c
                                 int n_weights, EncoderPlan** out, std::string* why);
 void encoder_plan_destroy(EncoderPlan* pl);
 size_t encoder_workspace_bytes(const EncoderPlan* pl, int batch);
-// mel: device f32 [batch, n_mels, frames]; out: device bf16 [batch, 1500, d_model].  Stream-ordered.
+// mel: device f32 [batch, n_mels, frames], or nullptr when the conv1 operand in the workspace was written directly
+// (fused PCM path); out: device bf16 [batch, 1500, d_model].  Stream-ordered.
 cudaError_t encoder_run(EncoderPlan* pl, const float* mel, int batch, int frames, void* out_bf16, void* workspace,
                         size_t ws_bytes, cudaStream_t stream);
-// f32 [batch, n_mels, 3000] scratch inside the workspace for the fused PCM path.
-float* encoder_workspace_mel(const EncoderPlan* pl, void* workspace, int batch);
+// The conv1 operand inside the workspace: bf16 time-major [batch, 3002, c_pad]; the fused PCM path has the log-mel
+// kernel write rows 1..3000 of it (rows 0 and 3001 are zeroed by encoder_run).
+void* encoder_workspace_conv1_operand(const EncoderPlan* pl, void* workspace, int batch, int* c_pad);
 const char* encoder_plan_error(const EncoderPlan* pl);
 int encoder_plan_last_launches(const EncoderPlan* pl);
 const EncoderShapeC* encoder_plan_cfg(const EncoderPlan* pl);

@@ -9,8 +9,17 @@
 //   -> exchange -> stage 2 (20-pt FFTs, |X|^2) -> sparse mel filters -> log10 / scale in registers
 //   -> coalesced stores of (log10(mel) + 4) / 4, plus the running per-item maximum (warp shuffles -> shared
 //   atomics -> one global atomic per tile) and the tile minimum.
-// The "max(x, global_max - 8)" clamp needs the maximum over the WHOLE call, so it is applied by a second, tiny
-// kernel that only rewrites tiles whose minimum is below the threshold (most tiles of real audio are not).
+// The "max(x, global_max - 8)" clamp needs the maximum over the WHOLE call.  FeatureExtractor.__call__ (f32 output in
+// upstream's [n_mels, frames] layout) applies it with a second, tiny kernel that only rewrites tiles whose minimum is
+// below the threshold (most tiles of real audio are not).
+// The fused PCM -> encoder path (aries_encode_pcm) uses the <kTM = true> instance instead: it writes the conv1 operand
+// directly -- bf16, time-major [B, 3002, c_pad], a tile being 64 consecutive rows = one contiguous, fully coalesced
+// block staged through shared memory -- so the f32 mel tensor never exists in HBM and the transpose kernel is gone.
+// The clamp is then applied to the flagged tiles of that bf16 tensor (logmel_clamp_tm_kernel, still in L2):
+// bf16(max(v, thr)) == max(bf16(v), bf16(thr)) because rounding is monotonic, so clamping the stored bf16 values is
+// bit-identical to clamping in f32 first.  (Round 2 also tried folding that pass into the same launch -- the CTA that
+// finishes a window's last tile fixing the window's flagged tiles -- and measured 2.0 ms instead of 0.2: on the
+// benchmark's signals 47 % of the tiles are flagged and one CTA per window walks them serially.)
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -72,7 +81,16 @@ struct Params {
     unsigned* gmax;             // [batch], order_f32 encoded
     float* tile_min;            // [batch][tiles_per_item]
     int bank_slot;
+    // <kTM>: bf16 time-major output [batch][frames_out + 2][c_pad] (rows 1 .. frames_out written)
+    unsigned short* out_tm;
+    int c_pad;
 };
+
+__device__ __forceinline__ unsigned short bf16_rn(float v) {
+    unsigned u = __float_as_uint(v);
+    u += 0x7FFFu + ((u >> 16) & 1u);
+    return (unsigned short)(u >> 16);
+}
 
 __device__ __forceinline__ float fast_log2(float x) {
     float y;
@@ -117,15 +135,29 @@ __device__ __forceinline__ void store_tile(float* pcm, const float4 (&r)[kPrefet
         const int i4 = threadIdx.x + k * kThreads;
         if (i4 < kFloat4PerTile) {
             float* d = pcm + pcm_addr(4 * i4);         // the 4 samples share one 160-block: consecutive words
-            d[0] = r[k].x; d[1] = r[k].y; d[2] = r[k].z; d[3] = r[k].w;
+            // lanes L and L + 8 start 32 words apart (the same bank): each group of 8 lanes writes its four words in
+            // a different rotation, so one store instruction touches 32 distinct banks (r01: 2.8 M conflicts here)
+            const float v[4] = {r[k].x, r[k].y, r[k].z, r[k].w};
+            const int rot = (threadIdx.x >> 3) & 3;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int e = (c + rot) & 3;
+                d[e] = (e == 0) ? v[0] : (e == 1) ? v[1] : (e == 2) ? v[2] : v[3];
+            }
         }
     }
 }
 
+constexpr int kStagePitch = 130;                 // bf16 per staged row: 65 words, so lane = frame hits 32 banks
+
+template <bool kTM>
 __global__ void __launch_bounds__(kThreads, 1) logmel_tiles_kernel(const Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
     float* P = sm.e_re;
+    // <kTM> staging tile [64 frames][kStagePitch] bf16 behind the power tile (P ends 64 floats into e_im)
+    unsigned short* staged = reinterpret_cast<unsigned short*>(sm.e_im + 64);
+    static_assert(64 * 4 + kTileFrames * kStagePitch * 2 <= kExchangeFloat2 * 4, "staging tile must fit behind P");
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -173,11 +205,25 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_tiles_kernel(const Params 
             float* o0 = p.out + (long long)b * p.out_stride + f0;
             const int lim = p.n_frames < p.frames_out ? p.n_frames : p.frames_out;
             const bool full_tile = (t + 1) * kTileFrames <= lim;          // uniform: every frame is real and stored
-            for (int m = warp; m < p.n_mels; m += kThreads / 32) {
+            for (int m = warp; m < (kTM ? p.c_pad : p.n_mels); m += kThreads / 32) {
+                if (kTM && m >= p.n_mels) {                    // channel padding of the conv1 operand
+                    staged[lane * kStagePitch + m] = 0;
+                    staged[(lane + 32) * kStagePitch + m] = 0;
+                    continue;
+                }
                 float a0, a1;
                 mel_dot2(P, bank, m, lane, a0, a1);
                 const float v0 = fmaf(fast_log2(fmaxf(a0, 1e-10f)), 0.07525749891599529f, 1.0f);   // (log10 + 4) / 4
                 const float v1 = fmaf(fast_log2(fmaxf(a1, 1e-10f)), 0.07525749891599529f, 1.0f);
+                if (kTM) {
+                    // frames past the audio are zero FEATURES (pad_or_trim); frames past frames_out are not stored below
+                    const bool r0 = f0 < p.n_frames, r1 = f0 + 32 < p.n_frames;
+                    if (r0) { vmax = fmaxf(vmax, v0); vmin = fminf(vmin, v0); }
+                    if (r1) { vmax = fmaxf(vmax, v1); vmin = fminf(vmin, v1); }
+                    staged[lane * kStagePitch + m] = r0 ? bf16_rn(v0) : (unsigned short)0;
+                    staged[(lane + 32) * kStagePitch + m] = r1 ? bf16_rn(v1) : (unsigned short)0;
+                    continue;
+                }
                 float* om = o0 + (size_t)m * p.frames_out;
                 if (full_tile) {
                     vmax = fmaxf(vmax, fmaxf(v0, v1));
@@ -217,6 +263,19 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_tiles_kernel(const Params 
             sm.red_min = 0xFFFFFFFFu;
         }
         // the next write of red_* is three barriers away; the next read of P/E likewise
+        if (kTM) {
+            // the tile = 64 consecutive rows of the time-major tensor: one contiguous block, 4-byte coalesced stores
+            const int wpr = p.c_pad >> 1;                                       // 32-bit words per row
+            unsigned* dst = reinterpret_cast<unsigned*>(p.out_tm) +
+                            ((long long)b * (p.frames_out + 2) + 1 + (long long)t * kTileFrames) * wpr;
+            const unsigned* src = reinterpret_cast<const unsigned*>(staged);
+            const int rows = min(kTileFrames, p.frames_out - t * kTileFrames);
+            for (int i = threadIdx.x; i < rows * wpr; i += kThreads) {
+                const int row = i / wpr, w = i - row * wpr;
+                dst[i] = src[row * (kStagePitch / 2) + w];
+            }
+            __syncthreads();                  // staged (aliasing E) is free again before the next tile's stage 1
+        }
     }
 }
 
@@ -242,6 +301,46 @@ __global__ void __launch_bounds__(256) logmel_clamp_kernel(const Params p) {
             const float v = *q;
             if (v < thr) *q = thr;
         }
+    }
+}
+
+// Clamp pass of the fused path: one CTA per (tile, window); only tiles whose minimum is below the window's threshold do
+// anything.  16 words (32 bf16) per thread, all loads issued before the first store.
+__global__ void __launch_bounds__(256) logmel_clamp_tm_kernel(const Params p) {
+    const int t = blockIdx.x;
+    const int b = blockIdx.y;
+    const float thr = unorder_f32(p.gmax[b]) - 2.0f;
+    if (!(p.tile_min[b * p.tiles_per_item + t] < thr)) return;
+    const unsigned short thr_bf = bf16_rn(thr);
+    const float thr_r = __uint_as_float((unsigned)thr_bf << 16);
+    const int wpr = p.c_pad >> 1;
+    const int lim = min(p.n_frames, p.frames_out);
+    const int rows = min(kTileFrames, lim - t * kTileFrames);              // real, stored frames of this tile
+    if (rows <= 0) return;
+    unsigned* tile_w = reinterpret_cast<unsigned*>(p.out_tm) +
+                       ((long long)b * (p.frames_out + 2) + 1 + (long long)t * kTileFrames) * wpr;
+    const int mel_words = (p.n_mels + 1) >> 1;
+    const int total = rows * mel_words;
+    constexpr int kPer = 16;
+    unsigned u[kPer];
+    int idx[kPer];
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+        const int i = threadIdx.x + k * 256;
+        const int row = i / mel_words, w = i - row * mel_words;
+        idx[k] = (i < total) ? row * wpr + w : -1;
+        u[k] = (i < total) ? tile_w[idx[k]] : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+        if (idx[k] < 0) continue;
+        const int w = idx[k] % wpr;
+        const float lo = __uint_as_float(u[k] << 16), hi = __uint_as_float(u[k] & 0xFFFF0000u);
+        const bool last_odd = (2 * w + 1 >= p.n_mels);                      // channel padding stays 0
+        const unsigned nlo = lo < thr_r ? thr_bf : (u[k] & 0xFFFFu);
+        const unsigned nhi = (!last_odd && hi < thr_r) ? thr_bf : (u[k] >> 16);
+        const unsigned nu = nlo | (nhi << 16);
+        if (nu != u[k]) tile_w[idx[k]] = nu;
     }
 }
 
@@ -363,7 +462,10 @@ cudaError_t logmel_plan_create(int device, int sm_count, int n_mels, const float
     Tables tb;
     build_tables(tb);
     if ((e = cudaMemcpyToSymbol(c_tables, &tb, sizeof(tb))) != cudaSuccess) goto fail;
-    if ((e = cudaFuncSetAttribute(logmel_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if ((e = cudaFuncSetAttribute(logmel_tiles_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)sizeof(Smem))) != cudaSuccess)
+        goto fail;
+    if ((e = cudaFuncSetAttribute(logmel_tiles_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)sizeof(Smem))) != cudaSuccess)
         goto fail;
     pl->bank_slot = acquire_bank_slot(device, mb, &e);
@@ -433,7 +535,7 @@ cudaError_t logmel_run(LogmelPlan* pl, const float* pcm, int batch, long long n_
     if (total > 0) {
         const int grid = (int)(total < pl->sm_count ? total : pl->sm_count);
         if (prof) prof->begin(KC_MEL, stream);
-        logmel_tiles_kernel<<<grid, kThreads, sizeof(Smem), stream>>>(p);
+        logmel_tiles_kernel<false><<<grid, kThreads, sizeof(Smem), stream>>>(p);
         if (prof) prof->end(stream);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         ++n_launch;
@@ -448,6 +550,67 @@ cudaError_t logmel_run(LogmelPlan* pl, const float* pcm, int batch, long long n_
         ++n_launch;
     }
     if (launches) *launches = n_launch;
+    return cudaSuccess;
+}
+
+cudaError_t logmel_run_time_major(LogmelPlan* pl, const float* pcm, int batch, long long n_samples, long long pcm_stride,
+                                  int padding, void* out_tm_bf16, int frames_out, int c_pad, cudaStream_t stream,
+                                  int* launches, Profiler* prof) {
+    const long long padded = n_samples + padding;
+    const int n_frames = (int)(padded / kHop);
+    const int tiles = (n_frames + kTileFrames - 1) / kTileFrames;
+    if (c_pad < pl->n_mels || c_pad > kStagePitch - 2 || (c_pad & 1) || frames_out <= 0 || tiles <= 0)
+        return cudaErrorInvalidValue;
+    cudaError_t e;
+    if (batch > pl->cap_batch || (long long)batch * tiles > pl->cap_tiles) {
+        if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
+        cudaFree(pl->d_gmax);
+        cudaFree(pl->d_tile_min);
+        pl->d_gmax = nullptr;
+        pl->d_tile_min = nullptr;
+        pl->cap_batch = 0;
+        pl->cap_tiles = 0;
+        if ((e = cudaMalloc(&pl->d_gmax, sizeof(unsigned) * batch)) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&pl->d_tile_min, sizeof(float) * (size_t)batch * tiles)) != cudaSuccess) return e;
+        pl->cap_batch = batch;
+        pl->cap_tiles = (long long)batch * tiles;
+    }
+    Params p{};
+    p.pcm = pcm;
+    p.pcm_stride = pcm_stride;
+    p.n_samples = n_samples;
+    p.padded_len = padded;
+    p.batch = batch;
+    p.n_frames = n_frames;
+    p.tiles_per_item = tiles;
+    p.n_mels = pl->n_mels;
+    p.frames_out = frames_out;
+    p.gmax = pl->d_gmax;
+    p.tile_min = pl->d_tile_min;
+    p.bank_slot = pl->bank_slot;
+    p.out_tm = static_cast<unsigned short*>(out_tm_bf16);
+    p.c_pad = c_pad;
+    if ((e = cudaMemsetAsync(pl->d_gmax, 0, sizeof(unsigned) * batch, stream)) != cudaSuccess) return e;
+    if (tiles * kTileFrames < frames_out) {
+        // audio shorter than the window: rows past its last tile are zero features (pad_or_trim); a rare, ragged-tail path
+        const size_t row_bytes = (size_t)c_pad * 2, first = (size_t)1 + (size_t)tiles * kTileFrames;
+        if ((e = cudaMemset2DAsync(static_cast<char*>(out_tm_bf16) + first * row_bytes, (size_t)(frames_out + 2) * row_bytes,
+                                   0, (size_t)(frames_out - tiles * kTileFrames) * row_bytes, batch, stream)) != cudaSuccess)
+            return e;
+    }
+    const long long total = (long long)batch * tiles;
+    const int grid = (int)(total < pl->sm_count ? total : pl->sm_count);
+    if (prof) prof->begin(KC_MEL, stream);
+    logmel_tiles_kernel<true><<<grid, kThreads, sizeof(Smem), stream>>>(p);
+    if (prof) prof->end(stream);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    const int real_tiles = ((n_frames < frames_out ? n_frames : frames_out) + kTileFrames - 1) / kTileFrames;
+    static_assert(kTileFrames * ((kStagePitch - 2) / 2) <= 16 * 256, "clamp kernel covers a tile with 16 words per thread");
+    if (prof) prof->begin(KC_MEL_CLAMP, stream);
+    logmel_clamp_tm_kernel<<<dim3(real_tiles, batch), 256, 0, stream>>>(p);
+    if (prof) prof->end(stream);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (launches) *launches = 2;
     return cudaSuccess;
 }
 

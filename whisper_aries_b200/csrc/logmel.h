@@ -22,6 +22,13 @@ cudaError_t logmel_run(LogmelPlan* pl, const float* pcm, int batch, long long n_
                        int padding, float* out, int frames_out, cudaStream_t stream, int* launches,
                        Profiler* prof = nullptr);
 
+// Fused variant for aries_encode_pcm: ONE launch that writes the conv1 operand directly -- bf16, time-major
+// [batch, frames_out + 2, c_pad] (rows 1 .. frames_out; channels >= n_mels zero; rows 0 and frames_out + 1 are the
+// caller's) -- clamp included (the CTA that finishes a window's last tile fixes that window's flagged tiles in L2).
+cudaError_t logmel_run_time_major(LogmelPlan* pl, const float* pcm, int batch, long long n_samples, long long pcm_stride,
+                                  int padding, void* out_tm_bf16, int frames_out, int c_pad, cudaStream_t stream,
+                                  int* launches, Profiler* prof = nullptr);
+
 // [B, n_mels, frames] f32 -> [B, 3002, c_pad] bf16 rows 1..3000 (time-major conv1 operand); pad rows untouched.
 cudaError_t mel_to_time_major(const float* mel, int batch, int n_mels, int frames, void* out_bf16, int c_pad,
                               cudaStream_t stream);

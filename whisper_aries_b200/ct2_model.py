@@ -15,13 +15,20 @@ On-disk format of ``model.bin`` (ctranslate2 4.x ``ModelSpec._serialize``, binar
     dtype_id: 0 float32, 1 int8, 2 int16, 3 int32, 4 float16, 5 bfloat16
 
 **[unverified offline]**: neither ctranslate2 nor a converted checkpoint exists in the build container, so the layout
-above is restated from the published converter source and pinned only by the round-trip test against
-``write_model_bin`` below (tests/test_ct2_model.py).  int8 / int16 weights carry a per-output-row ``weight_scale``
-variable (``weight = q / scale``), which is folded here; everything is returned as float32 (the C ABI rounds to bf16).
+above is restated from the published converter source (``python/ctranslate2/specs/model_spec.py``, ``_serialize``:
+``CURRENT_BINARY_VERSION = 6``; C++ ``DataType`` enum order FLOAT32, INT8, INT16, INT32, FLOAT16, BFLOAT16).  It is pinned
+by a fixture the test assembles byte by byte with ``struct.pack`` from that description -- independently of
+``write_model_bin`` below -- including an int8 + per-row ``weight_scale`` matrix, an int16 + scalar scale matrix, float16
+and bfloat16 tensors and an alias (tests/test_ct2_model.py), and by the writer / reader round trip.  int8 weights carry a
+per-output-row ``weight_scale`` variable, int16 weights a scalar one (``weight = q / scale``); both are folded here and
+everything is returned as float32 (the C ABI rounds to bf16).  The file is memory-mapped and parsed once per
+``WhisperModel``: the encoder and decoder loaders share the parse, and a tied output projection (an alias of the
+embedding in Whisper checkpoints) is not materialised a second time.
 """
 from __future__ import annotations
 
 import json
+import mmap
 import os
 import struct
 
@@ -64,12 +71,13 @@ class _Reader:
         self.pos += n
         return s
 
-    def raw(self, n: int) -> bytes:
+    def skip(self, n: int) -> int:
+        """Advance past ``n`` payload bytes; returns their offset (the payload is read lazily, straight from the map)."""
         if self.pos + n > len(self.buf):
             raise ValueError("model.bin is truncated")
-        b = self.buf[self.pos:self.pos + n]
+        at = self.pos
         self.pos += n
-        return b
+        return at
 
 
 def read_model_bin(path: str, prefix: str = "") -> tuple[dict, dict]:
@@ -77,7 +85,11 @@ def read_model_bin(path: str, prefix: str = "") -> tuple[dict, dict]:
     whose name starts with ``prefix``.  ``meta`` holds spec name / revision, binary version, aliases and the set of
     bfloat16 variable names."""
     with open(path, "rb") as f:
-        r = _Reader(f.read())
+        size = os.fstat(f.fileno()).st_size
+        if size < 4:
+            raise ValueError("model.bin is truncated")
+        buf = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)      # a ~3 GB checkpoint is never copied wholesale
+    r = _Reader(buf)
     version = r.take("I")
     if not 1 <= version <= BINARY_VERSION:
         raise ValueError(f"model.bin: unsupported binary version {version}")
@@ -101,9 +113,9 @@ def read_model_bin(path: str, prefix: str = "") -> tuple[dict, dict]:
         n = int(np.prod(dims, dtype=np.int64)) if dims else 1
         if n * dt.itemsize != n_bytes:
             raise ValueError(f"model.bin: variable {name!r}: {n_bytes} bytes for shape {dims} of {dt}")
-        data = r.raw(n_bytes)
+        at = r.skip(n_bytes)
         if name.startswith(prefix):
-            variables[name] = np.frombuffer(data, dtype=dt).reshape(dims)
+            variables[name] = np.frombuffer(buf, dtype=dt, count=n, offset=at).reshape(dims)   # view of the map
             if dtype_id == 5:
                 bf16.add(name)
     aliases = {}
@@ -182,19 +194,31 @@ def encoder_shape_of(weights: dict, name: str = "ct2") -> EncoderShape:
     return EncoderShape(name, n_mels, d, d // 64, layers, ffn)
 
 
-def load_encoder_weights(model_dir: str) -> tuple[EncoderShape, dict, dict]:
-    """``(shape, {CT2 variable name: float32 ndarray}, info)`` for the ``encoder/`` variables of a converted model
-    directory.  ``info`` carries ``config.json`` / ``preprocessor_config.json`` (when present) and the container's meta
-    data; ``preprocessor_config.json``'s ``feature_size`` must agree with conv1's input channels."""
+def parse_model_dir(model_dir: str) -> tuple[dict, dict]:
+    """Parses ``model.bin`` ONCE (memory-mapped views) for both loaders below: ``(variables, meta)``."""
     path = os.path.join(model_dir, "model.bin")
     if not os.path.exists(path):
         raise FileNotFoundError(f"{path}: not a CTranslate2 model directory")
-    variables, meta = read_model_bin(path, prefix="encoder/")
+    return read_model_bin(path)
+
+
+def _select(parsed: tuple[dict, dict], prefix: str, skip_aliases_of=()) -> tuple[dict, dict]:
+    """float32 weights of the variables under ``prefix``; an alias shares its target's array (no second dequantised copy)
+    and aliases whose target is in ``skip_aliases_of`` are left out altogether (tied output projection)."""
+    variables, meta = parsed
+    names = [n for n in variables if n.startswith(prefix) and not n.endswith("_scale") and variables[n].ndim >= 1]
+    weights = {n: _dequantise(n, variables, meta) for n in names}
     for alias, target in meta["aliases"].items():
-        if alias.startswith("encoder/") and target in variables:
-            variables[alias] = variables[target]
-    weights = {n: _dequantise(n, variables, meta) for n in variables
-               if not n.endswith("_scale") and variables[n].ndim >= 1}
+        if alias.startswith(prefix) and target in weights and target not in skip_aliases_of:
+            weights[alias] = weights[target]
+    return weights, meta
+
+
+def load_encoder_weights(model_dir: str, parsed=None) -> tuple[EncoderShape, dict, dict]:
+    """``(shape, {CT2 variable name: float32 ndarray}, info)`` for the ``encoder/`` variables of a converted model
+    directory.  ``info`` carries ``config.json`` / ``preprocessor_config.json`` (when present) and the container's meta
+    data; ``preprocessor_config.json``'s ``feature_size`` must agree with conv1's input channels."""
+    weights, meta = _select(parsed or parse_model_dir(model_dir), "encoder/")
     shape = encoder_shape_of(weights, os.path.basename(os.path.normpath(model_dir)) or "ct2")
     info = {"meta": {k: v for k, v in meta.items() if k != "bf16"}}
     for fname in ("config.json", "preprocessor_config.json"):
@@ -228,22 +252,19 @@ def decoder_shape_of(weights: dict, name: str = "ct2"):
     return DecoderShape(name, vocab, d, d // 64, layers, ffn, n_ctx)
 
 
-def load_decoder_weights(model_dir: str):
+def load_decoder_weights(model_dir: str, parsed=None):
     """``(shape, {CT2 variable name: float32 ndarray}, info)`` for the ``decoder/`` variables of a converted model
     directory (embeddings, learned positions, per-layer self-attention / cross-attention / ffn, final LayerNorm and
     the output projection -- an alias of the embedding in Whisper checkpoints).  ``info["suppress_ids"]`` /
-    ``info["suppress_ids_begin"]`` come from ``config.json`` (what upstream's ``suppress_tokens=[-1]`` expands to)."""
-    path = os.path.join(model_dir, "model.bin")
-    if not os.path.exists(path):
-        raise FileNotFoundError(f"{path}: not a CTranslate2 model directory")
-    variables, meta = read_model_bin(path, prefix="decoder/")
-    for alias, target in meta["aliases"].items():
-        if alias.startswith("decoder/") and target in variables:
-            variables[alias] = variables[target]
-    weights = {n: _dequantise(n, variables, meta) for n in variables
-               if not n.endswith("_scale") and variables[n].ndim >= 1}
+    ``info["suppress_ids_begin"]`` come from ``config.json`` (what upstream's ``suppress_tokens=[-1]`` expands to).
+    A projection that is an alias of the embedding is NOT returned as a second matrix: the decoder then takes its tied
+    path and keeps one copy of the 51866 x 1280 matrix in HBM (``info["tied_projection"]`` says so)."""
+    parsed = parsed or parse_model_dir(model_dir)
+    tied = parsed[1]["aliases"].get("decoder/projection/weight") == "decoder/embeddings/weight"
+    weights, meta = _select(parsed, "decoder/", skip_aliases_of=("decoder/embeddings/weight",) if tied else ())
     shape = decoder_shape_of(weights, os.path.basename(os.path.normpath(model_dir)) or "ct2")
-    info = {"meta": {k: v for k, v in meta.items() if k != "bf16"}, "suppress_ids": [], "suppress_ids_begin": []}
+    info = {"meta": {k: v for k, v in meta.items() if k != "bf16"}, "suppress_ids": [], "suppress_ids_begin": [],
+            "tied_projection": tied}
     p = os.path.join(model_dir, "config.json")
     if os.path.exists(p):
         with open(p) as f:

@@ -153,17 +153,18 @@ class WhisperModel:
             # upstream's first argument is "size or path of a converted model directory" (model.bin + config.json);
             # there is no network here, so only the path form can supply weights
             import os
-            from .ct2_model import load_encoder_weights
+            from .ct2_model import load_encoder_weights, parse_model_dir
             if not (isinstance(model_size_or_shape, str) and os.path.isdir(model_size_or_shape)):
                 raise ValueError("weights=None needs the path of a CTranslate2 model directory (model.bin); "
                                  f"got {model_size_or_shape!r}")
             model_dir = model_size_or_shape
-            model_size_or_shape, weights, self.model_info = load_encoder_weights(model_dir)
+            parsed = parse_model_dir(model_dir)                   # model.bin is mapped and parsed once for both halves
+            model_size_or_shape, weights, self.model_info = load_encoder_weights(model_dir, parsed)
             if decoder_shape is None:
                 # the same model.bin carries the decoder: build it too, as upstream's WhisperModel(path) does
                 from .ct2_model import load_decoder_weights
                 try:
-                    decoder_shape, dec_w, dec_info = load_decoder_weights(model_dir)
+                    decoder_shape, dec_w, dec_info = load_decoder_weights(model_dir, parsed)
                 except (KeyError, ValueError):
                     decoder_shape = None                       # an encoder-only directory
                 else:
