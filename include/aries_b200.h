@@ -208,6 +208,43 @@ ARIES_API int aries_decoder_detect_language(aries_decoder* dec, const void* enc_
  * out[4] kernels of the K|V projection phase. */
 ARIES_API int aries_decoder_last_stats(const aries_decoder* dec, float* out, int n);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Row f4: the voice-activity filter in front of the feature extractor.  The reference always passes
+ * vad_filter=True (final_optimized_transcriber.py:440, whitelisted at :318), so upstream's transcribe() runs
+ *     speech_chunks = get_speech_timestamps(audio, VadOptions())     -> aries_vad_speech_timestamps
+ *     audio = np.concatenate(collect_chunks(audio, speech_chunks))   -> aries_collect_chunks
+ * before FeatureExtractor.__call__.  The per-window speech probabilities come from upstream's Silero network, whose
+ * trained weights ship inside the faster-whisper wheel and are not available offline: they are an INPUT here (any model
+ * plugs in); aries_vad_energy_probs is a labelled stand-in (log-energy logistic), not Silero. */
+typedef struct aries_vad_opts {      /* faster_whisper.vad.VadOptions (1.1.1) */
+    float threshold;                 /* 0.5 */
+    float neg_threshold;             /* < 0 = None -> max(threshold - 0.15, 0.01) */
+    int32_t min_speech_duration_ms;  /* 0 */
+    float max_speech_duration_s;     /* <= 0 or inf = unlimited */
+    int32_t min_silence_duration_ms; /* 2000 */
+    int32_t speech_pad_ms;           /* 400 */
+} aries_vad_opts;
+
+/* Number of 512-sample windows upstream evaluates for n_samples of audio (it pads with 512 - n % 512 samples). */
+ARIES_API int64_t aries_vad_num_windows(int64_t n_samples);
+
+/* Replaces: the state machine + padding pass of faster_whisper.vad.get_speech_timestamps.  probs_host: f32
+ * [n_windows] speech probabilities; writes up to `cap` chunks as sample ranges [starts[k], ends[k]) and their count to
+ * *n_out (ARIES_EINVAL if cap is too small; *n_out then holds the needed count).  Host-only: needs no GPU. */
+ARIES_API int aries_vad_speech_timestamps(const float* probs_host, int64_t n_windows, int64_t audio_len,
+                                          const aries_vad_opts* opts, int64_t* starts, int64_t* ends, int cap, int* n_out);
+
+/* Stand-in probability model on the device (NOT Silero): p = sigmoid((20 log10(rms of the window + 1e-10) - center_db)
+ * / width_db); pcm_dev f32 [n_samples] -> probs_dev f32 [aries_vad_num_windows(n_samples)].  Stream-ordered. */
+ARIES_API int aries_vad_energy_probs(aries_ctx* ctx, const float* pcm_dev, int64_t n_samples, float center_db,
+                                     float width_db, float* probs_dev, void* stream);
+
+/* Replaces: faster_whisper.vad.collect_chunks + np.concatenate (one device gather instead of a host copy per chunk).
+ * out_dev f32 [sum(ends - starts)] (capacity out_cap samples); *out_len = samples written.  Stream-ordered. */
+ARIES_API int aries_collect_chunks(aries_ctx* ctx, const float* pcm_dev, int64_t n_samples, const int64_t* starts_host,
+                                   const int64_t* ends_host, int n_chunks, float* out_dev, int64_t out_cap,
+                                   int64_t* out_len, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -42,6 +42,14 @@ class GenerateOpts(ctypes.Structure):
                 ("n_suppress", ctypes.c_int32)]
 
 
+class VadOpts(ctypes.Structure):
+    _fields_ = [("threshold", ctypes.c_float), ("neg_threshold", ctypes.c_float),
+                ("min_speech_duration_ms", ctypes.c_int32), ("max_speech_duration_s", ctypes.c_float),
+                ("min_silence_duration_ms", ctypes.c_int32), ("speech_pad_ms", ctypes.c_int32)]
+
+
+c_float = ctypes.c_float
+
 # name -> (restype, argtypes); every symbol include/aries_b200.h and include/aries_b200_test.h declare
 PROTOTYPES = {
     "aries_abi_version": (c_int, []),
@@ -76,6 +84,12 @@ PROTOTYPES = {
     "aries_decoder_detect_language": (c_int, [c_void_p, c_void_p, c_int, ctypes.POINTER(GenerateOpts), c_void_p, c_int,
                                               c_void_p, c_void_p]),
     "aries_decoder_last_stats": (c_int, [c_void_p, c_float_p, c_int]),
+    "aries_vad_num_windows": (c_int64, [c_int64]),
+    "aries_vad_speech_timestamps": (c_int, [c_void_p, c_int64, c_int64, ctypes.POINTER(VadOpts), c_void_p, c_void_p, c_int,
+                                            ctypes.POINTER(c_int)]),
+    "aries_vad_energy_probs": (c_int, [c_void_p, c_void_p, c_int64, c_float, c_float, c_void_p, c_void_p]),
+    "aries_collect_chunks": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_int64,
+                                     ctypes.POINTER(c_int64), c_void_p]),
     "aries_test_decoder_generate": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, ctypes.POINTER(GenerateOpts),
                                             c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "aries_test_skinny_gemm": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,

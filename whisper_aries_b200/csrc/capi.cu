@@ -17,6 +17,7 @@
 #include "logmel.h"
 #include "profiler.h"
 #include "skinny.h"
+#include "vad.h"
 
 namespace {
 
@@ -41,6 +42,8 @@ struct aries_ctx {
     int device;
     int sm_count;
     bool kernels_ready;
+    long long* d_chunks = nullptr;     // aries_collect_chunks: device copy of (starts | offsets), grown on demand
+    size_t chunks_cap = 0;
 };
 
 struct aries_mel {
@@ -129,7 +132,13 @@ int aries_init(int device, aries_ctx** out) {
         return fail(ARIES_ECUDA, "device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
                                      "; this library is compiled for sm_100a (B200) only");
     if ((e = cudaSetDevice(device)) != cudaSuccess) return fail_cuda("cudaSetDevice", e);
-    aries_ctx* c = new (std::nothrow) aries_ctx{kMagicCtx, device, prop.multiProcessorCount, false};
+    aries_ctx* c = new (std::nothrow) aries_ctx();
+    if (c) {
+        c->magic = kMagicCtx;
+        c->device = device;
+        c->sm_count = prop.multiProcessorCount;
+        c->kernels_ready = false;
+    }
     if (!c) return fail(ARIES_ENOMEM, "out of host memory");
     *out = c;
     return ARIES_OK;
@@ -139,6 +148,7 @@ int aries_destroy(aries_ctx* ctx) {
     if (!ctx) return ARIES_OK;
     if (ctx->magic != kMagicCtx) return fail(ARIES_ESTATE, "invalid context handle");
     ctx->magic = 0;
+    if (ctx->d_chunks && cudaSetDevice(ctx->device) == cudaSuccess) cudaFree(ctx->d_chunks);
     delete ctx;
     return ARIES_OK;
 }
@@ -362,6 +372,74 @@ int aries_encode_pcm(aries_encoder* enc, aries_mel* mel, const float* pcm_dev, i
         cudaGetLastError();
         return e == cudaErrorInvalidValue ? ARIES_EINVAL : ARIES_ECUDA;
     }
+    return ARIES_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ VAD front end (row f4)
+int64_t aries_vad_num_windows(int64_t n_samples) { return n_samples < 0 ? 0 : aries::vad_num_windows(n_samples); }
+
+int aries_vad_speech_timestamps(const float* probs_host, int64_t n_windows, int64_t audio_len, const aries_vad_opts* opts,
+                                int64_t* starts, int64_t* ends, int cap, int* n_out) {
+    if (!probs_host || n_windows < 0 || audio_len < 0 || !opts || !n_out || cap < 0 || (cap > 0 && (!starts || !ends)))
+        return fail(ARIES_EINVAL, "aries_vad_speech_timestamps: bad arguments");
+    if (!(opts->threshold > 0.0f) || opts->min_speech_duration_ms < 0 || opts->min_silence_duration_ms < 0 ||
+        opts->speech_pad_ms < 0)
+        return fail(ARIES_EINVAL, "aries_vad_speech_timestamps: threshold must be > 0 and the durations >= 0");
+    aries::VadOpts o;
+    o.threshold = opts->threshold;
+    o.neg_threshold = opts->neg_threshold;
+    o.min_speech_duration_ms = opts->min_speech_duration_ms;
+    o.max_speech_duration_s = opts->max_speech_duration_s;
+    o.min_silence_duration_ms = opts->min_silence_duration_ms;
+    o.speech_pad_ms = opts->speech_pad_ms;
+    std::vector<long long> s, e;
+    aries::vad_speech_timestamps(probs_host, n_windows, audio_len, o, &s, &e);
+    *n_out = (int)s.size();
+    if ((int)s.size() > cap) return fail(ARIES_EINVAL, "aries_vad_speech_timestamps: more chunks than `cap`");
+    for (size_t i = 0; i < s.size(); ++i) {
+        starts[i] = s[i];
+        ends[i] = e[i];
+    }
+    return ARIES_OK;
+}
+
+int aries_vad_energy_probs(aries_ctx* ctx, const float* pcm_dev, int64_t n_samples, float center_db, float width_db,
+                           float* probs_dev, void* stream) {
+    int rc = use(ctx);
+    if (rc) return rc;
+    if (!pcm_dev || !probs_dev || n_samples <= 0 || !(width_db > 0.0f))
+        return fail(ARIES_EINVAL, "aries_vad_energy_probs: need non-NULL buffers, n_samples > 0 and width_db > 0");
+    cudaError_t e = aries::vad_energy_probs(pcm_dev, n_samples, center_db, width_db, probs_dev, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail_cuda("aries_vad_energy_probs", e);
+    return ARIES_OK;
+}
+
+int aries_collect_chunks(aries_ctx* ctx, const float* pcm_dev, int64_t n_samples, const int64_t* starts_host,
+                         const int64_t* ends_host, int n_chunks, float* out_dev, int64_t out_cap, int64_t* out_len,
+                         void* stream) {
+    int rc = use(ctx);
+    if (rc) return rc;
+    if (n_chunks < 0 || !out_len || (n_chunks > 0 && (!pcm_dev || !starts_host || !ends_host)))
+        return fail(ARIES_EINVAL, "aries_collect_chunks: bad arguments");
+    std::vector<long long> tab(2 * (size_t)(n_chunks > 0 ? n_chunks : 1));
+    long long total = 0;
+    for (int k = 0; k < n_chunks; ++k) {
+        if (starts_host[k] < 0 || ends_host[k] < starts_host[k] || ends_host[k] > n_samples)
+            return fail(ARIES_EINVAL, "aries_collect_chunks: chunk outside [0, n_samples]");
+        tab[k] = starts_host[k];
+        tab[n_chunks + k] = total;
+        total += ends_host[k] - starts_host[k];
+    }
+    *out_len = total;
+    if (total == 0) return ARIES_OK;
+    if (!out_dev || out_cap < total) return fail(ARIES_EINVAL, "aries_collect_chunks: out_dev is NULL or smaller than the chunks");
+    if ((rc = grow(&ctx->d_chunks, &ctx->chunks_cap, tab.size() * sizeof(long long)))) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // pageable source: the copy is staged before the call returns, so `tab` may go out of scope
+    cudaError_t e = cudaMemcpyAsync(ctx->d_chunks, tab.data(), (size_t)2 * n_chunks * sizeof(long long), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return fail_cuda("aries_collect_chunks (table upload)", e);
+    e = aries::collect_chunks(pcm_dev, ctx->d_chunks, ctx->d_chunks + n_chunks, n_chunks, total, out_dev, ctx->sm_count, st);
+    if (e != cudaSuccess) return fail_cuda("aries_collect_chunks", e);
     return ARIES_OK;
 }
 

@@ -205,17 +205,31 @@ class WhisperModel:
             pcm = pcm_s16_to_f32(pcm)
         return self.encoder.encode_pcm(self.feature_extractor, pcm, out=out)
 
-    def encode_long(self, pcm):
+    def encode_long(self, pcm, vad_filter: bool = False, vad_parameters=None, speech_probs=None, vad_model=None):
         """One waveform longer than 30 s, exactly as upstream's ``transcribe`` feeds it to the encoder when it steps
         ``seek`` by full windows: features over the WHOLE call (one clamp maximum, STFT frames that straddle a 30-s
         boundary see real samples on both sides, ref call site final_optimized_transcriber.py:326 with 185-s chunks),
         ``content_frames = frames - 1``, then ``pad_or_trim(features[:, seek:seek + 3000])`` per window -> CUDA bf16
-        ``[ceil(content_frames / 3000), 1500, d_model]``.  ``pcm``: 1-D float32 (numpy or torch, host or device)."""
+        ``[ceil(content_frames / 3000), 1500, d_model]``.  ``pcm``: 1-D float32 (numpy or torch, host or device).
+
+        ``vad_filter=True`` (what the reference always passes, ref: final_optimized_transcriber.py:440) first removes
+        non-speech as upstream does -- ``get_speech_timestamps`` + ``collect_chunks`` on the device (``vad.py``; the
+        probability model is pluggable, see there) -- and returns ``(states, speech_chunks)`` so that the caller can
+        map times back with ``vad.SpeechTimestampsMap``."""
         import torch
         x = pcm if isinstance(pcm, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(pcm, dtype=np.float32))
         if x.dim() != 1 or x.numel() == 0:
             raise ValueError("encode_long expects a non-empty 1-D waveform")
         x = x.to(device=self.encoder.device, dtype=torch.float32)
+        chunks = None
+        if vad_filter:
+            from . import vad
+            opts = vad_parameters if isinstance(vad_parameters, vad.VadOptions) else vad.VadOptions(**(vad_parameters or {}))
+            chunks = vad.get_speech_timestamps(x, opts, speech_probs=speech_probs, model=vad_model)
+            x = vad.collect_chunks(x, chunks)
+            if x.numel() == 0:                     # no speech at all: nothing reaches the feature extractor
+                return torch.empty((0, self.shape.n_ctx, self.shape.d_model), dtype=torch.bfloat16,
+                                   device=self.encoder.device), chunks
         feats = self.feature_extractor(x)                                   # [n_mels, (N + 160) // 160], device
         content = feats.shape[-1] - 1
         n_win = max(1, -(-content // 3000))
@@ -223,7 +237,8 @@ class WhisperModel:
         for k in range(n_win):
             seg = feats[:, k * 3000: min((k + 1) * 3000, content)]
             batch[k, :, : seg.shape[1]] = seg
-        return self.encoder.encode(batch)
+        out = self.encoder.encode(batch)
+        return (out, chunks) if vad_filter else out
 
 
 def pcm_s16_to_f32(pcm_s16, out=None):
