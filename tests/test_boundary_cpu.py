@@ -1,6 +1,7 @@
 """CPU: the C-ABI library loads and exports every symbol include/*.h declares; host logic of the shim and scheduler.
 No compute calls here (no GPU in this container)."""
 import ctypes
+import dataclasses
 import os
 import re
 
@@ -240,3 +241,20 @@ def test_lengths_reach_the_worker_and_ragged_tail_keeps_its_length():
     with pytest.raises(ValueError):
         sched.run(w, np.zeros((3, 1)), lengths=n[:2])
     sched.close()
+
+
+def test_product_and_oracle_generators_are_the_same_bytes():
+    """``whisper_aries_b200/synthetic.py`` (what bench.py / smoke() feed the kernels) and ``oracle/synth.py`` (what the
+    oracle and the golden fixtures are built from) are kept as two files on purpose -- the product package must not
+    import oracle/ -- so this test is what keeps them equal."""
+    for seed in (0, 1, 2, 63):
+        assert np.array_equal(synthetic.window_signal(seed, 48000), osynth.window_signal(seed, 48000))
+    assert np.array_equal(synthetic.batch_signals(3, 5, 16000), osynth.batch_signals(3, 5, 16000))
+    for name in ("micro", "tiny"):
+        a, b = synthetic.encoder_weights(synthetic.SHAPES[name], 1234), osynth.encoder_weights(osynth.SHAPES[name], 1234)
+        assert list(a) == list(b) and all(np.array_equal(a[k], b[k]) for k in a)
+    da, db = synthetic.decoder_weights(synthetic.DEC_SHAPES["micro"], 32), osynth.decoder_weights(osynth.DEC_SHAPES["micro"], 32)
+    assert list(da) == list(db) and all(np.array_equal(da[k], db[k]) for k in da)
+    ta, tb = synthetic.WhisperTokens.for_vocab(51866), osynth.WhisperTokens.for_vocab(51866)
+    assert dataclasses.asdict(ta) == dataclasses.asdict(tb)
+    assert np.array_equal(synthetic.sinusoids(1500, 384), osynth.sinusoids(1500, 384))

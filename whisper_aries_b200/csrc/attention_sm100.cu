@@ -56,7 +56,7 @@ constexpr int kSmemBytes = kQTiles * kQTileBytes + kKStages * kKBytes + kVStages
 constexpr uint32_t kTmemCols = 256 * kQTiles;            // per tile g: S0 [128g, +64) S1 [128g+64, +64); O_g [kTmemO+80g, +80)
 constexpr uint32_t kTmemO = 128 * kQTiles;
 constexpr float kScale = 0.18033688011112042f;           // log2(e) / sqrt(64)
-constexpr int kDefaultPoly = 0;                          // ARIES_ATTN_POLY overrides (0, 4 or 8)
+constexpr int kDefaultPoly = 8;                          // ARIES_ATTN_POLY overrides (0, 4 or 8); 8 measured best in the full step (round 2)
 constexpr float kRescaleThreshold = 8.0f;                // lazy rescale: only when the row max grew by > 2^8
 
 // Test-only timeline (variant bit 2, ARIES_ATTN_TRACE=1): clock64 stamps of lane 0 of every warp of a few CTAs.

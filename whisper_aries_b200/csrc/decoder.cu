@@ -460,12 +460,8 @@ cudaError_t decoder_generate(DecoderPlan* pl, const void* enc_out, int batch, co
         }
         h_bits[t >> 5] |= 1u << (t & 31);
     }
-    ARIES_TRY(cudaMemcpyAsync(pl->tokens, h_tok.data(), h_tok.size() * 4, cudaMemcpyHostToDevice, stream), "upload tokens");
-    ARIES_TRY(cudaMemcpyAsync(pl->sot_index, h_sot.data(), batch * 4, cudaMemcpyHostToDevice, stream), "upload state");
-    ARIES_TRY(cudaMemcpyAsync(pl->use_ts, h_uts.data(), batch * 4, cudaMemcpyHostToDevice, stream), "upload state");
-    ARIES_TRY(cudaMemcpyAsync(pl->last_ts, h_lts.data(), batch * 4, cudaMemcpyHostToDevice, stream), "upload state");
-    ARIES_TRY(cudaMemcpyAsync(pl->suppress_bits, h_bits.data(), h_bits.size() * 4, cudaMemcpyHostToDevice, stream),
-              "upload suppress mask");
+    // every argument is validated before the first enqueue: an early return must not leave copies from these stack-local
+    // vectors in flight
     std::vector<int> h_forced;
     if (o.forced && o.n_forced > 0) {
         h_forced.assign(o.forced, o.forced + (size_t)batch * o.n_forced);
@@ -474,9 +470,16 @@ cudaError_t decoder_generate(DecoderPlan* pl, const void* enc_out, int batch, co
                 pl->error = "forced token id outside the vocabulary";
                 return cudaErrorInvalidValue;
             }
+    }
+    ARIES_TRY(cudaMemcpyAsync(pl->tokens, h_tok.data(), h_tok.size() * 4, cudaMemcpyHostToDevice, stream), "upload tokens");
+    ARIES_TRY(cudaMemcpyAsync(pl->sot_index, h_sot.data(), batch * 4, cudaMemcpyHostToDevice, stream), "upload state");
+    ARIES_TRY(cudaMemcpyAsync(pl->use_ts, h_uts.data(), batch * 4, cudaMemcpyHostToDevice, stream), "upload state");
+    ARIES_TRY(cudaMemcpyAsync(pl->last_ts, h_lts.data(), batch * 4, cudaMemcpyHostToDevice, stream), "upload state");
+    ARIES_TRY(cudaMemcpyAsync(pl->suppress_bits, h_bits.data(), h_bits.size() * 4, cudaMemcpyHostToDevice, stream),
+              "upload suppress mask");
+    if (!h_forced.empty())
         ARIES_TRY(cudaMemcpyAsync(pl->forced, h_forced.data(), h_forced.size() * 4, cudaMemcpyHostToDevice, stream),
                   "upload forced tokens");
-    }
     ARIES_TRY(cudaMemsetAsync(pl->step, 0, 4, stream), "memset");
     ARIES_TRY(cudaMemsetAsync(pl->n_done, 0, 4, stream), "memset");
     ARIES_TRY(cudaMemsetAsync(pl->ticket, 0, 4, stream), "memset");
