@@ -7,8 +7,8 @@ B="python bench.py --steps 1 --warmup 1 --windows 16 --no-cpu-baseline --no-e2e"
 timeout -s KILL 300 $B > gpurun_out/plain_bench_w16.log 2>&1 && \
 timeout -s KILL 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/launches.csv $B > gpurun_out/ncu_launches.log 2>&1
 echo "launch list exit $?"
-for t in mel attn ln gemm-fc1 gemm-qkv gemm-o; do
-  case $t in mel) k="logmel_tiles";; attn) k="attention_fwd";; ln) k="layernorm";; *) k="gemm_bf16";; esac
+for t in mel mel-fused attn ln gemm-fc1 gemm-qkv gemm-o gemm-fc2; do
+  case $t in mel|mel-fused) k="logmel_tiles";; attn) k="attention_fwd";; ln) k="layernorm";; *) k="gemm_bf16";; esac
   timeout -s KILL 120 python tests/prof_target.py $t > gpurun_out/plain_$t.log 2>&1 && \
   timeout -s KILL 400 ncu --set full --clock-control none --import-source on -k regex:"$k" -s 2 -c 1 -o gpurun_out/final_$t -f python tests/prof_target.py $t > gpurun_out/ncu_final_$t.log 2>&1
   echo "ncu $t exit $?"

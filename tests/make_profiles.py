@@ -44,10 +44,13 @@ def source_summary(rep, top=14):
 
 
 traffic = {}
-names = {"mel": "logmel_tiles_kernel", "attn": "attention_fwd_kernel", "ln": "layernorm_kernel",
-         "gemm-fc1": "gemm_bf16_tcgen05 (fc1: M=96000 N=5120 K=1280, bias+GELU epilogue)",
-         "gemm-qkv": "gemm_bf16_tcgen05 (QKV: M=96000 N=3840 K=1280, bias epilogue)",
-         "gemm-o": "gemm_bf16_tcgen05 (out-proj: M=96000 N=1280 K=1280, bias + f16 residual epilogue)",
+names = {"mel": "logmel_tiles_kernel<false> (FeatureExtractor.__call__: f32 [n_mels, frames] output)",
+         "mel-fused": "logmel_tiles_kernel<true> (aries_encode_pcm: PCM -> bf16 time-major conv1 operand, 64 windows, 128 bins)",
+         "attn": "attention_fwd_kernel", "ln": "layernorm_kernel (ln_post: the one LayerNorm launch left per forward pass)",
+         "gemm-fc1": "gemm_bf16_tcgen05 (fc1: M=96000 N=5120 K=1280, f16 x f16, LayerNorm-folded + GELU epilogue)",
+         "gemm-qkv": "gemm_bf16_tcgen05 (QKV: M=96000 N=3840 K=1280, f16 x f16, LayerNorm-folded epilogue, Q|K row-major + V transposed)",
+         "gemm-o": "gemm_bf16_tcgen05 (out-proj: M=96000 N=1280 K=1280, bias + f16 residual epilogue + LayerNorm partials)",
+         "gemm-fc2": "gemm_bf16_tcgen05 (fc2: M=96000 N=1280 K=5120, bias + f16 residual epilogue + LayerNorm partials)",
          "dec-xattn": "decode_attention_kernel (row f1: cross-attention of one decode step, 64 windows x 20 heads x 1500 keys)",
          "dec-skinny": "skinny_gemm_tcgen05 (row f1: fc1 of one decode step, 64 sequences, N=5120 K=1280, cluster split-K 7)",
          "dec-logits": "skinny_gemm_tcgen05 (row f1: logits of one decode step, 64 sequences, N=51866 K=1280)"}
@@ -73,6 +76,17 @@ for tag, name in names.items():
     lines.append(f"dram bytes per launch: read {rd / 1e6:.1f} MB + write {wr / 1e6:.1f} MB = {(rd + wr) / 1e6:.1f} MB")
     traffic[tag] = {"kernel": name, "dram_read_bytes": rd, "dram_write_bytes": wr, "dram_bytes": rd + wr,
                     "duration_us_under_ncu": float(m["gpu__time_duration.sum"][1])}
+
+    def pct(key):
+        hit = [h for h in m if h == key or h.startswith(key + " ")]
+        try:
+            return float(m[hit[0]][1]) / 100.0 if hit else None
+        except ValueError:
+            return None
+    traffic[tag]["fma_pipe_frac"] = pct("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_elapsed")
+    traffic[tag]["issue_active_frac"] = pct("sm__issue_active.avg.pct_of_peak_sustained_elapsed")
+    traffic[tag]["tensor_pipe_frac"] = pct("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed")
+    traffic[tag]["xu_pipe_frac"] = pct("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_elapsed")
     lines += ["", "## source page (sampled stalls)", source_summary(rep)]
     with open(os.path.join(out_dir, f"ncu_full_{tag}.txt"), "w") as f:
         f.write("\n".join(lines) + "\n")
@@ -116,7 +130,11 @@ for B in (1, 64):
 # bench.py reads the fc1 GEMM as the representative launch of the dominant kernel class
 tj = {"source": f"profiles/{rnd}/ncu_full_*.txt (ncu --set full, one launch each, tests/prof_target.py shapes)",
       "gemm_bf16_tcgen05": traffic.get("gemm-fc1", {}).get("dram_bytes"),
-      "logmel_tiles_kernel": traffic.get("mel", {}).get("dram_bytes"),
-      "decode_attention_kernel": traffic.get("dec-xattn", {}).get("dram_bytes"), "detail": traffic}
+      "logmel_tiles_kernel": traffic.get("mel-fused", traffic.get("mel", {})).get("dram_bytes"),
+      "decode_attention_kernel": traffic.get("dec-xattn", {}).get("dram_bytes"),
+      "logmel_tiles_kernel_ncu": {"fma_pipe_frac": traffic.get("mel-fused", {}).get("fma_pipe_frac"),
+                                  "issue_active_frac": traffic.get("mel-fused", {}).get("issue_active_frac"),
+                                  "source": f"profiles/{rnd}/ncu_full_mel-fused.txt"},
+      "detail": traffic}
 json.dump(tj, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
 print(json.dumps({k: round(v["dram_bytes"] / 1e6, 1) for k, v in traffic.items()}))

@@ -76,16 +76,44 @@ elif what in ("dec-skinny", "dec-logits"):
         lib.aries_test_skinny_gemm(ctx.handle, epi, B_, N, K, ptr(x), ptr(w), ptr(bias), ptr(out), N, 0, None)
     torch.cuda.synchronize()
 else:
-    M = 96000
-    N, K, epi = {"gemm-o": (1280, 1280, 2), "gemm-fc1": (5120, 1280, 1), "gemm-qkv": (3840, 1280, 0),
+    # the GEMMs of one encoder layer at the bench shape (M = 64 x 1500) with the epilogues the encoder really uses:
+    #   gemm-fc1  LayerNorm-folded fc1 + GELU (epi 5)            gemm-qkv  LayerNorm-folded QKV, Q|K row-major, V transposed (epi 6)
+    #   gemm-o / gemm-fc2  bias + f16 residual, LayerNorm partials written (epi 2 with stats_out)
+    M, T_ = 96000, 1500
+    N, K, epi = {"gemm-o": (1280, 1280, 2), "gemm-fc1": (5120, 1280, 5), "gemm-qkv": (3840, 1280, 6),
                  "gemm-fc2": (1280, 5120, 2)}[what]
-    a = torch.randn(M, K, device=dev).bfloat16()
-    b = (torch.randn(N, K, device=dev) * 0.05).bfloat16()
     bias = torch.randn(N, device=dev)
-    resid = torch.randn(M, N, device=dev).half() if epi == 2 else None
-    out = torch.empty((M, N), device=dev, dtype=torch.bfloat16 if epi < 2 else torch.float16)
+    if epi == 2:
+        a = torch.randn(M, K, device=dev).bfloat16()
+        b = (torch.randn(N, K, device=dev) * 0.05).bfloat16()
+        resid = torch.randn(M, N, device=dev).half()
+        out = torch.empty((M, N), device=dev, dtype=torch.float16)
+        parts = lib.aries_test_gemm_stats_parts(N)
+        stats = torch.empty((M, parts, 2), device=dev)
+
+        def run():
+            lib.aries_test_gemm_ln(ctx.handle, 2, M, N, K, ptr(a), ptr(b), ptr(bias), None, None, 0, 0, ptr(resid), ptr(out),
+                                   None, 0, 0, 0, ptr(stats), None)
+    else:
+        a = (torch.randn(M, K, device=dev) * 2 + 0.3).half()                    # the f16 residual stream
+        b = (torch.randn(N, K, device=dev) * 0.05).half()                       # gamma-scaled f16 weights
+        c1 = b.float().sum(1).contiguous()
+        parts = lib.aries_test_gemm_stats_parts(K)
+        xs = a.float().view(M, parts, K // parts)
+        stats = torch.stack([xs.sum(2), (xs * xs).sum(2)], dim=2).contiguous()
+        del xs
+        if epi == 5:
+            out = torch.empty((M, N), device=dev, dtype=torch.bfloat16)
+            out2, n_split, t_pad = None, 0, 0
+        else:
+            out = torch.empty((M, 2 * K), device=dev, dtype=torch.bfloat16)
+            out2 = torch.empty((M // T_, K // 64, 64, 1504), device=dev, dtype=torch.bfloat16)
+            n_split, t_pad = 2 * K, 1504
+
+        def run():
+            lib.aries_test_gemm_ln(ctx.handle, epi, M, N, K, ptr(a), ptr(b), ptr(bias), ptr(c1), ptr(stats), parts, K, None,
+                                   ptr(out), ptr(out2), n_split, T_, t_pad, None, None)
     for _ in range(3):
-        lib.aries_test_gemm(ctx.handle, epi, M, N, K, ptr(a), ptr(b), ptr(bias), ptr(resid), None, 0, ptr(out), None, 0,
-                            0, 0, None)
+        run()
     torch.cuda.synchronize()
 print("ok", what)
