@@ -699,6 +699,10 @@ int aries_test_gemm_ln(aries_ctx* ctx, int epi, int M, int N, int K, const void*
     p.bias = bias; p.resid = resid; p.out = out;
     p.c1 = c1; p.stats_in = static_cast<const float2*>(stats_in); p.stats_parts = stats_parts; p.ln_dim = ln_dim;
     p.ln_eps = 1e-5f; p.stats_out = static_cast<float2*>(stats_out);
+    if (const char* tr = getenv("ARIES_GEMM_TRACE")) {            // test hook: device u64 [tiles][8], see gemm.h
+        p.trace = reinterpret_cast<unsigned long long*>(strtoull(tr, nullptr, 0));
+        p.trace_tiles = 48;
+    }
     if (epi == aries::EPI_LN_QKV_SPLIT_BF16) {
         p.p_in = t_rows; p.t_valid = t_rows; p.p_out = t_rows; p.ldo = n_split;
         p.out2 = out2; p.n_split = n_split; p.t_pad = t_pad;

@@ -46,6 +46,11 @@ struct GemmParams {
     int ln_dim;         // normalised width (d_model)
     float ln_eps;
     const float* c1;    // [N] (EPI_LN_*); c2 is passed in `bias`
+    // test-only timeline (tests/gemm_trace.py): clock64 stamps of CTA 0's MMA warp and first epilogue warp,
+    // [tile][8]: mma {before accumulator wait, after, cycles spent waiting for operands, main loop end} |
+    //            epilogue {before accumulator-full wait, after, end of tile, unused}
+    unsigned long long* trace;
+    int trace_tiles;
 };
 
 int gemm_block_n(int N);

@@ -11,7 +11,8 @@
 // layers (k=3) run as implicit GEMMs over a zero-padded time-major activation without materialising im2col
 // (CT2 ref: layers::WhisperEncoder conv1/conv2).  Epilogues fuse bias, exact-erf GELU,
 // the residual add (f16 residual stream) and the positional-embedding add and remap GEMM rows to output
-// rows so padded rows are never written.
+// rows so padded rows are never written.  The epilogue goes straight from the accumulator row a thread owns to global
+// memory in 32-byte sectors (no shared-memory staging: shared memory belongs to the MMA operands).
 #include <cuda_fp16.h>
 
 #include <cstdlib>
@@ -38,13 +39,12 @@ constexpr int kBBoxRows = 128;               // rows of one B TMA box (the tenso
 template <int BN, int CG>
 struct Cfg {
     static_assert(CG == 1 || (CG == 2 && BN == 256), "the CTA-pair kernel is built for BN = 256 only");
-    static constexpr int kStages = (BN == 256 && CG == 1) ? 4 : 6;
+    static constexpr int kStages = (BN == 256 && CG == 1) ? 4 : (CG == 2 ? 7 : 6);   // no epilogue staging buffer any more
     static constexpr int kABytes = BM * BK * 2;
     static constexpr int kBBytes = (BN / CG) * BK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kBarBytes = 256;
-    static constexpr int kEpiStageBytes = kEpiWarps * 32 * 32 * 4;                // 4 KB transpose buffer per warp
-    static constexpr int kSmemBytes = kStages * kStageBytes + kEpiStageBytes + kBarBytes + 1024;   // +1024: alignment
+    static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;   // +1024: alignment
     static constexpr uint32_t kTmemCols = 2 * BN;
 };
 
@@ -56,8 +56,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
-    uint8_t* epi_stage = smem + C::kStages * C::kStageBytes;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + C::kEpiStageBytes);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
     uint64_t* empty_bar = full_bar + C::kStages;
     uint64_t* tfull_bar = empty_bar + C::kStages;      // [2] accumulator ready
     uint64_t* tempty_bar = tfull_bar + 2;              // [2] accumulator drained
@@ -146,11 +145,18 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
                 const int as = it & 1;
                 const uint32_t aphase = (it >> 1) & 1;
+                const bool tr = p.trace != nullptr && blockIdx.x == 0 && it < p.trace_tiles;
+                unsigned long long t0 = 0, t_wait = 0;
+                if (tr) t0 = clock64();
                 mbar_wait(&tempty_bar[as], aphase ^ 1);
                 tc_fence_after();
+                if (tr && lane == 0) { p.trace[it * 8 + 0] = t0; p.trace[it * 8 + 1] = clock64(); }
                 const uint32_t d_tmem = tmem_base + as * BN;
                 for (int kb = 0; kb < num_kb; ++kb) {
+                    unsigned long long w0 = 0;
+                    if (tr) w0 = clock64();
                     mbar_wait(&full_bar[stage], phase);
+                    if (tr) t_wait += clock64() - w0;
                     tc_fence_after();
                     const uint32_t a_lo = desc_lo0 + ((uint32_t)(stage * C::kStageBytes) >> 4);
                     if (CG == 2) {
@@ -164,118 +170,107 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     }
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                 }
+                if (tr && lane == 0) { p.trace[it * 8 + 2] = t_wait; p.trace[it * 8 + 3] = clock64(); }
             }
         }
     } else {
         // ---------------------------------------------------------------- epilogue warps
-        // TMEM hands every thread one accumulator ROW (32 consecutive columns per load).  Storing that directly makes
-        // each warp-level access touch 32 different rows (32 half-used sectors), which made the f32 epilogues
-        // LSU-bound.  So each warp transposes its 32x32 chunk through a private, XOR-swizzled 4 KB shared buffer and
-        // then reads / writes global memory with 8 lanes per row: full 32-byte sectors, 4 rows per instruction.
+        // TMEM hands every thread one accumulator ROW (32 consecutive f32 columns per load).  Every output of this
+        // kernel is a 2-byte type, so those 32 columns are 64 contiguous bytes = two full 32-byte sectors of the thread's
+        // own row: each thread stores them with two 256-bit STG (and reads the f16 residual the same way), a warp-level
+        // access = 32 full sectors.  Round 1 transposed every 32x32 chunk through shared memory instead (needed when the
+        // residual stream was f32); the round-2 timeline (tests/gemm_trace.py) showed what that cost: the staging
+        // traffic shares the shared-memory port with the MMA's operand reads, and a K = 64 block took 632 cycles in fc1
+        // (epilogue active 54 % of the time) against 540 in fc2 (24 %) for the same 512-cycle MMA work.
         const int ew = warp - 2;
         const int quarter = warp & 3;          // TMEM lane quarter this warp may touch
         const int half = ew >> 2;              // which half of the tile's columns
         constexpr int kChunks = (BN / 2) / 32;
-        float4* stage = reinterpret_cast<float4*>(epi_stage + ew * 4096);
-        const int sub_row = lane >> 3;         // coalesced phase: row 4 i + sub_row, 16-byte column c4
-        const int c4 = lane & 7;
+        constexpr bool kLn = (EPI == EPI_LN_GELU_BF16 || EPI == EPI_LN_QKV_SPLIT_BF16);
+        constexpr bool kQkv = (EPI == EPI_QKV_SPLIT_BF16 || EPI == EPI_LN_QKV_SPLIT_BF16);
+        constexpr bool kGelu = (EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_GELU_POS_F16 || EPI == EPI_LN_GELU_BF16);
+        constexpr bool kResid = (EPI == EPI_BIAS_RESID_F16);
+        constexpr bool kPos = (EPI == EPI_BIAS_GELU_POS_F16);
+        constexpr bool kF16Out = kResid || kPos;
         int it = 0;
         for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
             const int m0 = (tile / num_n) * (BM * CG) + cta_rank * BM;
             const int n0 = (tile % num_n) * BN + half * (BN / 2);
-            const int rbase = m0 + quarter * 32;
-            // output rows of the coalesced phase: element offset of the row start (32-bit: the largest activation
-            // is far below 2^32 elements), 0 for rows that must not be written (their loads stay in bounds)
-            unsigned row_off_c[8];
-            int t_c[8];
-            unsigned valid_c = 0;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int r = rbase + 4 * i + sub_row;
-                const int b = r / p.p_in;
-                const int t = r - b * p.p_in;
-                const bool ok = (r < p.M) && (t < p.t_valid);
-                if (ok) valid_c |= 1u << i;
-                row_off_c[i] = ok ? (unsigned)(((long long)b * p.p_out + t + p.row_off) * p.ldo) : 0u;
-                t_c[i] = ok ? t : 0;
-            }
-            // this thread's own accumulator row (used by the transposed V store of the QKV epilogue)
-            const int r_own = rbase + lane;
+            // this thread's accumulator row -> output row
+            const int r_own = m0 + quarter * 32 + lane;
             const int b_own = r_own / p.p_in;
             const int t_own = r_own - b_own * p.p_in;
             const bool valid_own = (r_own < p.M) && (t_own < p.t_valid);
+            const long long orow = valid_own ? ((long long)b_own * p.p_out + t_own + p.row_off) : 0;
+            const long long obase = orow * p.ldo;                 // element offset of the row start (rows never written: row 0, loads stay in bounds)
 
-            // LayerNorm fold, consuming side: mean / rstd of this thread's own row from the producer's partials, then
-            // handed to the coalesced layout (rows 4 i + sub_row) by shuffles -- once per tile
-            constexpr bool kLn = (EPI == EPI_LN_GELU_BF16 || EPI == EPI_LN_QKV_SPLIT_BF16);
-            constexpr bool kQkv = (EPI == EPI_QKV_SPLIT_BF16 || EPI == EPI_LN_QKV_SPLIT_BF16);
-            constexpr bool kGelu = (EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_GELU_POS_F16 || EPI == EPI_LN_GELU_BF16);
-            float mean_own = 0.0f, rstd_own = 1.0f;
-            float nmean_c[8], rstd_c[8];                      // (-rstd mean, rstd) of rows 4 i + sub_row
-            if (kLn) {
-                if (r_own < p.M) {
-                    const float2* st = p.stats_in + (long long)r_own * p.stats_parts;
-                    float s1 = 0.0f, s2 = 0.0f;
-                    for (int k = 0; k < p.stats_parts; ++k) {
-                        const float2 v = __ldg(st + k);
-                        s1 += v.x;
-                        s2 += v.y;
-                    }
-                    const float inv_d = 1.0f / (float)p.ln_dim;
-                    mean_own = s1 * inv_d;
-                    rstd_own = rsqrtf(fmaxf(s2 * inv_d - mean_own * mean_own, 0.0f) + p.ln_eps);
+            // LayerNorm fold, consuming side: (-rstd mean, rstd) of the own row from the producer's partials, once per tile
+            float nmr = 0.0f, rstd = 1.0f;
+            if (kLn && r_own < p.M) {
+                const float2* st = p.stats_in + (long long)r_own * p.stats_parts;
+                float s1 = 0.0f, s2 = 0.0f;
+                for (int k = 0; k < p.stats_parts; ++k) {
+                    const float2 v = __ldg(st + k);
+                    s1 += v.x;
+                    s2 += v.y;
                 }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    nmean_c[i] = __shfl_sync(0xffffffffu, -mean_own * rstd_own, 4 * i + sub_row);
-                    rstd_c[i] = __shfl_sync(0xffffffffu, rstd_own, 4 * i + sub_row);
-                }
+                const float inv_d = 1.0f / (float)p.ln_dim;
+                const float mean = s1 * inv_d;
+                rstd = rsqrtf(fmaxf(s2 * inv_d - mean * mean, 0.0f) + p.ln_eps);
+                nmr = -mean * rstd;
             }
-            // LayerNorm fold, producing side: (sum, sum of squares) of what this warp stores, per row of the coalesced layout
-            constexpr bool kMayProduce = (EPI == EPI_BIAS_RESID_F16 || EPI == EPI_BIAS_GELU_POS_F16);
-            const bool produce = kMayProduce && p.stats_out != nullptr;
-            float st_s[8], st_q[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) st_s[i] = st_q[i] = 0.0f;
+            // LayerNorm fold, producing side: (sum, sum of squares) of what this thread stores of its row
+            const bool produce = (kResid || kPos) && p.stats_out != nullptr;
+            float st_s = 0.0f, st_q = 0.0f;
 
-            // residual / position rows do not depend on the accumulator: fetch chunk 0's before waiting for the MMA
-            // and chunk c+1's while chunk c is transposed, so their DRAM latency is off the critical path
-            constexpr bool kHasAdd = (EPI == EPI_BIAS_RESID_F16 || EPI == EPI_BIAS_GELU_POS_F16);
-            float4 add[2][8];
-            auto load_add = [&](int c, float4 (&dst)[8]) {
+            // the residual / position values do not depend on the accumulator: chunk 0's are fetched before waiting for
+            // the MMA and chunk c + 1's while chunk c is processed, so their DRAM latency is off the critical path
+            uint32_t addr[2][kPos ? 32 : 16];
+            auto load_add = [&](int c, uint32_t (&dst)[kPos ? 32 : 16]) {
                 const int nc = n0 + c * 32;
-                if (EPI == EPI_BIAS_RESID_F16) {
+                if (kResid) {
+                    const __half* src = reinterpret_cast<const __half*>(p.resid) + obase + nc;
+                    ldg256(src, dst[0], dst[1], dst[2], dst[3], dst[4], dst[5], dst[6], dst[7]);
+                    ldg256(src + 16, dst[8], dst[9], dst[10], dst[11], dst[12], dst[13], dst[14], dst[15]);
+                } else if (kPos) {
+                    const float* src = p.pos + (long long)(valid_own ? t_own : 0) * p.N + nc;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const uint2 h4 = *reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(p.resid) +
-                                                                         row_off_c[i] + nc + 4 * c4);
-                        const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&h4.x));
-                        const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&h4.y));
-                        dst[i] = make_float4(lo.x, lo.y, hi.x, hi.y);
-                    }
-                } else if (EPI == EPI_BIAS_GELU_POS_F16) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        dst[i] = __ldg(reinterpret_cast<const float4*>(p.pos + (long long)t_c[i] * p.N + nc) + c4);
+                    for (int q = 0; q < 4; ++q)
+                        ldg256_nc(src + 8 * q, dst[8 * q + 0], dst[8 * q + 1], dst[8 * q + 2], dst[8 * q + 3], dst[8 * q + 4],
+                                  dst[8 * q + 5], dst[8 * q + 6], dst[8 * q + 7]);
                 }
             };
-            if (kHasAdd) load_add(0, add[0]);
+            if (kResid || kPos) load_add(0, addr[0]);
 
+            const bool etr = p.trace != nullptr && blockIdx.x == 0 && ew == 0 && lane == 0 && it < p.trace_tiles;
+            if (etr) p.trace[it * 8 + 4] = clock64();
             mbar_wait(&tfull_bar[as], aphase);
             tc_fence_after();
+            if (etr) p.trace[it * 8 + 5] = clock64();
 #pragma unroll
             for (int c = 0; c < kChunks; ++c) {
                 uint32_t acc[32];
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN + half * (BN / 2) + c * 32;
                 tmem_ld_32x32b_x32(taddr, acc);
-                tmem_ld_wait_on(acc);
                 const int nc = n0 + c * 32;
+                const float4* bias4 = reinterpret_cast<const float4*>(p.bias + nc);
+                // the per-column vectors (warp-uniform addresses: one broadcast sector each) are fetched while the
+                // tcgen05.ld is in flight -- behind the wait their L1 latency would sit on every chunk's critical path
+                float4 bbv[8], ccv[kLn ? 8 : 1];
+                const bool v_part = kQkv && nc >= p.n_split;
+                if (!v_part) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        bbv[j] = __ldg(bias4 + j);
+                        if (kLn) ccv[j] = __ldg(reinterpret_cast<const float4*>(p.c1 + nc) + j);
+                    }
+                }
+                tmem_ld_wait_on(acc);
                 if (kQkv && nc >= p.n_split) {
                     // values: out2[b][head][c][t]; for a fixed column the warp's 32 rows are 32 consecutive t
                     if (valid_own) {
-                        const float4* bias4 = reinterpret_cast<const float4*>(p.bias + nc);
                         __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(p.out2) +
                                             ((long long)b_own * (p.N - p.n_split) + (nc - p.n_split)) * p.t_pad + t_own;
 #pragma unroll
@@ -285,102 +280,83 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                                                     __uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3]));
                             if (kLn) {
                                 const float4 cc = __ldg(reinterpret_cast<const float4*>(p.c1 + nc) + j);
-                                a4.x = fmaf(-mean_own, cc.x, a4.x) * rstd_own;
-                                a4.y = fmaf(-mean_own, cc.y, a4.y) * rstd_own;
-                                a4.z = fmaf(-mean_own, cc.z, a4.z) * rstd_own;
-                                a4.w = fmaf(-mean_own, cc.w, a4.w) * rstd_own;
+                                a4.x = fmaf(rstd, a4.x, fmaf(nmr, cc.x, bb.x));
+                                a4.y = fmaf(rstd, a4.y, fmaf(nmr, cc.y, bb.y));
+                                a4.z = fmaf(rstd, a4.z, fmaf(nmr, cc.z, bb.z));
+                                a4.w = fmaf(rstd, a4.w, fmaf(nmr, cc.w, bb.w));
+                            } else {
+                                a4.x += bb.x; a4.y += bb.y; a4.z += bb.z; a4.w += bb.w;
                             }
-                            o2[(long long)(4 * j + 0) * p.t_pad] = __float2bfloat16_rn(a4.x + bb.x);
-                            o2[(long long)(4 * j + 1) * p.t_pad] = __float2bfloat16_rn(a4.y + bb.y);
-                            o2[(long long)(4 * j + 2) * p.t_pad] = __float2bfloat16_rn(a4.z + bb.z);
-                            o2[(long long)(4 * j + 3) * p.t_pad] = __float2bfloat16_rn(a4.w + bb.w);
+                            o2[(long long)(4 * j + 0) * p.t_pad] = __float2bfloat16_rn(a4.x);
+                            o2[(long long)(4 * j + 1) * p.t_pad] = __float2bfloat16_rn(a4.y);
+                            o2[(long long)(4 * j + 2) * p.t_pad] = __float2bfloat16_rn(a4.z);
+                            o2[(long long)(4 * j + 3) * p.t_pad] = __float2bfloat16_rn(a4.w);
                         }
                     }
                     continue;
                 }
-                if (kHasAdd && c + 1 < kChunks) load_add(c + 1, add[(c + 1) & 1]);
-                // phase 1: own row -> staging, 16-byte column j stored at j ^ (row & 7)  (conflict-free both ways)
+                if ((kResid || kPos) && c + 1 < kChunks) load_add(c + 1, addr[(c + 1) & 1]);
+                uint32_t pk[16];
+                const float2 rs2 = make_float2(rstd, rstd), nm2 = make_float2(nmr, nmr);
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    stage[lane * 8 + (j ^ (lane & 7))] =
-                        make_float4(__uint_as_float(acc[4 * j + 0]), __uint_as_float(acc[4 * j + 1]),
-                                    __uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3]));
-                __syncwarp();
-                // phase 2: 8 lanes per row; bias / activation / residual applied on the way out.  The residual /
-                // position loads of all 8 rows are issued together, before anything depends on them.
-                const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + nc) + c4);
-                float4 cc = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (kLn) cc = __ldg(reinterpret_cast<const float4*>(p.c1 + nc) + c4);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int rl = 4 * i + sub_row;
-                    float4 v = stage[rl * 8 + (c4 ^ (rl & 7))];
+                for (int j = 0; j < 8; ++j) {
+                    const float4 bb = bbv[j];
+                    float2 lo = make_float2(__uint_as_float(acc[4 * j + 0]), __uint_as_float(acc[4 * j + 1]));
+                    float2 hi = make_float2(__uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3]));
                     if (kLn) {
                         // rstd acc + (c2 - rstd mean c1): two packed FMAs per pair, bias (= c2, in `bb`) included
-                        const float2 nm = make_float2(nmean_c[i], nmean_c[i]), rs = make_float2(rstd_c[i], rstd_c[i]);
-                        const float2 lo = __ffma2_rn(rs, make_float2(v.x, v.y),
-                                                     __ffma2_rn(nm, make_float2(cc.x, cc.y), make_float2(bb.x, bb.y)));
-                        const float2 hi = __ffma2_rn(rs, make_float2(v.z, v.w),
-                                                     __ffma2_rn(nm, make_float2(cc.z, cc.w), make_float2(bb.z, bb.w)));
-                        v = make_float4(lo.x, lo.y, hi.x, hi.y);
-                        if (kGelu) {
-                            const float2 g0 = gelu_poly2(lo), g1 = gelu_poly2(hi);
-                            v = make_float4(g0.x, g0.y, g1.x, g1.y);
-                        }
-                    } else if (kGelu) {
-                        const float2 lo = gelu_poly2(__fadd2_rn(make_float2(v.x, v.y), make_float2(bb.x, bb.y)));
-                        const float2 hi = gelu_poly2(__fadd2_rn(make_float2(v.z, v.w), make_float2(bb.z, bb.w)));
-                        v = make_float4(lo.x, lo.y, hi.x, hi.y);
+                        const float4 cc = ccv[j];
+                        lo = __ffma2_rn(rs2, lo, __ffma2_rn(nm2, make_float2(cc.x, cc.y), make_float2(bb.x, bb.y)));
+                        hi = __ffma2_rn(rs2, hi, __ffma2_rn(nm2, make_float2(cc.z, cc.w), make_float2(bb.z, bb.w)));
                     } else {
-                        v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+                        lo = __fadd2_rn(lo, make_float2(bb.x, bb.y));
+                        hi = __fadd2_rn(hi, make_float2(bb.z, bb.w));
                     }
-                    const bool ok = (valid_c >> i) & 1u;
-                    const unsigned off = row_off_c[i] + nc + 4 * c4;
-                    if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || kQkv || kLn) {
-                        uint2 q;
-                        q.x = pack_bf16x2(v.x, v.y);
-                        q.y = pack_bf16x2(v.z, v.w);
-                        if (ok) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off) = q;
+                    if (kGelu) {
+                        lo = gelu_poly2(lo);
+                        hi = gelu_poly2(hi);
+                    }
+                    if (!kF16Out) {
+                        pk[2 * j] = pack_bf16x2(lo.x, lo.y);
+                        pk[2 * j + 1] = pack_bf16x2(hi.x, hi.y);
                     } else {
+                        float a0, a1, a2, a3;
+                        if (kResid) {
+                            const float2 x0 = __half22float2(*reinterpret_cast<const __half2*>(&addr[c & 1][2 * j]));
+                            const float2 x1 = __half22float2(*reinterpret_cast<const __half2*>(&addr[c & 1][2 * j + 1]));
+                            a0 = x0.x; a1 = x0.y; a2 = x1.x; a3 = x1.y;
+                        } else {
+                            a0 = __uint_as_float(addr[c & 1][4 * j + 0]); a1 = __uint_as_float(addr[c & 1][4 * j + 1]);
+                            a2 = __uint_as_float(addr[c & 1][4 * j + 2]); a3 = __uint_as_float(addr[c & 1][4 * j + 3]);
+                        }
                         // residual stream in f16 (as CTranslate2's float16 mode keeps it): saturate instead of inf
                         const float kMaxHalf = 65504.0f;
-                        const float r0 = fminf(fmaxf(v.x + add[c & 1][i].x, -kMaxHalf), kMaxHalf);
-                        const float r1 = fminf(fmaxf(v.y + add[c & 1][i].y, -kMaxHalf), kMaxHalf);
-                        const float r2 = fminf(fmaxf(v.z + add[c & 1][i].z, -kMaxHalf), kMaxHalf);
-                        const float r3 = fminf(fmaxf(v.w + add[c & 1][i].w, -kMaxHalf), kMaxHalf);
-                        const __half2 lo = __floats2half2_rn(r0, r1), hi = __floats2half2_rn(r2, r3);
-                        uint2 q;
-                        q.x = *reinterpret_cast<const unsigned*>(&lo);
-                        q.y = *reinterpret_cast<const unsigned*>(&hi);
-                        if (ok) *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.out) + off) = q;
-                        if (kMayProduce) {
-                            st_s[i] += (r0 + r1) + (r2 + r3);
-                            st_q[i] = fmaf(r0, r0, fmaf(r1, r1, fmaf(r2, r2, fmaf(r3, r3, st_q[i]))));
-                        }
+                        const float r0 = fminf(fmaxf(lo.x + a0, -kMaxHalf), kMaxHalf);
+                        const float r1 = fminf(fmaxf(lo.y + a1, -kMaxHalf), kMaxHalf);
+                        const float r2 = fminf(fmaxf(hi.x + a2, -kMaxHalf), kMaxHalf);
+                        const float r3 = fminf(fmaxf(hi.y + a3, -kMaxHalf), kMaxHalf);
+                        const __half2 h0 = __floats2half2_rn(r0, r1), h1 = __floats2half2_rn(r2, r3);
+                        pk[2 * j] = *reinterpret_cast<const unsigned*>(&h0);
+                        pk[2 * j + 1] = *reinterpret_cast<const unsigned*>(&h1);
+                        st_s += (r0 + r1) + (r2 + r3);
+                        st_q = fmaf(r0, r0, fmaf(r1, r1, fmaf(r2, r2, fmaf(r3, r3, st_q))));
                     }
                 }
-                __syncwarp();
+                if (valid_own) {
+                    uint16_t* dst = reinterpret_cast<uint16_t*>(p.out) + obase + nc;
+                    stg256(dst, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
+                    stg256(dst + 16, pk[8], pk[9], pk[10], pk[11], pk[12], pk[13], pk[14], pk[15]);
+                }
             }
-            if (produce) {
-                // the 8 lanes of a row hold partials of this warp's BN / 2 columns: reduce, lane c4 == 0 writes the slice
+            if (produce && valid_own) {
+                // this thread owns BN / 2 columns of its row: one (sum, sum of squares) slice, no cross-lane reduction
                 const int parts = p.N / (BN / 2);
                 const int slice = (tile % num_n) * 2 + half;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    float a = st_s[i], b = st_q[i];
-#pragma unroll
-                    for (int o = 1; o < 8; o <<= 1) {
-                        a += __shfl_xor_sync(0xffffffffu, a, o);
-                        b += __shfl_xor_sync(0xffffffffu, b, o);
-                    }
-                    if (c4 == 0 && ((valid_c >> i) & 1u)) {
-                        const long long orow = (long long)(row_off_c[i] / (unsigned)p.ldo);
-                        p.stats_out[orow * parts + slice] = make_float2(a, b);
-                    }
-                }
+                p.stats_out[orow * parts + slice] = make_float2(st_s, st_q);
             }
             tc_fence_before();
             __syncwarp();
+            if (etr) p.trace[it * 8 + 6] = clock64();
             if (lane == 0) {
                 if (CG == 2) mbar_arrive_rank0(&tempty_bar[as]);
                 else mbar_arrive(&tempty_bar[as]);

@@ -298,6 +298,27 @@ __device__ __forceinline__ void tmem_st_wait() {
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
+// 256-bit global accesses (sm_100): one full 32-byte sector per thread and instruction.
+__device__ __forceinline__ void stg256(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f,
+                                       uint32_t g, uint32_t h) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e),
+                 "r"(f), "r"(g), "r"(h)
+                 : "memory");
+}
+__device__ __forceinline__ void ldg256(const void* p, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d, uint32_t& e,
+                                       uint32_t& f, uint32_t& g, uint32_t& h) {
+    asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(a), "=r"(b), "=r"(c), "=r"(d), "=r"(e), "=r"(f), "=r"(g), "=r"(h)
+                 : "l"(p)
+                 : "memory");
+}
+__device__ __forceinline__ void ldg256_nc(const void* p, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d, uint32_t& e,
+                                          uint32_t& f, uint32_t& g, uint32_t& h) {
+    asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(a), "=r"(b), "=r"(c), "=r"(d), "=r"(e), "=r"(f), "=r"(g), "=r"(h)
+                 : "l"(p));
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
