@@ -140,6 +140,11 @@ cudaError_t encoder_plan_create(int device, int sm_count, const EncoderShapeC& c
                "n_ctx 1500)";
         return cudaErrorInvalidValue;
     }
+    if (gemm_stats_parts(d) > 16) {
+        *why = "unsupported d_model: the LayerNorm hand-over between the GEMMs carries at most 16 column slices per row "
+               "(d_model a multiple of 256 up to 2048, or of 128 up to 1024)";
+        return cudaErrorInvalidValue;
+    }
     std::map<std::string, const WeightView*> by_name;
     for (int i = 0; i < n_weights; ++i) by_name[weights[i].name] = &weights[i];
     auto need = [&](const std::string& name, std::initializer_list<long long> shape) -> const float* {

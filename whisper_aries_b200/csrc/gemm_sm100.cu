@@ -43,8 +43,13 @@ struct Cfg {
     static constexpr int kABytes = BM * BK * 2;
     static constexpr int kBBytes = (BN / CG) * BK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kBarBytes = 256;
-    static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;   // +1024: alignment
+    static constexpr int kBarBytes = 192;                              // 2 * stages + 4 mbarriers, the TMEM slot
+    static constexpr int kVecBytes = 2 * BN * 4;                       // the tile's per-column vectors (bias | c1), f32
+    static constexpr int kUsedBytes = kStages * kStageBytes + kBarBytes + kVecBytes;
+    // + slack for aligning the operand ring to 1024 B (the dynamic segment is 1024-aligned in practice; the kernel traps
+    // if the slack does not suffice rather than overrunning): everything that is left below the 227 KB limit
+    static constexpr int kSmemBytes = (kUsedBytes + 1024 <= 232448) ? kUsedBytes + 1024 : 232448;
+    static_assert(kUsedBytes + 512 <= 232448, "shared memory budget");
     static constexpr uint32_t kTmemCols = 2 * BN;
 };
 
@@ -57,6 +62,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+    float* vec = reinterpret_cast<float*>(smem + C::kStages * C::kStageBytes + C::kBarBytes);   // [2][BN]: bias | c1 of the tile
+    if ((base - smem_u32(smem_raw)) + C::kUsedBytes > (uint32_t)C::kSmemBytes) __trap();       // alignment slack exhausted
     uint64_t* empty_bar = full_bar + C::kStages;
     uint64_t* tfull_bar = empty_bar + C::kStages;      // [2] accumulator ready
     uint64_t* tempty_bar = tfull_bar + 2;              // [2] accumulator drained
@@ -97,33 +104,38 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
-            // ------------------------------------------------------------ TMA producer
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
-                const int m0 = (tile / num_n) * (BM * CG) + cta_rank * BM;
-                const int n0 = (tile % num_n) * BN;
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    uint8_t* sa = smem + stage * C::kStageBytes;
-                    uint8_t* sb = sa + C::kABytes;
-                    const int kk = kb * BK;
-                    const int roff = kk / p.a_cols;
-                    if (CG == 2) {
-                        // both CTAs' bytes are counted on rank 0's barrier, which rank 0 arms for the pair
-                        if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * C::kStageBytes);
-                        tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], kk - roff * p.a_cols, m0 + roff);
-                        tma_load_2d_pair(sb, &tmap_b, &full_bar[stage], kk, n0 + cta_rank * kBBoxRows);
-                    } else {
-                        mbar_expect_tx(&full_bar[stage], C::kStageBytes);
-                        tma_load_2d(sa, &tmap_a, &full_bar[stage], kk - roff * p.a_cols, m0 + roff);
+        // ------------------------------------------------------------ TMA producer (the whole warp, convergent: ptx.cuh)
+        // A K block must be refilled within (stages - 1) MMA groups of its slot being freed, and this warp shares its
+        // scheduler with two epilogue warps: the loop below is ~20 instructions per K block, no division, no MUFU.
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+            const int m0 = (tile / num_n) * (BM * CG) + cta_rank * BM;
+            const int n0 = (tile % num_n) * BN;
+            int acol = 0, arow = m0;                       // K index kk reads A at (row + kk / a_cols, kk % a_cols)
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* sa = smem + stage * C::kStageBytes;
+                uint8_t* sb = sa + C::kABytes;
+                const int kk = kb * BK;
+                if (CG == 2) {
+                    // both CTAs' bytes are counted on rank 0's barrier, which rank 0 arms for the pair
+                    if (cta_rank == 0) mbar_expect_tx_elect(&full_bar[stage], 2 * C::kStageBytes);
+                    tma_load_2d_pair_elect(sa, &tmap_a, &full_bar[stage], acol, arow);
+                    tma_load_2d_pair_elect(sb, &tmap_b, &full_bar[stage], kk, n0 + cta_rank * kBBoxRows);
+                } else {
+                    mbar_expect_tx_elect(&full_bar[stage], C::kStageBytes);
+                    tma_load_2d_elect(sa, &tmap_a, &full_bar[stage], acol, arow);
 #pragma unroll
-                        for (int h = 0; h < BN / kBBoxRows; ++h)
-                            tma_load_2d(sb + h * kBBoxRows * BK * 2, &tmap_b, &full_bar[stage], kk, n0 + h * kBBoxRows);
-                    }
-                    if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                    for (int h = 0; h < BN / kBBoxRows; ++h)
+                        tma_load_2d_elect(sb + h * kBBoxRows * BK * 2, &tmap_b, &full_bar[stage], kk, n0 + h * kBBoxRows);
                 }
+                acol += BK;
+                if (acol == p.a_cols) {
+                    acol = 0;
+                    ++arow;
+                }
+                if (++stage == C::kStages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
@@ -192,12 +204,55 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         constexpr bool kResid = (EPI == EPI_BIAS_RESID_F16);
         constexpr bool kPos = (EPI == EPI_BIAS_GELU_POS_F16);
         constexpr bool kF16Out = kResid || kPos;
+        // Per-tile inputs that do not depend on the accumulator are fetched ONE TILE AHEAD, so that their L2 latency hides
+        // under the previous tile's drain instead of opening every tile (round-2 timeline: ~2700 of fc1's ~11300 cycles
+        // per tile): the row's LayerNorm partials (registers -> -rstd mean, rstd) and the tile's bias / c1 values (one
+        // register each, parked in shared memory at the next tile's start).
+        const int e_idx = threadIdx.x - 64;                              // 0 .. 255 among the epilogue threads
+        auto row_of = [&](int tile) { return (tile / num_n) * (BM * CG) + cta_rank * BM + quarter * 32 + lane; };
+        constexpr int kMaxParts = 16;
+        float2 pvn[kLn ? kMaxParts : 1];
+        auto stats_issue = [&](int tile) {                                   // loads only; consumed by stats_finish
+            const int r = row_of(tile);
+#pragma unroll
+            for (int k = 0; k < kMaxParts; ++k)
+                if (kLn) pvn[k] = (k < p.stats_parts && r < p.M) ? __ldg(p.stats_in + (long long)r * p.stats_parts + k)
+                                                                 : make_float2(0.f, 0.f);
+        };
+        auto stats_finish = [&](float& nmr_out, float& rstd_out) {
+            float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+            for (int k = 0; k < kMaxParts; ++k) {
+                if (kLn) {
+                    s1 += pvn[k].x;
+                    s2 += pvn[k].y;
+                }
+            }
+            const float inv_d = 1.0f / (float)p.ln_dim;
+            const float mean = s1 * inv_d;
+            rstd_out = rsqrtf(fmaxf(s2 * inv_d - mean * mean, 0.0f) + p.ln_eps);
+            nmr_out = -mean * rstd_out;
+        };
+        float nmr = 0.0f, rstd = 1.0f;
+        float vb_next = 0.0f, vc_next = 0.0f;
+        if (first_tile < num_tiles) {
+            if (kLn) {
+                stats_issue(first_tile);
+                stats_finish(nmr, rstd);
+            }
+            if (e_idx < BN) {
+                vb_next = __ldg(p.bias + (first_tile % num_n) * BN + e_idx);
+                if (kLn) vc_next = __ldg(p.c1 + (first_tile % num_n) * BN + e_idx);
+            }
+        }
         int it = 0;
         for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
             const int m0 = (tile / num_n) * (BM * CG) + cta_rank * BM;
             const int n0 = (tile % num_n) * BN + half * (BN / 2);
+            const int next_tile = tile + tile_step;
+            const bool has_next = next_tile < num_tiles;
             // this thread's accumulator row -> output row
             const int r_own = m0 + quarter * 32 + lane;
             const int b_own = r_own / p.p_in;
@@ -206,21 +261,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             const long long orow = valid_own ? ((long long)b_own * p.p_out + t_own + p.row_off) : 0;
             const long long obase = orow * p.ldo;                 // element offset of the row start (rows never written: row 0, loads stay in bounds)
 
-            // LayerNorm fold, consuming side: (-rstd mean, rstd) of the own row from the producer's partials, once per tile
-            float nmr = 0.0f, rstd = 1.0f;
-            if (kLn && r_own < p.M) {
-                const float2* st = p.stats_in + (long long)r_own * p.stats_parts;
-                float s1 = 0.0f, s2 = 0.0f;
-                for (int k = 0; k < p.stats_parts; ++k) {
-                    const float2 v = __ldg(st + k);
-                    s1 += v.x;
-                    s2 += v.y;
-                }
-                const float inv_d = 1.0f / (float)p.ln_dim;
-                const float mean = s1 * inv_d;
-                rstd = rsqrtf(fmaxf(s2 * inv_d - mean * mean, 0.0f) + p.ln_eps);
-                nmr = -mean * rstd;
-            }
+            // LayerNorm fold, consuming side: (nmr, rstd) = (-rstd mean, rstd) of the own row were prepared one tile ahead
             // LayerNorm fold, producing side: (sum, sum of squares) of what this thread stores of its row
             const bool produce = (kResid || kPos) && p.stats_out != nullptr;
             float st_s = 0.0f, st_q = 0.0f;
@@ -244,29 +285,37 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             };
             if (kResid || kPos) load_add(0, addr[0]);
 
+            // the tile's per-column vectors go through shared memory: 256 epilogue threads hold one bias (and c1) value each,
+            // fetched coalesced during the PREVIOUS tile; the chunk loop reads them as broadcast LDS.128.  (Fetched with
+            // warp-uniform __ldg per chunk they missed the ~25 KB of L1 left beside 227 KB of shared memory and their L2
+            // latency sat on every chunk's critical path: 16 % of fc1's samples in round 2.)
+            asm volatile("bar.sync 1, 256;" ::: "memory");                   // every warp is done with the previous tile's vectors
+            if (e_idx < BN) {
+                vec[e_idx] = vb_next;
+                if (kLn) vec[BN + e_idx] = vc_next;
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (has_next && e_idx < BN) {
+                vb_next = __ldg(p.bias + (next_tile % num_n) * BN + e_idx);
+                if (kLn) vc_next = __ldg(p.c1 + (next_tile % num_n) * BN + e_idx);
+            }
+            const float4* vbias = reinterpret_cast<const float4*>(vec + half * (BN / 2));
+            const float4* vc1 = reinterpret_cast<const float4*>(vec + BN + half * (BN / 2));
+
             const bool etr = p.trace != nullptr && blockIdx.x == 0 && ew == 0 && lane == 0 && it < p.trace_tiles;
             if (etr) p.trace[it * 8 + 4] = clock64();
             mbar_wait(&tfull_bar[as], aphase);
             tc_fence_after();
             if (etr) p.trace[it * 8 + 5] = clock64();
+            if (kLn && has_next) stats_issue(next_tile);
 #pragma unroll
             for (int c = 0; c < kChunks; ++c) {
                 uint32_t acc[32];
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN + half * (BN / 2) + c * 32;
                 tmem_ld_32x32b_x32(taddr, acc);
                 const int nc = n0 + c * 32;
-                const float4* bias4 = reinterpret_cast<const float4*>(p.bias + nc);
-                // the per-column vectors (warp-uniform addresses: one broadcast sector each) are fetched while the
-                // tcgen05.ld is in flight -- behind the wait their L1 latency would sit on every chunk's critical path
-                float4 bbv[8], ccv[kLn ? 8 : 1];
-                const bool v_part = kQkv && nc >= p.n_split;
-                if (!v_part) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        bbv[j] = __ldg(bias4 + j);
-                        if (kLn) ccv[j] = __ldg(reinterpret_cast<const float4*>(p.c1 + nc) + j);
-                    }
-                }
+                const float4* bias4 = vbias + c * 8;                     // shared memory, broadcast reads
+                const float4* c1_4 = vc1 + c * 8;
                 tmem_ld_wait_on(acc);
                 if (kQkv && nc >= p.n_split) {
                     // values: out2[b][head][c][t]; for a fixed column the warp's 32 rows are 32 consecutive t
@@ -275,11 +324,11 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                                             ((long long)b_own * (p.N - p.n_split) + (nc - p.n_split)) * p.t_pad + t_own;
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            const float4 bb = __ldg(bias4 + j);
+                            const float4 bb = bias4[j];
                             float4 a4 = make_float4(__uint_as_float(acc[4 * j + 0]), __uint_as_float(acc[4 * j + 1]),
                                                     __uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3]));
                             if (kLn) {
-                                const float4 cc = __ldg(reinterpret_cast<const float4*>(p.c1 + nc) + j);
+                                const float4 cc = c1_4[j];
                                 a4.x = fmaf(rstd, a4.x, fmaf(nmr, cc.x, bb.x));
                                 a4.y = fmaf(rstd, a4.y, fmaf(nmr, cc.y, bb.y));
                                 a4.z = fmaf(rstd, a4.z, fmaf(nmr, cc.z, bb.z));
@@ -300,12 +349,12 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 const float2 rs2 = make_float2(rstd, rstd), nm2 = make_float2(nmr, nmr);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float4 bb = bbv[j];
+                    const float4 bb = bias4[j];
                     float2 lo = make_float2(__uint_as_float(acc[4 * j + 0]), __uint_as_float(acc[4 * j + 1]));
                     float2 hi = make_float2(__uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3]));
                     if (kLn) {
                         // rstd acc + (c2 - rstd mean c1): two packed FMAs per pair, bias (= c2, in `bb`) included
-                        const float4 cc = ccv[j];
+                        const float4 cc = c1_4[j];
                         lo = __ffma2_rn(rs2, lo, __ffma2_rn(nm2, make_float2(cc.x, cc.y), make_float2(bb.x, bb.y)));
                         hi = __ffma2_rn(rs2, hi, __ffma2_rn(nm2, make_float2(cc.z, cc.w), make_float2(bb.z, bb.w)));
                     } else {
@@ -348,6 +397,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     stg256(dst + 16, pk[8], pk[9], pk[10], pk[11], pk[12], pk[13], pk[14], pk[15]);
                 }
             }
+            if (kLn && has_next) stats_finish(nmr, rstd);                   // for the next tile
             if (produce && valid_own) {
                 // this thread owns BN / 2 columns of its row: one (sum, sum of squares) slice, no cross-lane reduction
                 const int parts = p.N / (BN / 2);
@@ -464,7 +514,7 @@ cudaError_t gemm_launch(int epi, const CUtensorMap& ta, const CUtensorMap& tb, c
                         cudaStream_t stream) {
     if (p.K % BK != 0 || p.N % 128 != 0 || p.a_cols % BK != 0 || p.M <= 0) return cudaErrorInvalidValue;
     if ((epi == EPI_LN_GELU_BF16 || epi == EPI_LN_QKV_SPLIT_BF16) &&
-        (!p.stats_in || !p.c1 || p.stats_parts <= 0 || p.ln_dim <= 0))
+        (!p.stats_in || !p.c1 || p.stats_parts <= 0 || p.stats_parts > 16 || p.ln_dim <= 0))
         return cudaErrorInvalidValue;
     return gemm_block_n(p.N) == 256 ? launch_bn<256>(epi, ta, tb, p, sm_count, stream)
                                     : launch_bn<128>(epi, ta, tb, p, sm_count, stream);
