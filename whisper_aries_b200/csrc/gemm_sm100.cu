@@ -268,7 +268,11 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 
             // the residual / position values do not depend on the accumulator: chunk 0's are fetched before waiting for
             // the MMA and chunk c + 1's while chunk c is processed, so their DRAM latency is off the critical path
-            uint32_t addr[2][kPos ? 32 : 16];
+            // (f16 residual: all of the tile's chunks are requested up front -- 64 registers -- so that the chunk loop holds
+            //  no global loads at all: with one chunk of lookahead the tcgen05.ld of the next chunk queued behind the
+            //  outstanding residual loads on the scoreboard, 19 % of the out-projection's samples in round 2)
+            constexpr int kAddBufs = kResid ? kChunks : 2;
+            uint32_t addr[kAddBufs][kPos ? 32 : 16];
             auto load_add = [&](int c, uint32_t (&dst)[kPos ? 32 : 16]) {
                 const int nc = n0 + c * 32;
                 if (kResid) {
@@ -283,7 +287,12 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                                   dst[8 * q + 5], dst[8 * q + 6], dst[8 * q + 7]);
                 }
             };
-            if (kResid || kPos) load_add(0, addr[0]);
+            if (kResid) {
+#pragma unroll
+                for (int c = 0; c < kChunks; ++c) load_add(c, addr[c]);
+            } else if (kPos) {
+                load_add(0, addr[0]);
+            }
 
             // the tile's per-column vectors go through shared memory: 256 epilogue threads hold one bias (and c1) value each,
             // fetched coalesced during the PREVIOUS tile; the chunk loop reads them as broadcast LDS.128.  (Fetched with
@@ -316,6 +325,11 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 const int nc = n0 + c * 32;
                 const float4* bias4 = vbias + c * 8;                     // shared memory, broadcast reads
                 const float4* c1_4 = vc1 + c * 8;
+                float4 bbv[kLn ? 1 : 8];                                  // (non-LN kernels have the registers to read the
+                if (!kLn) {                                               //  bias under the tcgen05.ld's latency)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) bbv[j] = bias4[j];
+                }
                 tmem_ld_wait_on(acc);
                 if (kQkv && nc >= p.n_split) {
                     // values: out2[b][head][c][t]; for a fixed column the warp's 32 rows are 32 consecutive t
@@ -344,12 +358,12 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     }
                     continue;
                 }
-                if ((kResid || kPos) && c + 1 < kChunks) load_add(c + 1, addr[(c + 1) & 1]);
+                if (kPos && c + 1 < kChunks) load_add(c + 1, addr[(c + 1) & 1]);
                 uint32_t pk[16];
                 const float2 rs2 = make_float2(rstd, rstd), nm2 = make_float2(nmr, nmr);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float4 bb = bias4[j];
+                    const float4 bb = kLn ? bias4[j] : bbv[kLn ? 0 : j];
                     float2 lo = make_float2(__uint_as_float(acc[4 * j + 0]), __uint_as_float(acc[4 * j + 1]));
                     float2 hi = make_float2(__uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3]));
                     if (kLn) {
@@ -371,8 +385,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     } else {
                         float a0, a1, a2, a3;
                         if (kResid) {
-                            const float2 x0 = __half22float2(*reinterpret_cast<const __half2*>(&addr[c & 1][2 * j]));
-                            const float2 x1 = __half22float2(*reinterpret_cast<const __half2*>(&addr[c & 1][2 * j + 1]));
+                            const float2 x0 = __half22float2(*reinterpret_cast<const __half2*>(&addr[c][2 * j]));
+                            const float2 x1 = __half22float2(*reinterpret_cast<const __half2*>(&addr[c][2 * j + 1]));
                             a0 = x0.x; a1 = x0.y; a2 = x1.x; a3 = x1.y;
                         } else {
                             a0 = __uint_as_float(addr[c & 1][4 * j + 0]); a1 = __uint_as_float(addr[c & 1][4 * j + 1]);
