@@ -325,10 +325,16 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 const int nc = n0 + c * 32;
                 const float4* bias4 = vbias + c * 8;                     // shared memory, broadcast reads
                 const float4* c1_4 = vc1 + c * 8;
-                float4 bbv[kLn ? 1 : 8];                                  // (non-LN kernels have the registers to read the
-                if (!kLn) {                                               //  bias under the tcgen05.ld's latency)
+                // the chunk's bias (and c1) values are read under the tcgen05.ld's latency: left to ptxas the LDS sit right
+                // in front of their first use (short-scoreboard stalls: 24 % of fc1's samples in round 2); 320 threads per
+                // SM leave 204 registers per thread, so the 64 extra registers cost no occupancy
+                float4 bbv[8], ccv[kLn ? 8 : 1];
+                if (!(kQkv && nc >= p.n_split)) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) bbv[j] = bias4[j];
+                    for (int j = 0; j < 8; ++j) {
+                        bbv[j] = bias4[j];
+                        if (kLn) ccv[j] = c1_4[j];
+                    }
                 }
                 tmem_ld_wait_on(acc);
                 if (kQkv && nc >= p.n_split) {
@@ -363,12 +369,12 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 const float2 rs2 = make_float2(rstd, rstd), nm2 = make_float2(nmr, nmr);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float4 bb = kLn ? bias4[j] : bbv[kLn ? 0 : j];
+                    const float4 bb = bbv[j];
                     float2 lo = make_float2(__uint_as_float(acc[4 * j + 0]), __uint_as_float(acc[4 * j + 1]));
                     float2 hi = make_float2(__uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3]));
                     if (kLn) {
                         // rstd acc + (c2 - rstd mean c1): two packed FMAs per pair, bias (= c2, in `bb`) included
-                        const float4 cc = c1_4[j];
+                        const float4 cc = ccv[kLn ? j : 0];
                         lo = __ffma2_rn(rs2, lo, __ffma2_rn(nm2, make_float2(cc.x, cc.y), make_float2(bb.x, bb.y)));
                         hi = __ffma2_rn(rs2, hi, __ffma2_rn(nm2, make_float2(cc.z, cc.w), make_float2(bb.z, bb.w)));
                     } else {
