@@ -701,7 +701,9 @@ def main() -> int:
     gemm_launches = sum(prof[k][1] for k in gemm_classes)
     gemm_tflops = gemm_flops_per_step * args.steps / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     peak_tf = peaks["bf16_tflops_sustained"]
-    roofline = {"kernel": "gemm_bf16_tcgen05 (all GEMM launches of the step: conv stem, QKV, out-proj, fc1, fc2)",
+    roofline = {"kernel": "gemm_bf16_tcgen05 (all GEMM launches of the step: conv stem, QKV, out-proj, fc1, fc2; since round 2 "
+                          "these launches also carry the 64 in-layer LayerNorms -- statistics in the residual epilogues, "
+                          "normalisation in the QKV / fc1 epilogues -- which were 6.3 ms of separate kernels in BENCH_r01)",
                 "bound": "tensor", "achieved": gemm_tflops, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": gemm_tflops / peak_tf, "peak_source": f"{peaks['source']} (sustained bf16 GEMM)",
                 "flops_per_launch": gemm_flops_per_step * args.steps / max(gemm_launches, 1),
