@@ -224,3 +224,45 @@ def test_layernorm_folded_qkv_split(ctx):
     assert (qk.float() - ref[:, :2 * d]).abs().max().item() <= tol
     v = ref[:, 2 * d:].view(B, T, d // 64, 64).permute(0, 2, 3, 1)
     assert (vt[..., :T].float() - v).abs().max().item() <= tol
+
+
+def test_epilogues_write_only_their_rows_and_are_deterministic(ctx):
+    """The epilogues store with 256-bit accesses straight from the accumulator rows: rows past M (the last tile is partly
+    empty: M = 1000 is not a multiple of 128) must stay untouched in the output AND in the statistics, with guard zones
+    on both sides of every buffer, and two launches must give identical bytes."""
+    from whisper_aries_b200 import _lib
+    M, N, K, G = 1000, 1280, 1280, 64                      # G guard rows before and after
+    g = torch.Generator().manual_seed(77)
+    a = (torch.randn(M, K, generator=g) * 0.5).cuda().bfloat16()
+    b = (torch.randn(N, K, generator=g) * 0.05).cuda().bfloat16()
+    bias = torch.randn(N, generator=g).cuda()
+    resid_full = torch.full((M + 2 * G, N), 7.0, device="cuda", dtype=torch.float16)
+    resid_full[G:G + M] = torch.randn(M, N, generator=g).cuda().half()
+    parts = ctx.lib.aries_test_gemm_stats_parts(N)
+    runs = []
+    for _ in range(2):
+        out_full = resid_full.clone()                        # in place on the residual stream, as the encoder runs it
+        stats_full = torch.full((M + 2 * G, parts, 2), float("nan"), device="cuda")
+        out, stats = out_full[G:G + M], stats_full[G:G + M]
+        _lib.check(ctx.lib.aries_test_gemm_ln(ctx.handle, 2, M, N, K, ptr(a), ptr(b), ptr(bias), None, None, 0, 0, ptr(out),
+                                              ptr(out), None, 0, 0, 0, ptr(stats), None))
+        torch.cuda.synchronize()
+        assert (out_full[:G] == 7.0).all() and (out_full[G + M:] == 7.0).all()
+        assert torch.isnan(stats_full[:G]).all() and torch.isnan(stats_full[G + M:]).all() and torch.isfinite(stats).all()
+        runs.append((out.clone(), stats.clone()))
+    assert torch.equal(runs[0][0], runs[1][0]) and torch.equal(runs[0][1], runs[1][1])
+    ref = a.float() @ b.float().t() + bias + resid_full[G:G + M].float()
+    assert (runs[0][0].float() - ref).abs().max().item() <= 2e-3 + ref.abs().max().item() * 2 ** -10
+    # LayerNorm-folded consumer on the same ragged M, fed by those statistics
+    W = (torch.randn(N, K, generator=g) * 0.04).cuda()
+    Wf = W.half()
+    c1, c2 = Wf.float().sum(1).contiguous(), torch.zeros(N, device="cuda")
+    x = runs[0][0].contiguous()
+    o_full = torch.full((M + 2 * G, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    o = o_full[G:G + M]
+    _lib.check(ctx.lib.aries_test_gemm_ln(ctx.handle, 5, M, N, K, ptr(x), ptr(Wf), ptr(c2), ptr(c1), ptr(runs[0][1]), parts, K,
+                                          None, ptr(o), None, 0, 0, 0, None, None))
+    torch.cuda.synchronize()
+    assert torch.isnan(o_full[:G].float()).all() and torch.isnan(o_full[G + M:].float()).all()
+    want = torch.nn.functional.gelu(torch.nn.functional.layer_norm(x.float(), (K,), None, None, 1e-5) @ W.t())
+    assert (o.float() - want).abs().max().item() <= 4e-3 + want.abs().max().item() * 2 ** -7
