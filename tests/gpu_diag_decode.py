@@ -48,7 +48,7 @@ def err():
         print(name, "no_speech_prob", [r.no_speech_prob for r in res], [r["no_speech_prob"] for r in ref])
 
 
-def perf(batches):
+def perf(batches, modes=("graph+pdl", "graph", "stream+pdl", "stream"), stacks=("1",)):
     from whisper_aries_b200 import WhisperDecoder, synthetic
     shape = synthetic.DEC_SHAPES["large-v3"]
     tok = synthetic.WhisperTokens.for_vocab(shape.vocab)
@@ -63,7 +63,8 @@ def perf(batches):
     wbytes = (14 * shape.d_model ** 2 * shape.n_layers + shape.vocab * shape.d_model) * 2
     for B in batches:
         enc = torch.randn(B, shape.n_audio_ctx, shape.d_model, device="cuda").bfloat16()
-        for mode in ("graph+pdl", "graph", "stream+pdl", "stream"):
+        for mode, stack in [(m, s) for s in stacks for m in modes]:
+            os.environ["ARIES_DECODE_STACK"] = stack
             os.environ["ARIES_DECODE_GRAPH"] = "1" if mode.startswith("graph") else "0"
             os.environ["ARIES_DECODE_PDL"] = "1" if mode.endswith("pdl") else "0"
             L = 64 + len(prompt)
@@ -74,7 +75,7 @@ def perf(batches):
             kv = B * shape.n_layers * shape.n_audio_ctx * 2 * shape.d_model * 2
             self_kv = B * shape.n_layers * (L / 2) * 2 * shape.d_model * 2
             gbs = (wbytes + kv + self_kv) / ms / 1e6
-            print(f"B={B:3d} {mode:11s}: {ms:7.3f} ms/step ({st['kernels_per_step']} kernels, {ms * 1e3 / st['kernels_per_step']:.2f} us each) "
+            print(f"B={B:3d} {mode:11s} stack={stack}: {ms:7.3f} ms/step ({st['kernels_per_step']} kernels, {ms * 1e3 / st['kernels_per_step']:.2f} us each) "
                   f"{B / ms * 1e3:9.0f} tok/s  {gbs:7.0f} GB/s of {wbytes / 1e9:.2f}+{kv / 1e9:.2f} GB; cross-KV projection "
                   f"{st['cross_kv_ms']:.2f} ms", flush=True)
 
@@ -118,5 +119,8 @@ if __name__ == "__main__":
                 print(f"B={B} pdl mask {mask} (1 gemm, 2 attention, 4 rest): {st['decode_ms'] / st['steps']:.3f} ms/step", flush=True)
     elif what == "prof":
         prof(int(sys.argv[2]) if len(sys.argv) > 2 else 64)
+    elif what == "stack":
+        # persistent stack kernel (<= 8 windows) against the launch-per-op step, graph replay with programmatic launch
+        perf([int(a) for a in sys.argv[2:]] or [1, 2, 4, 8], modes=("graph+pdl",), stacks=("1", "0"))
     else:
         perf([int(a) for a in sys.argv[2:]] or [1, 8, 64])

@@ -406,6 +406,80 @@ def test_fused_and_unfused_layernorm_paths_agree(monkeypatch):
     assert [r.sequences_ids[0][:10] for r in outs["1"][0]] == [r.sequences_ids[0][:10] for r in outs["0"][0]]
 
 
+@pytest.mark.parametrize("shape_name,batch,seed", [("micro", 1, 32), ("micro", 8, 23), ("mini", 3, 35), ("mini", 5, 7)])
+def test_persistent_stack_agrees_with_the_launch_per_op_step(monkeypatch, shape_name, batch, seed):
+    """decode_stack_kernel (<= 8 windows, opt-in: ARIES_DECODE_STACK=1) against the launch-per-op step on the same decoder
+    object: not less accurate against the fp32 oracle, the same ids on the first decisions, 3 launches per token.
+    Batches 1 / 3 / 5 / 8 cover 8-, 4- and 1-way key splits of the attention phases."""
+    shape, tok, otok, enc, dec, oracle, wd = _setup(shape_name, batch, seed)
+    prompt = [tok.sot, tok.first_lang + 1, tok.transcribe]
+    L = len(prompt) + 12
+    outs = {}
+    for stack in ("1", "0"):
+        monkeypatch.setenv("ARIES_DECODE_STACK", stack)
+        res, extras = dec.generate(enc.cuda(), [prompt] * batch, max_length=L, suppress_tokens=[], _want_logits=True)
+        outs[stack] = (res, extras[0]["logits"], dec.last_stats()["kernels_per_step"])
+        res_g = dec.generate(enc.cuda(), [prompt] * batch, max_length=L, suppress_tokens=[])      # graph replay
+        assert [r.sequences_ids for r in res_g] == [r.sequences_ids for r in res]
+    assert outs["1"][2] == 3 and outs["0"][2] == 8 * shape.n_layers + 4
+    a, b = torch.from_numpy(outs["1"][1]), torch.from_numpy(outs["0"][1])               # [T, B, V]
+    assert torch.isfinite(a).all()
+    # both against the fp32 oracle on the ids the stack path produced: the persistent kernel may not be less accurate than
+    # the launch-per-op step ("mini" amplifies rounding differences, so the two are not compared with each other there)
+    ids = [r.sequences_ids[0] for r in outs["1"][0]]
+    if [r.sequences_ids[0] for r in outs["0"][0]] == ids:
+        n = min(len(i) for i in ids)
+        seqs = torch.tensor([prompt + i[:n] for i in ids])[:, :len(prompt) + n - 1] if n > 0 else torch.tensor([prompt] * batch)
+        ref = oracle.logits(seqs, enc.float()).transpose(0, 1)                          # [T, B, V]
+        T = ref.shape[0]
+        rms_stack = (a[:T] - ref).pow(2).mean().sqrt().item()
+        rms_perop = (b[:T] - ref).pow(2).mean().sqrt().item()
+        assert rms_stack <= 1.5 * rms_perop + 1e-3, (rms_stack, rms_perop)
+    if shape_name == "micro":
+        assert (a - b).abs().max().item() <= 0.02 * b.abs().max().item()
+        cos = torch.nn.functional.cosine_similarity(a.reshape(-1, a.shape[-1]), b.reshape(-1, b.shape[-1]), dim=-1)
+        assert cos.min().item() >= 0.9995, cos.min().item()
+    assert [r.sequences_ids[0][:6] for r in outs["1"][0]] == [r.sequences_ids[0][:6] for r in outs["0"][0]]
+
+
+def test_persistent_stack_odd_width_and_long_context(monkeypatch):
+    """The opt-in stack kernel on d_model = 192 / ffn = 320 (K tails: neither is a multiple of the 256-deep stage; 3 heads)
+    against the oracle, and on a decode to position 448 (self-attention key splits > 1 once the context exceeds 128)."""
+    from oracle import synth as osynth, whisper_decoder as wd
+    from whisper_aries_b200 import WhisperDecoder, synthetic
+    monkeypatch.setenv("ARIES_DECODE_STACK", "1")
+    shape = synthetic.DecoderShape("nano", 300, 192, 3, 2, 320)
+    oshape = osynth.DecoderShape("nano", 300, 192, 3, 2, 320)
+    tok = synthetic.WhisperTokens.for_vocab(shape.vocab)
+    dec = WhisperDecoder(shape, synthetic.decoder_weights(shape, 11), tokens=tok, device="cuda:0", max_batch=4)
+    oracle = wd.Decoder(osynth.decoder_weights(oshape, 11), oshape, round_weights_bf16=True)
+    enc = torch.randn(2, shape.n_audio_ctx, shape.d_model, generator=torch.Generator().manual_seed(2)).bfloat16()
+    prompt = [tok.sot, tok.first_lang, tok.transcribe, tok.no_timestamps]
+    forced = [[(7 * b + 3 * i) % 150 for i in range(8)] for b in range(2)]
+    L = len(prompt) + 8
+    res, extras = dec.generate(enc.cuda(), [prompt] * 2, max_length=L, suppress_tokens=[], _forced=forced, _want_logits=True)
+    assert dec.last_stats()["kernels_per_step"] == 3
+    ref = oracle.logits(torch.tensor([prompt + f for f in forced])[:, :L - 1], enc.float())
+    logits = torch.from_numpy(extras[0]["logits"]).transpose(0, 1)
+    cos = torch.nn.functional.cosine_similarity(logits.reshape(-1, shape.vocab), ref.reshape(-1, shape.vocab), dim=-1)
+    assert cos.min().item() >= 0.9995, cos.min().item()
+
+    shape, tok, otok, enc, dec, oracle, wd = _setup("micro", 2, 23)
+    prompt = [tok.sot, tok.first_lang, tok.transcribe, tok.no_timestamps]
+    L = shape.n_text_ctx
+    res = dec.generate(enc.cuda(), [prompt] * 2, max_length=L, suppress_tokens=[tok.eot])
+    assert dec.last_stats()["kernels_per_step"] == 3 and dec.last_stats()["steps"] == L - 1
+    forced = [r.sequences_ids[0] for r in res]
+    res2, extras = dec.generate(enc.cuda(), [prompt] * 2, max_length=L, suppress_tokens=[tok.eot], _forced=forced,
+                                _want_logits=True)
+    ref = oracle.logits(torch.tensor([prompt + f for f in forced])[:, :L - 1], enc.float())
+    logits = torch.from_numpy(extras[0]["logits"]).transpose(0, 1)
+    for t in (3, 127, 128, 129, 300, 446):
+        for b in range(2):
+            cos = torch.nn.functional.cosine_similarity(logits[b, t], ref[b, t], dim=0).item()
+            assert cos >= 0.9995, f"window {b} step {t}: logits cosine {cos}"
+
+
 def test_scheduler_transcribe_worker_returns_token_rows():
     """ChunkScheduler + gpu_transcribe_worker: PCM windows in, token rows out (prompt, sampled ids, EOT padding, count
     in column 0), in window order, equal to encode_audio + generate called directly; ragged last micro-batch."""

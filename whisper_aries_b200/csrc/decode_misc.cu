@@ -112,6 +112,7 @@ __global__ void __launch_bounds__(kSampleThreads) decode_sample_kernel(const Sam
     pdl_trigger();
     const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int kWarps = kSampleThreads / 32;
+    if (p.stack_bar != nullptr && b == 0 && tid == 0) *p.stack_bar = 0u;     // the stack kernel of this step has exited
     const int t = *p.step;
     const int pos = t + 1;
     const float* lg = p.logits + (size_t)b * p.logits_ld;

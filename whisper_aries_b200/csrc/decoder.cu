@@ -17,6 +17,7 @@
 #include <cuda_bf16.h>
 
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -49,11 +50,12 @@ bool env_on(const char* name, bool dflt) {
 struct DecLayerW {
     const float *ln1_g, *ln1_b, *bqkv, *bo, *ln2_g, *ln2_b, *bq2, *bkv2, *bo2, *ln3_g, *ln3_b, *b1, *b2;
     CUtensorMap m_qkv, m_o, m_q2, m_kv2, m_o2, m_fc1, m_fc2;
+    const void *wqkv, *wo, *wq2, *wo2, *w1, *w2;     // the same bf16 matrices as plain pointers (persistent stack kernel)
 };
 
 struct GraphKey {
     int batch, prompt_len, max_length, suppress_blank, blank_id, eot, no_speech, no_timestamps, timestamp_begin,
-        max_initial, n_forced, want_argmax, pdl, fuse_ln, pdl_mask;
+        max_initial, n_forced, want_argmax, pdl, fuse_ln, pdl_mask, stack;
     bool operator==(const GraphKey& o) const { return std::memcmp(this, &o, sizeof(GraphKey)) == 0; }
 };
 
@@ -88,7 +90,10 @@ struct DecoderPlan {
     char* d_state = nullptr;
     int *tokens = nullptr, *step = nullptr, *done = nullptr, *last_ts = nullptr, *n_done = nullptr, *sot_index = nullptr,
         *use_ts = nullptr, *forced = nullptr, *argmax = nullptr;
-    unsigned *ticket = nullptr, *suppress_bits = nullptr;
+    unsigned *ticket = nullptr, *suppress_bits = nullptr, *stack_bar = nullptr;
+    StackLayerW* d_stack_layers = nullptr;           // device copy of the per-layer pointers (persistent stack kernel)
+    float* stack_part = nullptr;                     // attention partials of the stack kernel
+    long long* stack_trace = nullptr;                // ARIES_STACK_TRACE diagnostics (managed memory)
     float *score = nullptr, *nsp = nullptr;
     int* h_ndone = nullptr;                          // pinned
     struct GraphEntry {
@@ -120,6 +125,9 @@ void decoder_plan_destroy(DecoderPlan* pl) {
     cudaFree(pl->vc);
     cudaFree(pl->xkv);
     cudaFree(pl->d_state);
+    cudaFree(pl->d_stack_layers);
+    cudaFree(pl->stack_part);
+    cudaFree(pl->stack_trace);
     if (pl->h_ndone) cudaFreeHost(pl->h_ndone);
     delete pl;
 }
@@ -247,6 +255,8 @@ cudaError_t decoder_plan_create(int device, int sm_count, const DecoderShapeC& c
         lw.ln1_g = F(o.ln1_g); lw.ln1_b = F(o.ln1_b); lw.bqkv = F(o.bqkv); lw.bo = F(o.bo);
         lw.ln2_g = F(o.ln2_g); lw.ln2_b = F(o.ln2_b); lw.bq2 = F(o.bq2); lw.bkv2 = F(o.bkv2); lw.bo2 = F(o.bo2);
         lw.ln3_g = F(o.ln3_g); lw.ln3_b = F(o.ln3_b); lw.b1 = F(o.b1); lw.b2 = F(o.b2);
+        lw.wqkv = base + o.wqkv; lw.wo = base + o.wo; lw.wq2 = base + o.wq2; lw.wo2 = base + o.wo2;
+        lw.w1 = base + o.w1; lw.w2 = base + o.w2;
         if ((e = map2d(&lw.m_qkv, base + o.wqkv, d, 3ull * d, 128)) != cudaSuccess) return fail(e);
         if ((e = map2d(&lw.m_o, base + o.wo, d, d, 128)) != cudaSuccess) return fail(e);
         if ((e = map2d(&lw.m_q2, base + o.wq2, d, d, 128)) != cudaSuccess) return fail(e);
@@ -283,7 +293,7 @@ cudaError_t decoder_plan_create(int device, int sm_count, const DecoderShapeC& c
     const size_t B = max_batch;
     const size_t s_tok = take(B * C * 4), s_forced = take(B * C * 4), s_argmax = take(B * C * 4), s_step = take(4),
                  s_done = take(B * 4), s_lts = take(B * 4), s_ndone = take(4), s_sot = take(B * 4), s_uts = take(B * 4),
-                 s_ticket = take(4), s_bits = take(((size_t)V + 31) / 32 * 4),
+                 s_ticket = take(4), s_sbar = take(4), s_bits = take(((size_t)V + 31) / 32 * 4),
                  s_score = take(B * 4), s_nsp = take(B * 4);
     if ((e = cudaMalloc(&pl->d_state, off)) != cudaSuccess) return fail(e);
     if ((e = cudaMemset(pl->d_state, 0, off)) != cudaSuccess) return fail(e);
@@ -291,8 +301,24 @@ cudaError_t decoder_plan_create(int device, int sm_count, const DecoderShapeC& c
     pl->tokens = (int*)(s + s_tok); pl->forced = (int*)(s + s_forced); pl->argmax = (int*)(s + s_argmax);
     pl->step = (int*)(s + s_step); pl->done = (int*)(s + s_done); pl->last_ts = (int*)(s + s_lts);
     pl->n_done = (int*)(s + s_ndone); pl->sot_index = (int*)(s + s_sot); pl->use_ts = (int*)(s + s_uts);
+    pl->stack_bar = (unsigned*)(s + s_sbar);
     pl->ticket = (unsigned*)(s + s_ticket); pl->suppress_bits = (unsigned*)(s + s_bits);
     pl->score = (float*)(s + s_score); pl->nsp = (float*)(s + s_nsp);
+    {
+        std::vector<StackLayerW> sl(L);
+        for (int i = 0; i < L; ++i) {
+            const DecLayerW& lw = pl->layers[i];
+            sl[i] = StackLayerW{lw.wqkv, lw.wo, lw.wq2, lw.wo2, lw.w1, lw.w2, lw.ln1_g, lw.ln1_b, lw.bqkv, lw.bo, lw.ln2_g,
+                                lw.ln2_b, lw.bq2, lw.bo2, lw.ln3_g, lw.ln3_b, lw.b1, lw.b2};
+        }
+        if ((e = cudaMalloc(&pl->d_stack_layers, L * sizeof(StackLayerW))) != cudaSuccess) return fail(e);
+        if ((e = cudaMemcpy(pl->d_stack_layers, sl.data(), L * sizeof(StackLayerW), cudaMemcpyHostToDevice)) != cudaSuccess)
+            return fail(e);
+        const size_t pf = decode_stack_part_floats(cfg.n_heads) * 4;
+        if ((e = cudaMalloc(&pl->stack_part, pf)) != cudaSuccess) return fail(e);
+        if ((e = cudaMemset(pl->stack_part, 0, pf)) != cudaSuccess) return fail(e);
+    }
+    if (getenv("ARIES_STACK_TRACE") && (e = cudaMallocManaged(&pl->stack_trace, 4096 * 8)) != cudaSuccess) return fail(e);
     if ((e = cudaMallocHost(&pl->h_ndone, 4)) != cudaSuccess) return fail(e);
     for (auto& ev : pl->ev)
         if ((e = cudaEventCreate(&ev)) != cudaSuccess) return fail(e);
@@ -313,7 +339,7 @@ cudaError_t decoder_plan_create(int device, int sm_count, const DecoderShapeC& c
 namespace {
 
 // One decode step: consumes tokens[:, *step], writes tokens[:, *step + 1], increments *step.
-cudaError_t run_step(DecoderPlan* pl, int batch, const SampleParams& sp, int xsplits, bool pdl, bool fuse_ln,
+cudaError_t run_step(DecoderPlan* pl, int batch, const SampleParams& sp, int xsplits, bool pdl, bool fuse_ln, bool stack,
                      cudaStream_t stream, int* launches) {
     const auto& c = pl->cfg;
     const int d = c.d_model, f = c.d_ffn, C = c.n_text_ctx, A = c.n_audio_ctx;
@@ -345,6 +371,29 @@ cudaError_t run_step(DecoderPlan* pl, int batch, const SampleParams& sp, int xsp
         ++n;
         return skinny_launch(epi, w, xin, q, stream);
     };
+    if (stack) {
+        // <= 8 sequences: embedding, every layer and the final LayerNorm in one persistent cooperative kernel
+        DecStackParams q{};
+        q.layers = pl->d_stack_layers; q.n_layers = c.n_layers; q.d = d; q.f = f; q.heads = c.n_heads; q.batch = batch;
+        q.max_batch = pl->max_batch; q.C = C; q.A = A;
+        q.tokens = pl->tokens; q.tokens_ld = C; q.step = pl->step; q.done = pl->done; q.emb = pl->emb; q.pos = pl->pos;
+        q.x = pl->x; q.q = pl->qkv; q.q2 = pl->q2; q.h = pl->h; q.y = pl->y; q.ctx = pl->ctx; q.kc = pl->kc; q.vc = pl->vc; q.xkv = pl->xkv;
+        q.part = pl->stack_part; q.bar = pl->stack_bar; q.lnf_g = pl->lnf_g; q.lnf_b = pl->lnf_b;
+        if (const char* tr = getenv("ARIES_STACK_TRACE")) {      // diagnostics: per-phase clock64 stamps of one CTA
+            q.trace = pl->stack_trace;                           // allocated at plan creation (not during capture)
+            q.trace_cta = atoi(tr);
+        }
+        ARIES_TRY(decode_stack_launch(q, pl->sm_count, stream), "decoder stack");
+        ++n;
+        ARIES_TRY(skinny(SK_LOGITS_F32, pl->m_proj, pl->a_y, c.vocab, d, nullptr, pl->logits, pl->v_pad), "logits");
+        SampleParams sp2 = sp;
+        sp2.pdl = pdl_o;
+        sp2.stack_bar = pl->stack_bar;
+        ARIES_TRY(decode_sample_launch(sp2, stream), "sampling");
+        ++n;
+        *launches = n;
+        return cudaSuccess;
+    }
     ARIES_TRY(decode_embed_launch(pl->tokens, C, pl->step, pl->emb, pl->pos, pl->x, batch, d, pdl_o, stream), "embed");
     ++n;
     const __nv_bfloat16* qkv = reinterpret_cast<const __nv_bfloat16*>(pl->qkv);
@@ -483,6 +532,7 @@ cudaError_t decoder_generate(DecoderPlan* pl, const void* enc_out, int batch, co
     ARIES_TRY(cudaMemsetAsync(pl->step, 0, 4, stream), "memset");
     ARIES_TRY(cudaMemsetAsync(pl->n_done, 0, 4, stream), "memset");
     ARIES_TRY(cudaMemsetAsync(pl->ticket, 0, 4, stream), "memset");
+    ARIES_TRY(cudaMemsetAsync(pl->stack_bar, 0, 4, stream), "memset");
     ARIES_TRY(cudaMemsetAsync(pl->done, 0, batch * 4, stream), "memset");
     ARIES_TRY(cudaMemsetAsync(pl->score, 0, batch * 4, stream), "memset");
     ARIES_TRY(cudaMemsetAsync(pl->nsp, 0, batch * 4, stream), "memset");
@@ -526,6 +576,10 @@ cudaError_t decoder_generate(DecoderPlan* pl, const void* enc_out, int batch, co
     const bool fuse_ln = env_on("ARIES_DECODE_FUSED_LN", true) && batch <= 8 && d <= 1280 &&
                          skinny_pick_splits_ln(3 * d, d, pl->sm_count) > 0 && skinny_pick_splits_ln(d, d, pl->sm_count) > 0 &&
                          skinny_pick_splits_ln(c.d_ffn, d, pl->sm_count) > 0;
+    // persistent stack kernel (<= 8 sequences): opt-in with ARIES_DECODE_STACK=1 -- measured SLOWER than the launch-per-op
+    // step on B200 (1.69 vs 1.54 ms per token at 1 window, 3.4 vs 2.0 at 8; decode_stack.cu header)
+    const bool stack = env_on("ARIES_DECODE_STACK", false) &&
+                       decode_stack_supported(d, c.d_ffn, c.n_heads, batch, pl->sm_count);
     const bool use_graph = env_on("ARIES_DECODE_GRAPH", true) && !o.logits_out;
     // programmatic dependent launch (GEMMs and the small kernels; see run_step): -5 .. -12 % per step at every batch size
     bool pdl = env_on("ARIES_DECODE_PDL", true);
@@ -536,7 +590,8 @@ cudaError_t decoder_generate(DecoderPlan* pl, const void* enc_out, int batch, co
     if (use_graph) {
         GraphKey key{batch, prompt_len, o.max_length, o.suppress_blank, o.blank_id, o.eot, o.no_speech, o.no_timestamps,
                      o.timestamp_begin, o.max_initial_timestamp_index, o.n_forced, o.argmax_out ? 1 : 0, pdl ? 1 : 0,
-                     fuse_ln ? 1 : 0, getenv("ARIES_DECODE_PDL_MASK") ? atoi(getenv("ARIES_DECODE_PDL_MASK")) : -1};
+                     fuse_ln ? 1 : 0, getenv("ARIES_DECODE_PDL_MASK") ? atoi(getenv("ARIES_DECODE_PDL_MASK")) : -1,
+                     stack ? 1 : 0};
         for (auto& g : pl->graphs)
             if (g.key == key) {
                 graph = g.exec;
@@ -547,7 +602,7 @@ cudaError_t decoder_generate(DecoderPlan* pl, const void* enc_out, int batch, co
                 sp.pdl = pdl;
                 cudaGraph_t g = nullptr;
                 ARIES_TRY(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal), "begin capture");
-                cudaError_t e1 = run_step(pl, batch, sp, xsplits, pdl, fuse_ln, stream, &per_step);
+                cudaError_t e1 = run_step(pl, batch, sp, xsplits, pdl, fuse_ln, stack, stream, &per_step);
                 cudaError_t e2 = cudaStreamEndCapture(stream, &g);
                 cudaError_t e3 = (e1 == cudaSuccess && e2 == cudaSuccess) ? cudaGraphInstantiate(&graph, g, 0) : cudaErrorUnknown;
                 if (g) cudaGraphDestroy(g);
@@ -577,7 +632,7 @@ cudaError_t decoder_generate(DecoderPlan* pl, const void* enc_out, int batch, co
         if (use_graph) {
             ARIES_TRY(cudaGraphLaunch(graph, stream), "graph launch");
         } else {
-            cudaError_t e = run_step(pl, batch, sp, xsplits, pdl, fuse_ln, stream, &per_step);
+            cudaError_t e = run_step(pl, batch, sp, xsplits, pdl, fuse_ln, stack, stream, &per_step);
             if (e != cudaSuccess) return e;
             if (o.logits_out)
                 ARIES_TRY(cudaMemcpy2DAsync(o.logits_out + (size_t)t * batch * V, (size_t)V * 4, pl->logits,
@@ -618,6 +673,17 @@ cudaError_t decoder_generate(DecoderPlan* pl, const void* enc_out, int batch, co
             ++n;
         }
         if (lengths) lengths[b] = n;
+    }
+    if (pl->stack_trace && getenv("ARIES_STACK_TRACE")) {
+        // last step: 17 stamps per layer (see decode_stack_kernel): phase start, staged, weights done / barrier done
+        const long long* t = pl->stack_trace;
+        const int per_layer = 23;   // LN1 QKV sync | attn sync | ctx O sync | LN2 Q2 sync | xattn sync | ctx O2 sync | LN3 fc1 sync | h fc2 sync
+        for (int l = 0; l < L && l < 3; ++l) {
+            fprintf(stderr, "stack trace layer %d (cycles):", l);
+            for (int i = 1; i < per_layer; ++i) fprintf(stderr, " %lld", t[l * per_layer + i] - t[l * per_layer + i - 1]);
+            fprintf(stderr, "\n");
+        }
+        fprintf(stderr, "stack trace: whole stack %lld cycles\n", t[L * per_layer - 1] - t[0]);
     }
     float ms_kv = 0, ms_loop = 0;
     cudaEventElapsedTime(&ms_kv, pl->ev[0], pl->ev[1]);

@@ -111,8 +111,43 @@ struct SampleParams {
     int forced_ld, n_forced;
     int* argmax_out;            // tests: [batch, tokens_ld] what the argmax was at each sampled position (or NULL)
     int pdl;
+    unsigned* stack_bar;        // grid-barrier counter of decode_stack_kernel, zeroed here for the next step (or NULL)
 };
 cudaError_t decode_sample_launch(const SampleParams& p, cudaStream_t stream);
+
+// ------------------------------------------------------------------------------------------------ persistent stack
+// All decoder layers of one step in ONE cooperative kernel (decode_stack.cu), <= 8 sequences: one CTA per SM, weights
+// prefetched through a shared-memory ring by a producer warp, grid-wide barriers between the phases of a layer.
+struct StackLayerW {
+    const void *wqkv, *wo, *wq2, *wo2, *w1, *w2;      // bf16 [N, K] row-major
+    const float *ln1_g, *ln1_b, *bqkv, *bo, *ln2_g, *ln2_b, *bq2, *bo2, *ln3_g, *ln3_b, *b1, *b2;
+};
+constexpr int kPartStride = 72;                       // floats per attention partial: 64 sums, weight sum, max, pad
+struct DecStackParams {
+    const StackLayerW* layers;                        // device array [n_layers]
+    int n_layers, d, f, heads, batch, max_batch;
+    int C, A;                                         // n_text_ctx (rows per sequence of the caches), n_audio_ctx
+    const int* tokens;                                // [batch, tokens_ld]
+    int tokens_ld;
+    const int* step;                                  // device scalar: position of the token being consumed
+    const int* done;                                  // [batch] or NULL
+    const void* emb;                                  // bf16 [vocab, d]
+    const float* pos;                                 // f32 [C, d]
+    void* x;                                          // f16 [batch, d] residual stream
+    void *q, *q2, *h, *y, *ctx;                       // bf16 [batch, d | d | f | d | d]; y = final LayerNorm output
+    void *kc, *vc;                                    // bf16 [layers][max_batch][C][d]
+    const void* xkv;                                  // bf16 [layers][batch * A][2 d]
+    float* part;                                      // decode_stack_part_floats(heads) floats, zero at allocation
+    unsigned* cnt;                                    // arrival counters per (sequence, head): tail of `part` (set by the launch)
+    unsigned* bar;                                    // zero at launch (decode_sample_kernel resets it)
+    const float *lnf_g, *lnf_b;
+    int splits_self, splits_cross, n_stages;          // filled by decode_stack_launch
+    long long* trace;                                 // diagnostics (ARIES_STACK_TRACE): clock64 stamps of CTA trace_cta, or NULL
+    int trace_cta;
+};
+bool decode_stack_supported(int d, int f, int heads, int batch, int sm_count);
+size_t decode_stack_part_floats(int heads);
+cudaError_t decode_stack_launch(const DecStackParams& p, int sm_count, cudaStream_t stream);
 
 // griddepcontrol-aware launch helper shared by the decode kernels
 cudaError_t launch_maybe_pdl(const void* func, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, void** args,
