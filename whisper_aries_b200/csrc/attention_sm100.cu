@@ -24,6 +24,7 @@
 // pre-transposed ([B, h, 64, t_pad]) from that GEMM's epilogue so that both MMAs use K-major operands.
 // Keys >= T are zero-filled by TMA and masked to -inf here; query rows >= T are computed and dropped.
 #include <cstdlib>
+#include <type_traits>
 
 #include "attention.h"
 #include "ptx.cuh"
@@ -304,25 +305,39 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         const uint32_t tmem_s = tmem_base + lane_addr + g * 128;               // S_g buffers, P_g on top of them
         const uint32_t tmem_o = tmem_base + lane_addr + kTmemO + g * kOCols;
         float m_ref = 0.0f;
+        // Padding trim (T = 1500 = 11.7 query tiles = 23.4 key tiles): a warp whose 32 query rows all lie past T only keeps
+        // the handshake going -- its rows are never stored, so what the PV MMA reads as their P is irrelevant -- and the
+        // second 32 columns of a last key tile with <= 32 real keys are published as zeros without being loaded,
+        // compared or exponentiated.  Both are warp-uniform; together ~4 % of the MUFU work of large-v3.
+        const bool dead_rows = q0 + g * kBlockQ + quarter * 32 >= p.T;
 
-#pragma unroll 1
-        for (int j = 0; j < n_kv; ++j) {
+        // One key tile.  kLast is a compile-time tag: the steady-state instance carries no masking and no branch on the
+        // tile index at all (this loop is bound by the MUFU / MIO issue order and measurably sensitive to any extra
+        // control flow), the last-tile instance masks the keys >= T and drops the second half when it is all padding.
+        auto tile = [&](int j, auto last_tag) {
+            constexpr bool kLast = decltype(last_tag)::value;
             const int buf = j & 1;
             if (kTrace) tr.stamp();
             mbar_wait(&s_full[2 * g + buf], (j >> 1) & 1);
             tc_fence_after();
             if (kTrace) tr.stamp();
+            const int kv_valid = p.T - j * kBlockKV;
+            const bool half_tile = kLast && kv_valid <= 32;
             uint32_t s0[32], s1[32];
             tmem_ld_32x32b_x32(tmem_s + buf * kBlockKV, s0);
-            tmem_ld_32x32b_x32(tmem_s + buf * kBlockKV + 32, s1);
+            if (!half_tile) tmem_ld_32x32b_x32(tmem_s + buf * kBlockKV + 32, s1);
             tmem_ld_wait_on(s0);
-            tmem_ld_wait_on(s1);
-            const int kv_valid = p.T - j * kBlockKV;
-            if (kv_valid < kBlockKV) {                       // only the last tile: keys >= T do not exist
-                mask32(s0, 0, kv_valid);
-                mask32(s1, 32, kv_valid);
+            if (!half_tile) {
+                tmem_ld_wait_on(s1);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) s1[i] = 0xFF800000u;
             }
-            const float m_tile = fmaxf(max32(s0), max32(s1));
+            if (kLast && kv_valid < kBlockKV) {              // keys >= T do not exist
+                mask32(s0, 0, kv_valid);
+                if (!half_tile) mask32(s1, 32, kv_valid);
+            }
+            const float m_tile = half_tile ? max32(s0) : fmaxf(max32(s0), max32(s1));
             if (j == 0) {
                 m_ref = m_tile;
             } else {
@@ -331,7 +346,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                 if (__any_sync(0xffffffffu, need)) {
                     // O_g += P_g(j-1) V_(j-1) must have retired: S_g(j+1) was issued after it, so its commit
                     // covers it; the last tile has no successor and uses a commit of its own
-                    if (j + 1 < n_kv) mbar_wait(&s_full[2 * g + (buf ^ 1)], ((j + 1) >> 1) & 1);
+                    if (!kLast) mbar_wait(&s_full[2 * g + (buf ^ 1)], ((j + 1) >> 1) & 1);
                     else mbar_wait(&pv_done[g], 0);
                     tc_fence_after();
                     const float f = need ? fast_exp2((m_ref - m_tile) * kScale) : 1.0f;
@@ -359,13 +374,32 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             uint32_t pk0[16], pk1[16];
             if (kTrace) tr.stamp();
             exp_pack<kPoly>(s0, neg_m, pk0);
-            exp_pack<kPoly>(s1, neg_m, pk1);
+            if (!half_tile) {
+                exp_pack<kPoly>(s1, neg_m, pk1);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) pk1[i] = 0u;    // exp2(-inf) = 0, as the masked path would have produced
+            }
             if (kTrace) tr.stamp();
             tmem_st_32x32b_x16(tmem_s + buf * kBlockKV, pk0);
             tmem_st_32x32b_x16(tmem_s + buf * kBlockKV + 16, pk1);
             tmem_st_wait();
             tc_fence_before();              // our TMEM reads / writes are complete and ordered before the arrive
             mbar_arrive(&p_full[2 * g + buf]);
+        };
+        if (dead_rows) {
+            // all 32 query rows of this warp lie past T: keep the handshake going, compute nothing
+#pragma unroll 1
+            for (int j = 0; j < n_kv; ++j) {
+                mbar_wait(&s_full[2 * g + (j & 1)], (j >> 1) & 1);
+                tc_fence_after();
+                tc_fence_before();
+                mbar_arrive(&p_full[2 * g + (j & 1)]);
+            }
+        } else {
+#pragma unroll 1
+            for (int j = 0; j + 1 < n_kv; ++j) tile(j, std::false_type{});
+            tile(n_kv - 1, std::true_type{});
         }
 
         if (kTrace) tr.stamp();
