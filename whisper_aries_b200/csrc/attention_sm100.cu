@@ -57,7 +57,7 @@ constexpr int kSmemBytes = kQTiles * kQTileBytes + kKStages * kKBytes + kVStages
 constexpr uint32_t kTmemCols = 256 * kQTiles;            // per tile g: S0 [128g, +64) S1 [128g+64, +64); O_g [kTmemO+80g, +80)
 constexpr uint32_t kTmemO = 128 * kQTiles;
 constexpr float kScale = 0.18033688011112042f;           // log2(e) / sqrt(64)
-constexpr int kDefaultPoly = 8;                          // ARIES_ATTN_POLY overrides (0, 4 or 8); 8 measured best in the full step (round 2)
+constexpr int kDefaultPoly = 104;                        // ARIES_ATTN_POLY overrides (0, 4, 8, 102 .. 108): 1/4 of the exponentials as packed polynomials, measured best (tests/attn_ab.py)
 constexpr float kRescaleThreshold = 8.0f;                // lazy rescale: only when the row max grew by > 2^8
 
 // Test-only timeline (variant bit 2, ARIES_ATTN_TRACE=1): clock64 stamps of lane 0 of every warp of a few CTAs.
@@ -130,8 +130,57 @@ __device__ __forceinline__ void join32(float (&e)[32]) {
 // p = exp2(s * c - m * c) for 32 scores -> 16 packed bf16x2 (low half = the lower key index).  The scale / offset is
 // a packed f32x2 FMA (two scores per instruction); with kPoly every 8th exponential runs on the FMA pipe instead of
 // the MUFU.
+// Two exponentials at once on the FMA pipe: the range reduction and the polynomial are packed f32x2 instructions
+// (5.5 issue slots per element against ~10 for the scalar form).
+__device__ __forceinline__ float2 poly_exp2x2(float2 x) {
+    x.x = fmaxf(x.x, -120.0f);
+    x.y = fmaxf(x.y, -120.0f);
+    const float2 magic = make_float2(12582912.0f, 12582912.0f);
+    const float2 t = __fadd2_rn(x, magic);
+    const float2 r = __fadd2_rn(t, make_float2(-12582912.0f, -12582912.0f));
+    const float2 f = __ffma2_rn(r, make_float2(-1.0f, -1.0f), x);
+    float2 p = __ffma2_rn(make_float2(9.6181291e-3f, 9.6181291e-3f), f, make_float2(5.5504109e-2f, 5.5504109e-2f));
+    p = __ffma2_rn(p, f, make_float2(2.4022651e-1f, 2.4022651e-1f));
+    p = __ffma2_rn(p, f, make_float2(6.9314718e-1f, 6.9314718e-1f));
+    p = __ffma2_rn(p, f, make_float2(1.0f, 1.0f));
+    return make_float2(__int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23)),
+                       __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23)));
+}
+
+// kPoly: 0 = every exponential on the MUFU; 4 / 8 = every 4th / 8th on the FMA pipe (scalar polynomial);
+// 100 + n = n PAIRS of every 16 pairs on the FMA pipe with the packed polynomial (102: 1/8, 104: 1/4, 106: 3/8, 108: 1/2)
 template <int kPoly>
 __device__ __forceinline__ void exp_pack(const uint32_t (&s)[32], float neg_m, uint32_t (&out)[16]) {
+    if constexpr (kPoly >= 100) {
+        constexpr int kPairs = kPoly - 100;              // of 16
+        const float2 c2 = make_float2(kScale, kScale);
+        const float2 m2 = make_float2(neg_m, neg_m);
+        float e[32];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+            const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), c2, m2);
+            e[i] = x.x;
+            e[i + 1] = x.y;
+        }
+        join32(e);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            // pair k goes to the FMA pipe when the running count k * kPairs / 16 steps up (evenly spread)
+            const bool poly = ((k + 1) * kPairs) / 16 != (k * kPairs) / 16;
+            if (poly) {
+                const float2 y = poly_exp2x2(make_float2(e[2 * k], e[2 * k + 1]));
+                e[2 * k] = y.x;
+                e[2 * k + 1] = y.y;
+            } else {
+                e[2 * k] = fast_exp2(e[2 * k]);
+                e[2 * k + 1] = fast_exp2(e[2 * k + 1]);
+            }
+        }
+        join32(e);
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) out[i >> 1] = pack_bf16x2(e[i], e[i + 1]);
+        return;
+    }
     const float2 c2 = make_float2(kScale, kScale);
     const float2 m2 = make_float2(neg_m, neg_m);
     float e[32];
@@ -450,7 +499,7 @@ int attn_variant() {               // 0: all exponentials on the MUFU; 8 / 4: ev
         const char* r = getenv("ARIES_ATTN_TRACE");
         if (r && r[0] != '0') return -1;
         const int n = e ? atoi(e) : kDefaultPoly;
-        return (n == 4 || n == 8) ? n : 0;
+        return (n == 4 || n == 8 || n == 102 || n == 104 || n == 106 || n == 108) ? n : 0;
     }();
     return v;
 }
@@ -468,6 +517,10 @@ cudaError_t attention_init_device() {
     if ((e = set_smem<0, false>()) != cudaSuccess) return e;
     if ((e = set_smem<8, false>()) != cudaSuccess) return e;
     if ((e = set_smem<4, false>()) != cudaSuccess) return e;
+    if ((e = set_smem<102, false>()) != cudaSuccess) return e;
+    if ((e = set_smem<104, false>()) != cudaSuccess) return e;
+    if ((e = set_smem<106, false>()) != cudaSuccess) return e;
+    if ((e = set_smem<108, false>()) != cudaSuccess) return e;
     return set_smem<0, true>();
 }
 
@@ -501,6 +554,10 @@ cudaError_t attention_launch(const AttnMaps& maps, const AttnParams& p, cudaStre
     switch (attn_variant()) {
         case 8: attention_fwd_kernel<8, false><<<grid, kThreads, kSmemBytes, stream>>>(maps.q, maps.k, maps.vt, p); break;
         case 4: attention_fwd_kernel<4, false><<<grid, kThreads, kSmemBytes, stream>>>(maps.q, maps.k, maps.vt, p); break;
+        case 102: attention_fwd_kernel<102, false><<<grid, kThreads, kSmemBytes, stream>>>(maps.q, maps.k, maps.vt, p); break;
+        case 104: attention_fwd_kernel<104, false><<<grid, kThreads, kSmemBytes, stream>>>(maps.q, maps.k, maps.vt, p); break;
+        case 106: attention_fwd_kernel<106, false><<<grid, kThreads, kSmemBytes, stream>>>(maps.q, maps.k, maps.vt, p); break;
+        case 108: attention_fwd_kernel<108, false><<<grid, kThreads, kSmemBytes, stream>>>(maps.q, maps.k, maps.vt, p); break;
         case -1: attention_fwd_kernel<0, true><<<grid, kThreads, kSmemBytes, stream>>>(maps.q, maps.k, maps.vt, p); break;
         default: attention_fwd_kernel<0, false><<<grid, kThreads, kSmemBytes, stream>>>(maps.q, maps.k, maps.vt, p); break;
     }
