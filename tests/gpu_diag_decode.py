@@ -48,7 +48,7 @@ def err():
         print(name, "no_speech_prob", [r.no_speech_prob for r in res], [r["no_speech_prob"] for r in ref])
 
 
-def perf(batches, modes=("graph+pdl", "graph", "stream+pdl", "stream"), stacks=("1",)):
+def perf(batches, modes=("graph+pdl", "graph", "stream+pdl", "stream"), stacks=("0",)):
     from whisper_aries_b200 import WhisperDecoder, synthetic
     shape = synthetic.DEC_SHAPES["large-v3"]
     tok = synthetic.WhisperTokens.for_vocab(shape.vocab)
