@@ -56,6 +56,16 @@ ARIES_API int aries_test_skinny_gemm_ln(aries_ctx* ctx, int epi, int B, int N, i
                               const float* beta, const void* w, const float* bias, void* out, int ldo, int splits,
                               void* stream);
 
+/* The decode step's folded LayerNorm, both sides in one call (csrc/skinny.h SK_LNF_*):
+ *   (1) resid_x_f16 [NB, K] f16 += ctx_in [NB, K] bf16 . w_o [K, K]^T + bias_o   (SK_BIAS_RESID_F16, in place) and the
+ *       partial (sum, sum of squares) of the stored rows -> stats [B, ceil(K / 128)] float2;
+ *   (2) out_bf16 [B, N] = [gelu](rstd (x . w_folded_f16^T - mean c1) + c2) with w_folded_f16 [N, K] = f16(gamma * W),
+ *       c1[n] = sum_k w_folded[n, k], c2[n] = sum_k beta_k W[n, k] + b[n].
+ * NB = B rounded up to 16 (rows >= B must be zero); K % 64 == 0, K <= 2048. */
+ARIES_API int aries_test_skinny_gemm_folded(aries_ctx* ctx, int B, int N, int K, const void* resid_x_f16, const void* ctx_in,
+                                  const void* w_o, const float* bias_o, const void* w_folded_f16, const float* c1,
+                                  const float* c2, int gelu, void* out_bf16, float* stats, void* stream);
+
 /* Single-query attention over a bf16 key/value cache (see csrc/skinny.h DecAttnParams). n_keys_fixed == 0: self-attention
  * (appends new_k / new_v at position *step_dev, attends to 0 .. *step_dev); otherwise cross-attention over n_keys_fixed
  * keys with `splits` CTAs per (sequence, head). */

@@ -128,6 +128,57 @@ def test_skinny_gemm_fused_layernorm(ctx, shape, epi):
         assert err <= tol, f"splits={splits}: max err {err} > {tol}"
 
 
+@pytest.mark.parametrize("shape", [(1, 384, 128), (5, 1152, 384), (16, 3840, 1280), (64, 5120, 1280), (100, 1280, 1280),
+                                   (9, 320, 192)])
+@pytest.mark.parametrize("gelu", [0, 1])
+def test_skinny_gemm_folded_layernorm(ctx, shape, gelu):
+    """LayerNorm folded into the GEMM by algebra (every batch size; csrc/skinny.h SK_LNF_*), both sides: the residual GEMM
+    updates the f16 stream and leaves the partial row sums, the consumer multiplies the raw stream by f16(gamma W) and
+    applies mean / rstd in its epilogue.  Against LayerNorm -> Linear in torch fp32 on the stream the kernel stored."""
+    from whisper_aries_b200 import _lib
+    B, N, K = shape
+    NB = (B + 15) // 16 * 16
+    g = torch.Generator().manual_seed(B + N + K + gelu)
+    x0 = torch.zeros(NB, K)
+    x0[:B] = torch.randn(B, K, generator=g) * 2.0 + 0.5
+    x = x0.cuda().half()
+    cin = torch.zeros(NB, K)
+    cin[:B] = torch.randn(B, K, generator=g)
+    cin = cin.cuda().bfloat16()
+    w_o = (torch.randn(K, K, generator=g) * 0.05).cuda().bfloat16()
+    b_o = torch.randn(K, generator=g).cuda()
+    gamma = (1.0 + 0.1 * torch.randn(K, generator=g)).cuda()
+    beta = (0.1 * torch.randn(K, generator=g)).cuda()
+    w = (torch.randn(N, K, generator=g) * 0.05).cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    wf = (w * gamma[None, :]).half()
+    c1 = wf.float().sum(dim=1).contiguous()
+    c2 = (w.double() @ beta.double() + bias.double()).float().contiguous()
+    parts = (K + 127) // 128
+    stats = torch.full((B, parts, 2), float("nan"), device="cuda")
+    out = torch.full((B, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    x_ref = (x[:B].float() + cin[:B].float() @ w_o.float().t() + b_o).half()
+    _lib.check(ctx.lib.aries_test_skinny_gemm_folded(ctx.handle, B, N, K, ptr(x), ptr(cin), ptr(w_o), ptr(b_o), ptr(wf), ptr(c1),
+                                                     ptr(c2), gelu, ptr(out), ptr(stats), None))
+    torch.cuda.synchronize()
+    # (1) the stream and its statistics
+    assert (x[:B].float() - x_ref.float()).abs().max().item() <= 2e-2
+    assert x[B:].abs().max().item() == 0 if NB > B else True
+    xs = x[:B].float()
+    got_sum, got_sq = stats[..., 0].sum(dim=1), stats[..., 1].sum(dim=1)
+    assert torch.allclose(got_sum, xs.sum(dim=1), rtol=1e-5, atol=1e-2)
+    assert torch.allclose(got_sq, (xs * xs).sum(dim=1), rtol=1e-5, atol=1e-2)
+    per_tile = torch.stack([xs[:, 128 * t:128 * (t + 1)].sum(dim=1) for t in range(parts)], dim=1)
+    assert torch.allclose(stats[..., 0], per_tile, rtol=1e-5, atol=1e-2)
+    # (2) the consumer against LayerNorm -> Linear on the stored stream
+    ref = torch.nn.functional.layer_norm(xs, (K,), gamma, beta, 1e-5) @ w.t() + bias
+    if gelu:
+        ref = torch.nn.functional.gelu(ref)
+    scale = ref.abs().max().item()
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 2e-3 + scale * 2 ** -7, f"max err {err} (scale {scale})"
+
+
 def test_fused_layernorm_rejects_large_batches(ctx):
     from whisper_aries_b200 import _lib
     x = torch.zeros(16, 128, device="cuda", dtype=torch.float16)
@@ -480,6 +531,36 @@ def test_persistent_stack_odd_width_and_long_context(monkeypatch):
             assert cos >= 0.9995, f"window {b} step {t}: logits cosine {cos}"
 
 
+@pytest.mark.parametrize("shape_name,batch,seed", [("micro", 2, 32), ("micro", 12, 23), ("mini", 3, 35)])
+def test_folded_layernorm_step_agrees_with_the_older_paths(monkeypatch, shape_name, batch, seed):
+    """The opt-in decode step with LayerNorm folded into the GEMMs by algebra (ARIES_DECODE_FOLD_LN=1, 8 kernels per layer
+    at every batch size) against the default (LayerNorm in the operand load at <= 8 windows, separate kernels above): not
+    less accurate against the fp32 oracle, the same ids on the first decisions."""
+    monkeypatch.setenv("ARIES_DECODE_FOLD_LN", "1")         # read when the handle is created (the f16 weight copies)
+    shape, tok, otok, enc, dec, oracle, wd = _setup(shape_name, batch, seed)
+    prompt = [tok.sot, tok.first_lang + 1, tok.transcribe]
+    L = len(prompt) + 12
+    outs = {}
+    for fold in ("1", "0"):
+        monkeypatch.setenv("ARIES_DECODE_FOLD_LN", fold)
+        res, extras = dec.generate(enc.cuda(), [prompt] * batch, max_length=L, suppress_tokens=[], _want_logits=True)
+        outs[fold] = (res, extras[0]["logits"], dec.last_stats()["kernels_per_step"])
+    assert outs["1"][2] == 8 * shape.n_layers + 4
+    assert outs["0"][2] == (8 if batch <= 8 else 11) * shape.n_layers + 4
+    a, b = torch.from_numpy(outs["1"][1]), torch.from_numpy(outs["0"][1])
+    assert torch.isfinite(a).all()
+    ids = [r.sequences_ids[0] for r in outs["1"][0]]
+    assert [i[:6] for i in ids] == [r.sequences_ids[0][:6] for r in outs["0"][0]]
+    if [r.sequences_ids[0] for r in outs["0"][0]] == ids:
+        n = min(len(i) for i in ids)
+        seqs = torch.tensor([prompt + i[:n] for i in ids])[:, :len(prompt) + n - 1]
+        ref = oracle.logits(seqs, enc.float()).transpose(0, 1)
+        T = ref.shape[0]
+        rms_fold = (a[:T] - ref).pow(2).mean().sqrt().item()
+        rms_old = (b[:T] - ref).pow(2).mean().sqrt().item()
+        assert rms_fold <= 1.5 * rms_old + 1e-3, (rms_fold, rms_old)
+
+
 def test_scheduler_transcribe_worker_returns_token_rows():
     """ChunkScheduler + gpu_transcribe_worker: PCM windows in, token rows out (prompt, sampled ids, EOT padding, count
     in column 0), in window order, equal to encode_audio + generate called directly; ragged last micro-batch."""
@@ -563,10 +644,12 @@ def test_detect_language_matches_oracle():
     assert len(dec.generate(enc.cuda(), [prompt] * 3, max_length=10, suppress_tokens=[])) == 3
 
 
-@pytest.mark.parametrize("batch", [2, 9])
-def test_odd_width_decoder_uses_the_generic_layernorm(batch):
-    """d_model = 192 (3 heads; not a multiple of 128, so the register-resident LayerNorm kernel does not apply): 2 windows
-    take the fused-LayerNorm GEMMs with a partly filled chunk row, 9 windows the generic LayerNorm kernel."""
+@pytest.mark.parametrize("batch,fold", [(2, "1"), (9, "1"), (2, "0"), (9, "0")])
+def test_odd_width_decoder_uses_the_generic_layernorm(monkeypatch, batch, fold):
+    """d_model = 192 (3 heads; not a multiple of 128, so the register-resident LayerNorm kernel does not apply).  Default:
+    2 windows take the fused-LayerNorm GEMMs with a partly filled chunk row, 9 windows the generic LayerNorm kernel.
+    ARIES_DECODE_FOLD_LN=1 (opt-in): LayerNorm folded into the GEMMs by algebra, a half-filled second statistics tile."""
+    monkeypatch.setenv("ARIES_DECODE_FOLD_LN", fold)
     from oracle import synth as osynth, whisper_decoder as wd
     from whisper_aries_b200 import WhisperDecoder, synthetic
     shape = synthetic.DecoderShape("nano", 300, 192, 3, 2, 320)
@@ -582,7 +665,7 @@ def test_odd_width_decoder_uses_the_generic_layernorm(batch):
     L = len(prompt) + 8
     res, extras = dec.generate(enc.cuda(), [prompt] * batch, max_length=L, suppress_tokens=[], _forced=forced,
                                _want_logits=True)
-    assert dec.last_stats()["kernels_per_step"] == (8 if batch <= 8 else 11) * shape.n_layers + 4
+    assert dec.last_stats()["kernels_per_step"] == (8 if batch <= 8 or fold == "1" else 11) * shape.n_layers + 4
     seqs = torch.tensor([prompt + f for f in forced])[:, :L - 1]
     ref = oracle.logits(seqs, enc.float())
     logits = torch.from_numpy(extras[0]["logits"]).transpose(0, 1)

@@ -636,6 +636,48 @@ int aries_test_skinny_gemm_ln(aries_ctx* ctx, int epi, int B, int N, int K, cons
     return ARIES_OK;
 }
 
+int aries_test_skinny_gemm_folded(aries_ctx* ctx, int B, int N, int K, const void* resid_x_f16, const void* ctx_in,
+                                  const void* w_o, const float* bias_o, const void* w_folded_f16, const float* c1, const float* c2,
+                                  int gelu, void* out_bf16, float* stats, void* stream) {
+    int rc = use(ctx);
+    if (rc) return rc;
+    if ((rc = ensure_kernels(ctx))) return rc;
+    if (B <= 0 || B > 128 || N <= 0 || K <= 0 || K % 64 || !resid_x_f16 || !ctx_in || !w_o || !bias_o || !w_folded_f16 || !c1 || !c2 ||
+        !out_bf16 || !stats)
+        return fail(ARIES_EINVAL, "aries_test_skinny_gemm_folded: bad arguments");
+    const int parts = (K + 127) / 128;
+    if (parts > 16 || aries::skinny_pick_splits(K, K, ctx->sm_count) < 2)
+        return fail(ARIES_EINVAL, "aries_test_skinny_gemm_folded: needs K <= 2048 and a split residual GEMM");
+    const int NB = (B + 15) / 16 * 16;
+    CUtensorMap t_wo, t_ctx, t_wf, t_x;
+    const unsigned long long st[2] = {2, (unsigned long long)K * 2};
+    const unsigned long long d_wo[2] = {(unsigned long long)K, (unsigned long long)K}, d_x[2] = {(unsigned long long)K, (unsigned long long)NB};
+    const unsigned long long d_wf[2] = {(unsigned long long)K, (unsigned long long)N};
+    const unsigned bw[2] = {64, 128}, bx[2] = {64, (unsigned)NB};
+    cudaError_t e;
+    if ((e = aries::make_tmap_bf16(&t_wo, w_o, 2, d_wo, st, bw)) != cudaSuccess) return fail_cuda("tensor map", e);
+    if ((e = aries::make_tmap_bf16(&t_ctx, ctx_in, 2, d_x, st, bx)) != cudaSuccess) return fail_cuda("tensor map", e);
+    if ((e = aries::make_tmap_bf16(&t_wf, w_folded_f16, 2, d_wf, st, bw)) != cudaSuccess) return fail_cuda("tensor map", e);
+    if ((e = aries::make_tmap_bf16(&t_x, resid_x_f16, 2, d_x, st, bx)) != cudaSuccess) return fail_cuda("tensor map", e);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    // (1) the producing side: x += ctx W_o^T + b (f16 stream, in place) and the partial row sums of what it stored
+    aries::SkinnyParams a{};
+    a.B = B; a.NB = NB; a.N = K; a.K = K;
+    a.splits = aries::skinny_pick_splits(K, K, ctx->sm_count);
+    a.bias = bias_o; a.out = const_cast<void*>(resid_x_f16); a.ldo = K;
+    a.stats_out = reinterpret_cast<float2*>(stats);
+    if ((e = aries::skinny_launch(aries::SK_BIAS_RESID_F16, t_wo, t_ctx, a, s)) != cudaSuccess) return fail_cuda("skinny_launch (residual + statistics)", e);
+    // (2) the consuming side: out = [gelu](rstd (x W'^T - mean c1) + c2)
+    aries::SkinnyParams q{};
+    q.B = B; q.NB = NB; q.N = N; q.K = K;
+    q.splits = aries::skinny_pick_splits(N, K, ctx->sm_count);
+    q.bias = c2; q.c1 = c1; q.stats_in = reinterpret_cast<const float2*>(stats); q.stats_parts = parts; q.ln_dim = K;
+    q.out = out_bf16; q.ldo = N;
+    if ((e = aries::skinny_launch(gelu ? aries::SK_LNF_GELU_BF16 : aries::SK_LNF_BF16, t_wf, t_x, q, s)) != cudaSuccess)
+        return fail_cuda("skinny_launch (folded LayerNorm)", e);
+    return ARIES_OK;
+}
+
 int aries_test_decode_attention(aries_ctx* ctx, const void* q, int q_ld, void* k, void* v, int64_t kv_rows, int kv_ld,
                                 const void* new_k, const void* new_v, int new_ld, const int* step_dev, int n_keys_fixed,
                                 int batch, int heads, void* out, int out_ld, int splits, void* stream) {

@@ -22,7 +22,9 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 
 __global__ void __launch_bounds__(128) decode_embed_kernel(const int* __restrict__ tokens, int tokens_ld, const int* step,
                                                            const __nv_bfloat16* __restrict__ emb,
-                                                           const float* __restrict__ pos, __half* __restrict__ x, int d) {
+                                                           const float* __restrict__ pos, __half* __restrict__ x, int d,
+                                                           float2* __restrict__ stats, int stats_parts) {
+    __shared__ float2 s_part[4];
     pdl_wait();
     pdl_trigger();
     const int b = blockIdx.x;
@@ -31,10 +33,30 @@ __global__ void __launch_bounds__(128) decode_embed_kernel(const int* __restrict
     const __nv_bfloat162* e = reinterpret_cast<const __nv_bfloat162*>(emb + (size_t)tok * d);
     const float2* p2 = reinterpret_cast<const float2*>(pos + (size_t)t * d);
     __half2* xo = reinterpret_cast<__half2*>(x + (size_t)b * d);
+    float s1 = 0.0f, s2 = 0.0f;
     for (int i = threadIdx.x; i < d / 2; i += blockDim.x) {
         const float2 a = __bfloat1622float2(e[i]);
         const float2 c = p2[i];
-        xo[i] = __floats2half2_rn(a.x + c.x, a.y + c.y);
+        const __half2 h = __floats2half2_rn(a.x + c.x, a.y + c.y);
+        xo[i] = h;
+        const float2 r = __half22float2(h);
+        s1 += r.x + r.y;
+        s2 += r.x * r.x + r.y * r.y;
+    }
+    if (stats == nullptr) return;
+    // folded LayerNorm (decoder.cu): the row's (sum, sum of squares) in slot 0 of the layout the residual GEMMs write
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = make_float2(s1, s2);
+    __syncthreads();
+    if (threadIdx.x < stats_parts) {
+        float2 v = make_float2(0.0f, 0.0f);
+        if (threadIdx.x == 0)
+            v = make_float2(s_part[0].x + s_part[1].x + s_part[2].x + s_part[3].x, s_part[0].y + s_part[1].y + s_part[2].y + s_part[3].y);
+        stats[(size_t)b * stats_parts + threadIdx.x] = v;
     }
 }
 
@@ -287,11 +309,11 @@ __global__ void __launch_bounds__(kSampleThreads) decode_sample_kernel(const Sam
 }  // namespace
 
 cudaError_t decode_embed_launch(const int* tokens, int tokens_ld, const int* step, const void* emb_bf16, const float* pos,
-                                void* x_f16, int batch, int d, int pdl, cudaStream_t stream) {
-    if (batch <= 0 || d % 2 != 0) return cudaErrorInvalidValue;
+                                void* x_f16, int batch, int d, int pdl, cudaStream_t stream, float2* stats, int stats_parts) {
+    if (batch <= 0 || d % 2 != 0 || (stats && (stats_parts < 1 || stats_parts > 128))) return cudaErrorInvalidValue;
     const __nv_bfloat16* emb = reinterpret_cast<const __nv_bfloat16*>(emb_bf16);
     __half* x = reinterpret_cast<__half*>(x_f16);
-    void* args[] = {&tokens, &tokens_ld, &step, &emb, &pos, &x, &d};
+    void* args[] = {&tokens, &tokens_ld, &step, &emb, &pos, &x, &d, &stats, &stats_parts};
     return launch_maybe_pdl(reinterpret_cast<const void*>(decode_embed_kernel), dim3(batch), dim3(128), 0, stream, args,
                             pdl != 0);
 }

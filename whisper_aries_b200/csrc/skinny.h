@@ -18,7 +18,13 @@ enum SkinnyEpilogue {
     SK_BIAS_GELU_BF16 = 1,   // out bf16 = gelu_erf(acc + bias)
     SK_BIAS_RESID_F16 = 2,   // out f16 = acc + bias + out (in place on the f16 residual stream)
     SK_LOGITS_F32 = 3,       // out f32 [B, ldo] = acc (no bias; N need not be a multiple of 128)
-    SK_COUNT = 4,
+    // LayerNorm FOLDED into the GEMM (any batch size; the algebra of the encoder's EPI_LN_*): the token-row operand is the
+    // f16 residual stream itself, W holds f16(gamma * W), and with the row statistics (mean, rstd) from the partial sums
+    // the producing SK_BIAS_RESID_F16 GEMM left in stats_in:  out = rstd * (acc - mean * c1[n]) + bias[n],
+    // c1[n] = sum_k f16(gamma_k W[n, k]), bias[n] = sum_k beta_k W[n, k] + b[n].  Both operands are f16 (kind::f16 MMA).
+    SK_LNF_BF16 = 4,         // out bf16
+    SK_LNF_GELU_BF16 = 5,    // out bf16 = gelu_erf(...)
+    SK_COUNT = 6,
 };
 
 struct SkinnyParams {
@@ -37,6 +43,13 @@ struct SkinnyParams {
     const void* ln_x;       // f16 [B, K]
     const float* ln_gamma;  // [K]
     const float* ln_beta;   // [K]
+    // Folded LayerNorm (SK_LNF_*): per-row partial sums [B, stats_parts] of (x, x^2) over ln_dim features, and c1 [N].
+    const float* c1;
+    const float2* stats_in;
+    int stats_parts, ln_dim;
+    // SK_BIAS_RESID_F16 only, optional: partial (sum, sum of squares) of the f16 values this launch stores, one slot
+    // per 128-feature tile: stats_out[b * gridDim.x + tile].  Needs splits > 1 (the cluster reduction path).
+    float2* stats_out;
 };
 
 int skinny_pick_splits(int N, int K, int sm_count);
@@ -77,8 +90,10 @@ cudaError_t decode_attention_launch(const DecAttnParams& p, cudaStream_t stream)
 
 // ------------------------------------------------------------------------------------------------ embedding / sampling
 // x f16 [B, d] = emb[tokens[b, *step]] (bf16 table, tied with the output projection) + pos[*step] (f32 table)
+// stats != NULL (folded LayerNorm): also stats[b, 0] = (sum, sum of squares) of the stored row, stats[b, 1 ..] = 0
 cudaError_t decode_embed_launch(const int* tokens, int tokens_ld, const int* step, const void* emb_bf16, const float* pos,
-                                void* x_f16, int batch, int d, int pdl, cudaStream_t stream);
+                                void* x_f16, int batch, int d, int pdl, cudaStream_t stream, float2* stats = nullptr,
+                                int stats_parts = 0);
 
 // y bf16 [rows, d] = LayerNorm(x f16 [rows, d]) * gamma + beta (eps 1e-5), griddepcontrol-aware (rows = sequences).
 cudaError_t decode_layernorm_launch(const void* x_f16, const float* gamma, const float* beta, void* y_bf16, int rows, int d,

@@ -68,22 +68,52 @@ __device__ __forceinline__ float load_resid(const SkinnyParams& p, int b, int n)
     return __half2float(reinterpret_cast<const __half*>(p.out)[(size_t)b * p.ldo + n]);
 }
 
+constexpr bool is_lnf(int epi) { return epi == SK_LNF_BF16 || epi == SK_LNF_GELU_BF16; }
+constexpr bool is_gelu(int epi) { return epi == SK_BIAS_GELU_BF16 || epi == SK_LNF_GELU_BF16; }
+
+// Row statistics of the folded LayerNorm: (-mean * rstd, rstd) from the producer's partial sums.
+struct RowStat {
+    float nm, rstd;
+};
 template <int EPI>
-__device__ __forceinline__ void store_one(const SkinnyParams& p, int b, int n, float v, float resid) {
+__device__ __forceinline__ RowStat row_stat(const SkinnyParams& p, int b) {
+    RowStat r{0.0f, 1.0f};
+    if (!is_lnf(EPI)) return r;
+    float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll 4
+    for (int k = 0; k < p.stats_parts; ++k) {
+        const float2 v = __ldcg(p.stats_in + (size_t)b * p.stats_parts + k);
+        s1 += v.x;
+        s2 += v.y;
+    }
+    const float inv_d = 1.0f / (float)p.ln_dim;
+    const float mean = s1 * inv_d;
+    r.rstd = rsqrtf(fmaxf(s2 * inv_d - mean * mean, 0.0f) + 1e-5f);
+    r.nm = -mean * r.rstd;
+    return r;
+}
+
+// Returns the value as stored (after rounding) for the residual epilogue's statistics, else the input.
+template <int EPI>
+__device__ __forceinline__ float store_one(const SkinnyParams& p, int b, int n, float v, float resid, RowStat rs) {
     const size_t at = (size_t)b * p.ldo + n;
     if (EPI == SK_LOGITS_F32) {
         reinterpret_cast<float*>(p.out)[at] = v;
-        return;
+        return v;
     }
-    v += __ldg(p.bias + n);
-    if (EPI == SK_BIAS_GELU_BF16) v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+    if (is_lnf(EPI)) v = fmaf(rs.rstd, v, fmaf(rs.nm, __ldg(p.c1 + n), __ldg(p.bias + n)));
+    else v += __ldg(p.bias + n);
+    if (is_gelu(EPI)) v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
     if (EPI == SK_BIAS_RESID_F16) {
         __half* o = reinterpret_cast<__half*>(p.out);
         v += resid;
-        o[at] = __float2half_rn(fminf(fmaxf(v, -65504.0f), 65504.0f));
+        const __half h = __float2half_rn(fminf(fmaxf(v, -65504.0f), 65504.0f));
+        o[at] = h;
+        return __half2float(h);
     } else {
         reinterpret_cast<__nv_bfloat16*>(p.out)[at] = __float2bfloat16_rn(v);
     }
+    return v;
 }
 
 // Four consecutive output features of one sequence (n % 4 == 0): vector loads / stores when the row pitch allows it.
@@ -102,17 +132,26 @@ __device__ __forceinline__ float4 load_resid4(const SkinnyParams& p, int b, int 
     return make_float4(r[0], r[1], r[2], r[3]);
 }
 
+// (returns the four values as stored, see store_one)
 template <int EPI>
-__device__ __forceinline__ void store_four(const SkinnyParams& p, int b, int n, float4 v, float4 resid) {
+__device__ __forceinline__ float4 store_four(const SkinnyParams& p, int b, int n, float4 v, float4 resid, RowStat rs) {
     if (n + 3 < p.N && (p.ldo & 3) == 0) {
         const size_t at = (size_t)b * p.ldo + n;
         if (EPI == SK_LOGITS_F32) {
             *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + at) = v;
-            return;
+            return v;
         }
         const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-        v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
-        if (EPI == SK_BIAS_GELU_BF16) {
+        if (is_lnf(EPI)) {
+            const float4 cc = __ldg(reinterpret_cast<const float4*>(p.c1 + n));
+            v.x = fmaf(rs.rstd, v.x, fmaf(rs.nm, cc.x, bb.x));
+            v.y = fmaf(rs.rstd, v.y, fmaf(rs.nm, cc.y, bb.y));
+            v.z = fmaf(rs.rstd, v.z, fmaf(rs.nm, cc.z, bb.z));
+            v.w = fmaf(rs.rstd, v.w, fmaf(rs.nm, cc.w, bb.w));
+        } else {
+            v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+        }
+        if (is_gelu(EPI)) {
             v.x = 0.5f * v.x * (1.0f + erff(v.x * 0.70710678118654752f));
             v.y = 0.5f * v.y * (1.0f + erff(v.y * 0.70710678118654752f));
             v.z = 0.5f * v.z * (1.0f + erff(v.z * 0.70710678118654752f));
@@ -126,17 +165,21 @@ __device__ __forceinline__ void store_four(const SkinnyParams& p, int b, int n, 
             q.x = *reinterpret_cast<const unsigned*>(&lo);
             q.y = *reinterpret_cast<const unsigned*>(&hi);
             *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.out) + at) = q;
+            const float2 flo = __half22float2(lo), fhi = __half22float2(hi);
+            return make_float4(flo.x, flo.y, fhi.x, fhi.y);
         } else {
             q.x = pack_bf16x2(v.x, v.y);
             q.y = pack_bf16x2(v.z, v.w);
             *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + at) = q;
         }
-        return;
+        return v;
     }
     const float vv[4] = {v.x, v.y, v.z, v.w}, rr[4] = {resid.x, resid.y, resid.z, resid.w};
+    float st[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
     for (int e = 0; e < 4; ++e)
-        if (n + e < p.N) store_one<EPI>(p, b, n + e, vv[e], rr[e]);
+        if (n + e < p.N) st[e] = store_one<EPI>(p, b, n + e, vv[e], rr[e], rs);
+    return make_float4(st[0], st[1], st[2], st[3]);
 }
 
 template <int EPI, int MODE>
@@ -218,7 +261,7 @@ skinny_gemm_tcgen05(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
         // -------------------------------------------------------------------- MMA issuer (convergent, elect-predicated)
         pdl_wait();
         pdl_trigger();
-        const uint32_t idesc = umma_idesc_bf16(BMW, (uint32_t)p.NB, false, false);
+        const uint32_t idesc = is_lnf(EPI) ? umma_idesc_f16(BMW, (uint32_t)p.NB) : umma_idesc_bf16(BMW, (uint32_t)p.NB, false, false);
         constexpr uint64_t desc_hi64 = umma_smem_desc_hi(16, 1024);
         constexpr uint32_t desc_hi = (uint32_t)(desc_hi64 >> 32);
         const uint32_t desc_lo0 = (uint32_t)(desc_hi64 & 0xFFFFFFFFu) | ((base >> 4) & 0x3FFF);
@@ -344,7 +387,7 @@ skinny_gemm_tcgen05(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const int b = c * 16 + j;
-                    if (b < p.B && n < p.N) store_one<EPI>(p, b, n, __uint_as_float(acc[j]), res[j]);
+                    if (b < p.B && n < p.N) store_one<EPI>(p, b, n, __uint_as_float(acc[j]), res[j], row_stat<EPI>(p, b));
                 }
             } else {
                 // the pipeline stages are free: every MMA of this CTA has retired (tfull)
@@ -378,6 +421,7 @@ skinny_gemm_tcgen05(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
                     r1 = load_resid4<EPI>(p, b, n);
                     if (has2) r2 = load_resid4<EPI>(p, b2, n);
                 }
+                const RowStat rs1 = row_stat<EPI>(p, b), rs2 = has2 ? row_stat<EPI>(p, b2) : RowStat{0.0f, 1.0f};
                 float4 v[kMaxSplits], w[kMaxSplits];
 #pragma unroll
                 for (int s = 0; s < kMaxSplits; ++s) {
@@ -390,9 +434,27 @@ skinny_gemm_tcgen05(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
                     sum.x += v[s].x; sum.y += v[s].y; sum.z += v[s].z; sum.w += v[s].w;
                     sum2.x += w[s].x; sum2.y += w[s].y; sum2.z += w[s].z; sum2.w += w[s].w;
                 }
+                float4 st1 = make_float4(0, 0, 0, 0), st2 = st1;
                 if (n < p.N) {
-                    store_four<EPI>(p, b, n, sum, r1);
-                    if (has2) store_four<EPI>(p, b2, n, sum2, r2);
+                    st1 = store_four<EPI>(p, b, n, sum, r1, rs1);
+                    if (has2) st2 = store_four<EPI>(p, b2, n, sum2, r2, rs2);
+                }
+                if (EPI == SK_BIAS_RESID_F16 && p.stats_out != nullptr) {
+                    // folded LayerNorm, producing side: (sum, sum of squares) of this tile's 128 stored values of rows
+                    // b and b2 -- the 32 lanes of the warp hold 4 features each (b, b2 and has2 are warp-uniform)
+                    float a1 = st1.x + st1.y + st1.z + st1.w, q1 = st1.x * st1.x + st1.y * st1.y + st1.z * st1.z + st1.w * st1.w;
+                    float a2 = st2.x + st2.y + st2.z + st2.w, q2 = st2.x * st2.x + st2.y * st2.y + st2.z * st2.z + st2.w * st2.w;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+                        q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+                        a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+                        q2 += __shfl_xor_sync(0xffffffffu, q2, o);
+                    }
+                    if (n4 == 0) {
+                        p.stats_out[(size_t)b * gridDim.x + blockIdx.x] = make_float2(a1, q1);
+                        if (has2) p.stats_out[(size_t)b2 * gridDim.x + blockIdx.x] = make_float2(a2, q2);
+                    }
                 }
             }
         }
@@ -485,6 +547,8 @@ cudaError_t skinny_init_device() {
     if ((e = set_smem<SK_BIAS_BF16>()) != cudaSuccess) return e;
     if ((e = set_smem<SK_BIAS_GELU_BF16>()) != cudaSuccess) return e;
     if ((e = set_smem<SK_BIAS_RESID_F16>()) != cudaSuccess) return e;
+    if ((e = set_smem<SK_LNF_BF16>()) != cudaSuccess) return e;
+    if ((e = set_smem<SK_LNF_GELU_BF16>()) != cudaSuccess) return e;
     return set_smem<SK_LOGITS_F32>();
 }
 
@@ -498,7 +562,12 @@ cudaError_t skinny_launch(int epi, const CUtensorMap& tw, const CUtensorMap& tx,
     if (p.ln_x && (p.B > kLnMaxB || p.NB != 16 || p.K > kLnMaxJ * 256 || kps > kStagesLn || !p.ln_gamma || !p.ln_beta ||
                    epi == SK_BIAS_RESID_F16))
         return cudaErrorInvalidValue;
+    const bool lnf = epi == SK_LNF_BF16 || epi == SK_LNF_GELU_BF16;
+    if (lnf && (p.ln_x || !p.c1 || !p.stats_in || p.stats_parts < 1 || p.ln_dim < 1 || !p.bias)) return cudaErrorInvalidValue;
+    if (p.stats_out && (epi != SK_BIAS_RESID_F16 || p.splits < 2)) return cudaErrorInvalidValue;
     switch (epi) {
+        case SK_LNF_BF16: return launch_epi<SK_LNF_BF16>(tw, tx, p, stream);
+        case SK_LNF_GELU_BF16: return launch_epi<SK_LNF_GELU_BF16>(tw, tx, p, stream);
         case SK_BIAS_BF16: return launch_epi<SK_BIAS_BF16>(tw, tx, p, stream);
         case SK_BIAS_GELU_BF16: return launch_epi<SK_BIAS_GELU_BF16>(tw, tx, p, stream);
         case SK_BIAS_RESID_F16: return launch_epi<SK_BIAS_RESID_F16>(tw, tx, p, stream);
