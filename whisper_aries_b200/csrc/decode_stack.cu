@@ -69,7 +69,7 @@ constexpr int kRedBytes = 2 * 8 * 128 * 4;           // two buffers of [8 warps]
 constexpr int kMaxB = 8;
 constexpr int kLnJ = 5;                              // 16-byte chunks of a row per lane: d <= 1280
 constexpr int kSmemLimit = 232448;
-constexpr int kMaxHeads = 20;                          // Whisper large: the context staging keeps 5 items per thread
+constexpr int kMaxHeads = 32;                        // head_dim 64: d <= 2048 (the LayerNorm staging limits d to 1280 anyway)
 
 struct Ctx {
     uint64_t *full, *empty;
