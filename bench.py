@@ -655,18 +655,28 @@ def main() -> int:
     e2e = None
     if not args.no_e2e:
         sched = ChunkScheduler([gpu_worker(model, micro_batch=args.micro_batch)])
+        # Two pinned gather buffers: step i+1 is submitted before step i's rows are awaited (ChunkScheduler.submit), so
+        # the download of step i overlaps the kernels of step i+1 -- every step still uploads its PCM from pinned host
+        # memory and its result is read on the host (Job.result()) inside the timed region.
+        out_hosts = [out_host, torch.empty_like(out_host).pin_memory()]
 
-        def step_e2e():
-            res = sched.run(pcm_host, out_host)
-            if not all(r.success for r in res):
-                raise RuntimeError(f"e2e step failed: {[r.error for r in res if not r.success]}")
+        def run_e2e(n_steps: int) -> None:
+            jobs = []
+            for i in range(n_steps):
+                jobs.append(sched.submit(pcm_host, out_hosts[i & 1]))
+                if len(jobs) > 1:
+                    res = jobs.pop(0).result()
+                    if not all(r.success for r in res):
+                        raise RuntimeError(f"e2e step failed: {[r.error for r in res if not r.success]}")
+            for j in jobs:
+                res = j.result()
+                if not all(r.success for r in res):
+                    raise RuntimeError(f"e2e step failed: {[r.error for r in res if not r.success]}")
 
-        for _ in range(max(1, min(args.warmup, 2))):
-            step_e2e()
+        run_e2e(max(1, min(args.warmup, 2)))
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            step_e2e()
+        run_e2e(args.steps)
         torch.cuda.synchronize(dev)
         dt = time.perf_counter() - t0
         t = torch.tensor([dt], dtype=torch.float64, device=dev)
@@ -674,12 +684,11 @@ def main() -> int:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = {"value": world * B * WINDOW_SECONDS * args.steps / float(t.item()), "unit": UNIT,
                "h2d_bytes_per_step": int(pcm_host.numel() * 4), "d2h_bytes_per_step": int(out_host.numel() * 2),
-               "api": "ChunkScheduler(gpu_worker(WhisperModel)).run(pinned pcm, pinned out)",
+               "api": "ChunkScheduler(gpu_worker(WhisperModel)).submit(pinned pcm, pinned out) / Job.result(), two steps in flight",
                "micro_batch": args.micro_batch,
-               "pipeline": ("one micro-batch per step at this setting: H2D, kernels and D2H run back to back inside a step "
-                            "(measured best: 16 / 32 / 64 windows per micro-batch give 12 150 / 12 415 / 12 568 audio-s/s); the "
-                            "double-buffered H2D / compute / D2H pipeline is what config4 / config5 below exercise"
-                            if args.micro_batch >= B else "double-buffered: H2D, kernels and D2H of consecutive micro-batches overlap")}
+               "pipeline": "uploads, kernels and downloads on three streams, double-buffered across micro-batches and "
+                           "across steps: the download of step i overlaps the kernels of step i+1; every step's rows are "
+                           "on the host when its Job.result() returns, inside the timed region"}
 
     # Rank 0 goes on to the in-process multi-GPU jobs (configs 4 / 5) and needs every GPU of the box to itself: the other
     # ranks drop their replicas and park on the rendezvous store (a host-side wait: an NCCL barrier would spin on their GPUs).
@@ -764,6 +773,8 @@ def main() -> int:
 
     # ---------------------------------------------------------------- outside every timed region: parity + widened jobs
     del pcm_dev, out_dev, out_host, pcm_host
+    if not args.no_e2e:
+        del out_hosts
     torch.cuda.empty_cache()
     extras = {}
     if not args.no_extras:

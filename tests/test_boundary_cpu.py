@@ -5,6 +5,8 @@ import dataclasses
 import os
 import re
 
+import time
+
 import numpy as np
 import pytest
 
@@ -139,6 +141,60 @@ def test_scheduler_with_fake_devices_keeps_order_and_isolates_failures():
     # more devices than windows: trailing shards are empty and succeed
     res = ChunkScheduler([make(i) for i in range(4)]).run(windows[:2], np.zeros((2, 2), np.float32))
     assert [r.n_windows for r in res] == [1, 1, 0, 0] and all(r.success for r in res)
+
+
+def test_submit_pipelines_two_jobs_through_two_phase_workers():
+    """``submit`` returns at once and ``Job.result()`` gathers; a worker exposing ``enqueue(...) -> finish()`` (what
+    ``gpu_worker`` does with CUDA streams) gets the SECOND job enqueued before the first one is finished, finishes them
+    in order, and a failure in either phase lands in that job's ChunkResult only."""
+    import threading
+    from whisper_aries_b200 import Job
+    events, gate = [], threading.Event()
+
+    def make(worker_id):
+        def enqueue(w, start, stop, o, lengths=None):
+            events.append(("enqueue", int(w[0, 0]), worker_id))
+            if w[0, 0] == 300:
+                raise RuntimeError("bad input")
+
+            def finish():
+                if w[0, 0] == 100:
+                    gate.wait(5.0)                       # job A stays in flight until job B has been enqueued
+                if w[0, 0] == 400:
+                    raise RuntimeError("device lost in flight")
+                o[start:stop] = w[start:stop] + 1
+                events.append(("finish", int(w[0, 0]), worker_id))
+            return finish
+
+        def run(w, start, stop, o, lengths=None):
+            enqueue(w, start, stop, o, lengths=lengths)()
+        run.enqueue = enqueue
+        return run
+
+    sched = ChunkScheduler([make(0)])
+    a, b = np.full((2, 1), 100.0, np.float32), np.full((2, 1), 200.0, np.float32)
+    oa, ob = np.zeros_like(a), np.zeros_like(b)
+    ja = sched.submit(a, oa)
+    jb = sched.submit(b, ob)
+    assert isinstance(ja, Job)
+    for _ in range(200):                                 # the worker thread enqueues B while A is still unfinished
+        if ("enqueue", 200, 0) in events:
+            break
+        time.sleep(0.01)
+    assert ("enqueue", 200, 0) in events and ("finish", 100, 0) not in events
+    gate.set()
+    assert all(r.success for r in ja.result()) and all(r.success for r in jb.result())
+    assert (oa == 101).all() and (ob == 201).all()
+    assert events.index(("finish", 100, 0)) < events.index(("finish", 200, 0))
+    assert ja.result() is ja.result()                    # gathered once
+    # failures: at enqueue time and in flight
+    c, d_ = np.full((1, 1), 300.0, np.float32), np.full((1, 1), 400.0, np.float32)
+    rc = sched.submit(c, np.zeros_like(c)).result()
+    rd = sched.submit(d_, np.zeros_like(d_)).result()
+    assert not rc[0].success and "bad input" in rc[0].error
+    assert not rd[0].success and "in flight" in rd[0].error
+    assert all(r.success for r in sched.run(b, ob))      # the worker thread survives both
+    sched.close()
 
 
 def test_reference_chunk_plan_and_zero_copy_windows():

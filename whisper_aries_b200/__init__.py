@@ -6,10 +6,10 @@ from . import ct2_model, vad
 from .decoder import WhisperDecoder, WhisperGenerationResult
 from .encoder import WhisperEncoder, WhisperModel, pcm_s16_to_f32
 from .feature_extractor import FeatureExtractor
-from .scheduler import (ChunkResult, ChunkScheduler, ChunkWork, chunk_windows, gpu_transcribe_worker, gpu_worker,
+from .scheduler import (ChunkResult, ChunkScheduler, ChunkWork, Job, chunk_windows, gpu_transcribe_worker, gpu_worker,
                         partition_windows, plan_reference_chunks)
 from .synthetic import DEC_SHAPES, SHAPES, DecoderShape, EncoderShape, WhisperTokens
 
-__all__ = ["FeatureExtractor", "WhisperEncoder", "WhisperModel", "ChunkScheduler", "ChunkWork", "ChunkResult",
+__all__ = ["FeatureExtractor", "WhisperEncoder", "WhisperModel", "ChunkScheduler", "ChunkWork", "ChunkResult", "Job",
            "partition_windows", "plan_reference_chunks", "chunk_windows", "gpu_worker", "gpu_transcribe_worker", "pcm_s16_to_f32", "SHAPES", "EncoderShape", "ct2_model", "vad", "WhisperDecoder", "WhisperGenerationResult", "DEC_SHAPES",
            "DecoderShape", "WhisperTokens"]

@@ -15,6 +15,7 @@ Two launch styles share the partition function:
   * one process per GPU under torchrun      -> ``partition_windows(n, world_size)[rank]`` (bench.py --gpus N)."""
 from __future__ import annotations
 
+import collections
 import queue
 import threading
 import time
@@ -176,24 +177,53 @@ class ChunkScheduler:
     # ------------------------------------------------------------------ worker threads
     def _loop(self, worker_id: int, inbox: "queue.Queue") -> None:
         worker = self.workers[worker_id]
-        while True:
-            job = inbox.get()
-            if job is _STOP:
-                return
-            work, windows, out, lengths, results = job
-            res = ChunkResult(work.chunk_id, work.start, work.stop, worker_id)
-            t0 = time.perf_counter()
+        enqueue = getattr(worker, "enqueue", None)       # two-phase worker: enqueue(...) -> finish()  (see gpu_worker)
+        pending: "collections.deque" = collections.deque()
+
+        def complete_oldest() -> None:
+            res, results, finish, t0 = pending.popleft()
             try:
-                if work.stop > work.start:
-                    if lengths is None:
-                        worker(windows, work.start, work.stop, out)
-                    else:
-                        worker(windows, work.start, work.stop, out, lengths=lengths)
-            except Exception as exc:                      # one bad shard must not sink the call (ref: :355-365)
+                finish()
+            except Exception as exc:
                 res.success = False
                 res.error = f"{type(exc).__name__}: {exc}"
             res.processing_time = time.perf_counter() - t0
             results.put(res)
+
+        while True:
+            # With work in flight only LOOK for the next item: if one is already queued (a pipelined ``submit``) its H2D
+            # and kernels are enqueued behind the current item's before this thread blocks on the current item's D2H.
+            if pending:
+                try:
+                    job = inbox.get_nowait()
+                except queue.Empty:
+                    job = None
+            else:
+                job = inbox.get()
+            if job is _STOP:
+                while pending:
+                    complete_oldest()
+                return
+            if job is not None:
+                work, windows, out, lengths, results = job
+                res = ChunkResult(work.chunk_id, work.start, work.stop, worker_id)
+                t0 = time.perf_counter()
+                try:
+                    if work.stop > work.start:
+                        kw = {} if lengths is None else {"lengths": lengths}
+                        if enqueue is not None:
+                            pending.append((res, results, enqueue(windows, work.start, work.stop, out, **kw), t0))
+                            res = None
+                        else:
+                            worker(windows, work.start, work.stop, out, **kw)
+                except Exception as exc:                  # one bad shard must not sink the call (ref: :355-365)
+                    res.success = False
+                    res.error = f"{type(exc).__name__}: {exc}"
+                if res is not None:
+                    res.processing_time = time.perf_counter() - t0
+                    results.put(res)
+            if pending and (job is None or len(pending) > 1):
+                complete_oldest()
 
     def _ensure_threads(self) -> None:
         if self._closed:
@@ -240,10 +270,11 @@ class ChunkScheduler:
         step = self.chunk or max(1, -(-n_windows // (4 * len(self.workers))))
         return [ChunkWork(i, a, min(a + step, n_windows), -1) for i, a in enumerate(range(0, n_windows, step))]
 
-    def run(self, windows, out, lengths=None) -> list[ChunkResult]:
-        """Process every window of ``windows`` into the rows of ``out`` (one preallocated, ideally pinned, gather
-        buffer: order is restored by construction).  ``lengths`` = valid samples per window (``chunk_windows(...,
-        return_lengths=True)``); ``None`` means every window is full."""
+    def submit(self, windows, out, lengths=None) -> "Job":
+        """Enqueue a job and return at once; ``Job.result()`` gathers it.  Two jobs may be in flight per scheduler: with
+        two-phase workers (``gpu_worker``) the second job's H2D and kernels queue up behind the first's on the device,
+        so the first job's D2H overlaps the second's compute -- across calls, not only across micro-batches.  The caller
+        keeps ``windows`` and ``out`` of a job alive and untouched until its ``result()`` has returned."""
         n = int(windows.shape[0])
         if lengths is not None and len(lengths) != n:
             raise ValueError("lengths must hold one entry per window")
@@ -254,24 +285,47 @@ class ChunkScheduler:
             for w in works:
                 inbox = self._inboxes[w.worker_id if self.policy == "static" else 0]
                 inbox.put((w, windows, out, lengths, results))
-            got: dict[int, ChunkResult] = {}
-            while len(got) < len(works):
-                try:
-                    r = results.get(timeout=self.result_timeout)
-                    got[r.chunk_id] = r
-                except queue.Empty:
-                    if not any(t.is_alive() for t in self._threads):
-                        break                              # ref: :483-490 "All workers stopped, breaking..."
-            for w in works:
-                if w.chunk_id not in got:
-                    got[w.chunk_id] = ChunkResult(w.chunk_id, w.start, w.stop, w.worker_id, success=False,
-                                                  error="no result: every worker thread has stopped")
-            self.results = [got[w.chunk_id] for w in works]
-            return self.results
+        return Job(self, works, results)
+
+    def _gather(self, works, results) -> list[ChunkResult]:
+        got: dict[int, ChunkResult] = {}
+        while len(got) < len(works):
+            try:
+                r = results.get(timeout=self.result_timeout)
+                got[r.chunk_id] = r
+            except queue.Empty:
+                if not any(t.is_alive() for t in self._threads):
+                    break                                  # ref: :483-490 "All workers stopped, breaking..."
+        for w in works:
+            if w.chunk_id not in got:
+                got[w.chunk_id] = ChunkResult(w.chunk_id, w.start, w.stop, w.worker_id, success=False,
+                                              error="no result: every worker thread has stopped")
+        self.results = [got[w.chunk_id] for w in works]
+        return self.results
+
+    def run(self, windows, out, lengths=None) -> list[ChunkResult]:
+        """Process every window of ``windows`` into the rows of ``out`` (one preallocated, ideally pinned, gather
+        buffer: order is restored by construction).  ``lengths`` = valid samples per window (``chunk_windows(...,
+        return_lengths=True)``); ``None`` means every window is full.  Returns when every row is on the host."""
+        return self.submit(windows, out, lengths).result()
+
+
+class Job:
+    """A submitted job (``ChunkScheduler.submit``): ``result()`` blocks until every work item has reported and returns
+    the ``ChunkResult`` list in window order (the same collector and time-out as ``run``)."""
+
+    def __init__(self, scheduler: ChunkScheduler, works, results):
+        self._scheduler, self._works, self._results, self._done = scheduler, works, results, None
+
+    def result(self) -> list[ChunkResult]:
+        if self._done is None:
+            self._done = self._scheduler._gather(self._works, self._results)
+        return self._done
 
 
 def gpu_worker(model, micro_batch: int = 16) -> Worker:
-    """Worker for one GPU: pinned staging, H2D on a side stream double-buffered against compute, fused
+    """Worker for one GPU: uploads, kernels and downloads on three streams, double-buffered (the upload of micro-batch
+    k+1 and the download of k-1 overlap the kernels of k, within a call and -- through ``enqueue`` -- across calls), fused
     PCM -> mel -> encoder on the device, D2H of the bf16 states into the caller's (pinned) output rows.
     ``windows`` may be float32 or int16 (ffmpeg's pcm_s16le, ref: utils.py:116): int16 halves the H2D bytes and is
     converted on the GPU."""
@@ -281,48 +335,68 @@ def gpu_worker(model, micro_batch: int = 16) -> Worker:
     d, t = model.shape.d_model, model.shape.n_ctx
     state = {}
 
-    def run(windows, start: int, stop: int, out, lengths=None) -> None:
+    def enqueue(windows, start: int, stop: int, out, lengths=None):
+        """Enqueue H2D, kernels and D2H of windows [start, stop) and return ``finish()``, which blocks until the rows are
+        on the host.  Micro-batches alternate between two device buffer pairs ACROSS calls, so a second call enqueued
+        before the first is finished overlaps with it exactly as consecutive micro-batches of one call do."""
         torch.cuda.set_device(dev)
         n_s = int(windows.shape[1])
         wt = windows if isinstance(windows, torch.Tensor) else torch.from_numpy(windows)
         if wt.dtype not in (torch.float32, torch.int16):
             raise ValueError("windows must be float32 or int16 PCM")
         if "bufs" not in state or state["n_s"] != n_s or state["dtype"] != wt.dtype:
+            if "comp" in state:                           # a new shape: nothing of the old one may still be in flight
+                for name in ("h2d", "comp", "d2h"):
+                    state[name].synchronize()
             state["n_s"], state["dtype"] = n_s, wt.dtype
             state["bufs"] = [torch.empty((micro_batch, n_s), dtype=wt.dtype, device=dev) for _ in range(2)]
             state["outs"] = [torch.empty((micro_batch, t, d), dtype=torch.bfloat16, device=dev) for _ in range(2)]
-            state["copy"] = torch.cuda.Stream(dev)
+            # one stream per direction: on a shared copy stream the upload of micro-batch k+1 queues up BEHIND the
+            # download of micro-batch k, which waits for k's kernels -- nothing would overlap (round 2 finding)
+            state["h2d"] = torch.cuda.Stream(dev)
             state["comp"] = torch.cuda.Stream(dev)
+            state["d2h"] = torch.cuda.Stream(dev)
             state["h2d_done"] = [torch.cuda.Event() for _ in range(2)]
             state["comp_done"] = [torch.cuda.Event() for _ in range(2)]
             state["d2h_done"] = [torch.cuda.Event() for _ in range(2)]
-        copy, comp = state["copy"], state["comp"]
+            state["k"] = 0                                # micro-batches enqueued so far, over all calls
+        h2d, comp, d2h = state["h2d"], state["comp"], state["d2h"]
         ot = out if isinstance(out, torch.Tensor) else torch.from_numpy(out)
         if ot.dtype != torch.bfloat16:
             ot = ot.view(torch.bfloat16)
-        steps = list(range(start, stop, micro_batch))
-        for k, s in enumerate(steps):
+        for s in range(start, stop, micro_batch):
             e = min(s + micro_batch, stop)
+            k = state["k"]
+            state["k"] = k + 1
             i = k & 1
-            with torch.cuda.stream(copy):
+            with torch.cuda.stream(h2d):
                 if k >= 2:
-                    copy.wait_event(state["comp_done"][i])      # buffer i is free once step k-2 consumed it
+                    h2d.wait_event(state["comp_done"][i])       # buffer i is free once micro-batch k-2 consumed it
                 state["bufs"][i][: e - s].copy_(wt[s:e], non_blocking=True)
-                state["h2d_done"][i].record(copy)
+                state["h2d_done"][i].record(h2d)
             with torch.cuda.stream(comp):
                 comp.wait_event(state["h2d_done"][i])
                 if k >= 2:
-                    comp.wait_event(state["d2h_done"][i])       # out buffer i drained by step k-2's D2H
+                    comp.wait_event(state["d2h_done"][i])       # out buffer i drained by micro-batch k-2's D2H
                 for a, b, n in _length_runs(lengths, s, e, n_s):      # a ragged tail runs with its true length
                     model.encode_audio(state["bufs"][i][a - s: b - s, :n], out=state["outs"][i][a - s: b - s])
                 state["comp_done"][i].record(comp)
-            with torch.cuda.stream(copy):
-                copy.wait_event(state["comp_done"][i])
+            with torch.cuda.stream(d2h):
+                d2h.wait_event(state["comp_done"][i])
                 ot[s:e].copy_(state["outs"][i][: e - s], non_blocking=True)
-                state["d2h_done"][i].record(copy)
-        copy.synchronize()
-        comp.synchronize()
+                state["d2h_done"][i].record(d2h)
+        done = torch.cuda.Event()
+        done.record(d2h)                                  # downloads are FIFO on their stream: this covers the whole call
 
+        def finish() -> None:
+            done.synchronize()
+
+        return finish
+
+    def run(windows, start: int, stop: int, out, lengths=None) -> None:
+        enqueue(windows, start, stop, out, lengths=lengths)()
+
+    run.enqueue = enqueue
     return run
 
 
